@@ -1,0 +1,158 @@
+/*
+ * neurite_b200.h -- C ABI of libneurite_b200.so (hand-written CUDA for sm_100a).
+ *
+ * The reference (adalca/neurite @ 7c4b05e) has no FFI: its extension boundary is python
+ * callables / Keras layers over TensorFlow ops.  Each entry point below
+ * replaces the TensorFlow op sequence of the cited reference function; the python package
+ * neurite_b200 binds them with ctypes and re-exposes the reference signatures
+ * (see INTEGRATION.md for the binding a maintainer would add on the reference side).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the ABI.
+ *   - every device pointer is caller-owned, contiguous, channels-last ([batch,*spatial,C]),
+ *     fp32 (int32 where stated); inputs are const; no entry point allocates or frees
+ *     device memory, and none synchronises the device.
+ *   - `stream` is a cudaStream_t (CUstream) passed as void*; work is enqueued on it.
+ *   - return value: NRT_OK or a negative nrt_status; nrt_last_error_string() gives the
+ *     thread-local detail.  Nothing throws across the ABI.
+ *   - index arithmetic follows the reference: row-major flat index (utils.py:1068-1082).
+ *     Outputs with more than 2^31-1 elements per batch item are rejected (NRT_E_SIZE).
+ */
+#ifndef NEURITE_B200_H_
+#define NEURITE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NRT_API __attribute__((visibility("default")))
+#else
+#define NRT_API
+#endif
+
+typedef enum {
+  NRT_OK = 0,
+  NRT_E_ARG = -1,     /* bad argument (null pointer, rank, method, shape)              */
+  NRT_E_SIZE = -2,    /* size outside what the kernels index (int32 per batch item)    */
+  NRT_E_LAUNCH = -3,  /* CUDA launch / runtime error (string has cudaGetErrorString)   */
+  NRT_E_ALIGN = -4,   /* pointer not aligned as the entry point requires               */
+  NRT_E_NODEV = -5    /* no usable sm_100 device / driver                              */
+} nrt_status;
+
+enum { NRT_LINEAR = 0, NRT_NEAREST = 1 };
+enum { NRT_ACT_LINEAR = 0, NRT_ACT_RELU = 1, NRT_ACT_SIGMOID = 2, NRT_ACT_TANH = 3 };
+
+NRT_API int nrt_version(void);
+NRT_API const char* nrt_last_error_string(void);
+NRT_API const char* nrt_status_string(int status);
+
+/* ---------------------------------------------------------------------------------------
+ * interpn -- replaces neurite/tf/utils/utils.py:73-220 (interpn).
+ *   vol  [S_0..S_{D-1}, C]   loc [n_out, D]   out [n_out, C]      D in 1..3
+ *   method NRT_LINEAR: clip / floor / 2^D-corner gather in itertools.product order with
+ *   weights ((w0*w1)*w2), separate mul and add roundings (utils.py:139-191);
+ *   NRT_NEAREST: int32(round_half_even(loc)) THEN clip (utils.py:196-197).
+ *   has_fill: out = out*(!oob) + oob*fill with oob on the UNCLIPPED loc, strict (utils.py:206-213).
+ * ------------------------------------------------------------------------------------- */
+NRT_API int nrt_interpn_f32(const float* vol, const int32_t* vol_shape, int D, int C,
+                    const float* loc, int64_t n_out, int method, int has_fill, float fill,
+                    float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * warp -- replaces voxelmorph.layers.SpatialTransformer on a dense shift (call sites
+ * neurite/tf/models.py:806-807, 1157-1159): out[b] = interpn(vol[b], ndgrid + flow[b]).
+ * The identity grid is generated in registers (no loc tensor).
+ *   vol  [B, src_n0, S_1.., C]  the planes [src_z0, src_z0+src_n0) of a volume whose full
+ *                               extent along spatial axis 0 is full_s0 (slab sharding;
+ *                               pass src_z0=0, src_n0=full_s0 for a whole volume)
+ *   flow [B, out_n0, S_1.., D]  shifts for output planes [out_z0, out_z0+out_n0)
+ *   out  [B, out_n0, S_1.., C]
+ *   shape = {full_s0, S_1, S_2} (D entries).  Coordinates are clipped against the FULL
+ *   volume; a corner that falls outside the resident source planes sets *err_flag (device
+ *   int32, may be null) and reads the nearest resident plane.
+ *   halo: expected max |flow| in voxels (tiling hint for the shared-memory path only;
+ *   results do not depend on it).  <=0 selects the default (3).
+ * ------------------------------------------------------------------------------------- */
+NRT_API int nrt_warp_f32(const float* vol, const float* flow, float* out, int B,
+                 const int32_t* shape, int D, int C, int method, int has_fill, float fill,
+                 int src_z0, int src_n0, int out_z0, int out_n0, int halo,
+                 int32_t* err_flag, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * resize -- replaces neurite/tf/utils/utils.py:223-265 (resize/zoom) and the per-batch
+ * map of neurite/tf/layers.py:154-181 (Resize.call).  Sample positions come from an
+ * in-kernel fp32 linspace(0, S_d-1, M_d) (endpoints exact, interior delta*i), no grid tensor.
+ *   vol [B, S.., C] -> out [B, M.., C];  out planes [out_z0, out_z0+out_n0) of axis 0 are
+ *   produced (slab sharding; out points at the first produced plane).
+ * ------------------------------------------------------------------------------------- */
+NRT_API int nrt_resize_f32(const float* vol, float* out, int B, const int32_t* in_shape,
+                   const int32_t* out_shape, int D, int C, int method,
+                   int out_z0, int out_n0, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Dice -- replaces neurite/tf/metrics.py:415-482 (Dice.dice) after batch_channel_flatten.
+ *   y_true, y_pred [B, V, L] fp32.  One pass produces sums[b,l,{0,1,2}] =
+ *   {sum t*p, sum t*t, sum p*p} over voxels [v0, v0+nv) of every batch item (voxel-range
+ *   sharding: all-reduce `sums` across ranks, then finalize), and ORs bit0 into *flag if
+ *   any element of t or p is outside [0,1] (or NaN) when check_limits != 0
+ *   (metrics.py:439-444).  workspace: device scratch of nrt_dice_workspace_bytes(B,L).
+ *   normalize != 0 divides each voxel's labels by their sum first (divide_no_nan, :434-436).
+ * ------------------------------------------------------------------------------------- */
+NRT_API int64_t nrt_dice_workspace_bytes(int B, int L);
+NRT_API int nrt_dice_sums_f32(const float* y_true, const float* y_pred, int B, int64_t V, int L,
+                      int64_t v0, int64_t nv, int normalize, int check_limits,
+                      float* sums, int32_t* flag, void* workspace, int64_t workspace_bytes,
+                      void* stream);
+/* hard Dice on label maps (metrics.py:450-468 without materialising one-hot):
+ *   t_lab, p_lab [B, V] int32; sums as above (counts).  Labels outside [0,L) count nowhere. */
+NRT_API int nrt_dice_label_sums_i32(const int32_t* t_lab, const int32_t* p_lab, int B, int64_t V, int L,
+                            int64_t v0, int64_t nv, float* sums, void* workspace,
+                            int64_t workspace_bytes, void* stream);
+/* argmax over the last axis (first max wins, like tf.argmax): x [n, L] -> idx [n] int32 */
+NRT_API int nrt_argmax_f32(const float* x, int64_t n, int L, int32_t* idx, void* stream);
+/* dice[b,l] = laplace>0 ? (2*tp+eps)/(tt+pp+eps) : divide_no_nan(2*tp, tt+pp)  (:476-482) */
+NRT_API int nrt_dice_finalize_f32(const float* sums, int B, int L, float laplace, float* dice,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Categorical cross-entropy -- replaces neurite/tf/metrics.py:640-650 plus the Keras
+ * CategoricalCrossentropy arithmetic underneath (third party): t *= w_label;
+ * [label smoothing]; p /= sum_c p; p = clip(p, 1e-7, 1-1e-7); l = -sum_c t*log p
+ * (from_logits: l = -sum_c t*log_softmax(p)); l *= sample_weight.
+ *   y_true, y_pred [n, C]; label_w [C] or null; sample_w [n] or null;
+ *   per_elem [n] or null (reduction 'none'); sum_out [1] (fp32 sum of l over the n rows;
+ *   the caller divides by the global n for 'sum_over_batch_size').
+ *   workspace: nrt_cce_workspace_bytes().
+ * ------------------------------------------------------------------------------------- */
+NRT_API int64_t nrt_cce_workspace_bytes(void);
+NRT_API int nrt_cce_f32(const float* y_true, const float* y_pred, const float* label_w,
+                const float* sample_w, int64_t n, int C, int from_logits, float label_smoothing,
+                float* per_elem, float* sum_out, void* workspace, int64_t workspace_bytes,
+                void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * LocallyConnected3D, implementation 1 -- replaces neurite/tf/layers.py:1072-1102 (call)
+ * and :1126-1197 (local_conv): out[b,p,f] = act(sum_j patch[b,p,j]*kernel[p,j,f] + bias[p,f]).
+ *   x      [B, I0, I1, I2, Cin]  (channels-last storage)
+ *   kernel [P, F, Cout], P = O0*O1*O2 row-major, F = k0*k1*k2*Cin (layers.py:974-977)
+ *   bias   [O0, O1, O2, Cout] or null (layers.py:1034-1040)
+ *   out    [B, p_count, Cout] for output positions [p0, p0+p_count) (position sharding:
+ *          kernel/bias/out point at position p0 of the rank's shard)
+ *   feature_order 0: j = ((i0*k1+i1)*k2+i2)*Cin + c   (data_format channels_last)
+ *                 1: j = ((c*k0+i0)*k1+i1)*k2+i2     (kernel trained channels_first)
+ *   'valid' padding only (layers.py:934-936).
+ * ------------------------------------------------------------------------------------- */
+NRT_API int nrt_lc3d_fwd_f32(const float* x, const float* kernel, const float* bias, float* out,
+                     int B, const int32_t* in_shape, int Cin, int Cout,
+                     const int32_t* ksize, const int32_t* strides, int feature_order,
+                     int activation, int64_t p0, int64_t p_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEURITE_B200_H_ */

@@ -1,0 +1,260 @@
+// nrt_lc3d.cu -- LocallyConnected3D (implementation 1) forward for sm_100a.
+// Reference: neurite/tf/layers.py:1126-1197 (local_conv), :1098-1101 (bias, activation).
+//
+// The layer is a weight STREAM: every output position owns a private F x Cout block
+// (cfg 4: 432 x 16 fp32 = 27,648 B; 238,328 positions = 6.59 GB) that is used exactly once
+// per forward pass, against a 16.8 MB input that lives in L2.  Arithmetic intensity is
+// 0.5*B flop/byte, so the kernel is HBM-bound for any realistic batch and the design goal
+// is to keep >= ~40 KB of weight loads in flight per SM.
+//
+//   lc3d_stream_kernel : persistent CTAs; a producer thread streams whole per-position
+//       weight blocks into a shared-memory ring with cp.async.bulk (TMA 1-D bulk copy)
+//       completing on mbarriers; 8 consumer warps contract a staged block against the
+//       position's input patch (gathered from L2 into registers through a shared index
+//       table) and release the slot.  One warp owns one position; lanes own fixed
+//       4-wide output-channel quads so no weight is read twice.
+//   lc3d_generic_kernel: one thread per (b, p, f) -- any Cout / F, used when the fast
+//       path's divisibility requirements do not hold.
+#include "nrt_common.cuh"
+
+namespace nrt {
+
+struct LcGeo {
+  int B;
+  int I[3];        // input spatial extent
+  int O[3];        // output spatial extent (full layer)
+  int K[3];
+  int St[3];
+  int Cin, Cout, F;
+  int feature_order;
+  int activation;
+  int64_t p0, pn;  // this call's output positions [p0, p0+pn)
+  int64_t P;       // O0*O1*O2
+  int64_t x_batch; // elements per batch item of x
+};
+
+__device__ __forceinline__ float activate(float v, int act) {
+  switch (act) {
+    case NRT_ACT_RELU: return fmaxf(v, 0.f);
+    case NRT_ACT_SIGMOID: return __fdiv_rn(1.f, 1.f + expf(-v));
+    case NRT_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+// offset of patch feature j inside the input, relative to the patch origin voxel
+__device__ __forceinline__ int feature_offset(const LcGeo& g, int j) {
+  int i0, i1, i2, c;
+  if (g.feature_order == 0) {            // j = ((i0*k1+i1)*k2+i2)*Cin + c
+    c = j % g.Cin; j /= g.Cin;
+    i2 = j % g.K[2]; j /= g.K[2];
+    i1 = j % g.K[1]; i0 = j / g.K[1];
+  } else {                               // j = ((c*k0+i0)*k1+i1)*k2+i2
+    i2 = j % g.K[2]; j /= g.K[2];
+    i1 = j % g.K[1]; j /= g.K[1];
+    i0 = j % g.K[0]; c = j / g.K[0];
+  }
+  return ((i0 * g.I[1] + i1) * g.I[2] + i2) * g.Cin + c;
+}
+
+__device__ __forceinline__ int64_t patch_origin(const LcGeo& g, int64_t p) {
+  const int o2 = (int)(p % g.O[2]); p /= g.O[2];
+  const int o1 = (int)(p % g.O[1]);
+  const int o0 = (int)(p / g.O[1]);
+  return (((int64_t)o0 * g.St[0] * g.I[1] + (int64_t)o1 * g.St[1]) * g.I[2] + (int64_t)o2 * g.St[2]) * g.Cin;
+}
+
+// ---------------------------------------------------------------------------------------
+// streaming kernel.  CQ = Cout/4 (power of two <= 32), BB = batch items per pass.
+// ---------------------------------------------------------------------------------------
+constexpr int kLcWarps = 4;                 // consumer warps (one position each at a time)
+constexpr int kLcThreads = (kLcWarps + 1) * 32;   // + 1 producer warp
+constexpr int kLcMaxStages = 8;
+
+template <int BB>
+__global__ void __launch_bounds__(kLcThreads, 1)
+lc3d_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
+                   const float* __restrict__ bias, float* __restrict__ out, LcGeo g, int b_base,
+                   int stages, int cq_log2) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int CQ = 1 << cq_log2;
+  const uint32_t blk_bytes = (uint32_t)g.F * g.Cout * sizeof(float);
+  const uint32_t blk_stride = (blk_bytes + 127u) & ~127u;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * blk_stride);
+  uint64_t* empty = full + stages;
+  int* s_jmap = reinterpret_cast<int*>(empty + stages);                          // [F]
+
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  for (int j = tid; j < g.F; j += kLcThreads) s_jmap[j] = feature_offset(g, j);
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  // This CTA owns positions n_k = blockIdx.x + k*gridDim.x (k = 0, 1, ...): neighbouring
+  // CTAs work on neighbouring patches at the same time, so the input stays hot in L2 while
+  // the weight stream as a whole advances contiguously.  Step k uses ring slot k % stages
+  // and is consumed by warp k % kLcWarps.
+  if (wid == kLcWarps) {
+    // ===== producer: one thread streams weight blocks into the ring =====
+    if (lane == 0) {
+      int k = 0;
+      for (int64_t n = blockIdx.x; n < g.pn; n += gridDim.x, ++k) {
+        const int slot = k % stages;
+        const int round = k / stages;
+        if (round >= 1) mbar_wait(empty + slot, (uint32_t)((round - 1) & 1));   // slot released
+        mbar_expect_tx(full + slot, blk_bytes);
+        bulk_load_1d(smem_raw + (size_t)slot * blk_stride, kernel + n * (int64_t)g.F * g.Cout,
+                     blk_bytes, full + slot);
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps =====
+  const int n4 = g.F * CQ;                      // float4s per block
+  const int fq = lane & (CQ - 1);               // this lane's output-channel quad
+  int k = wid;
+  for (int64_t n = (int64_t)blockIdx.x + (int64_t)wid * gridDim.x; n < g.pn;
+       n += (int64_t)kLcWarps * gridDim.x, k += kLcWarps) {
+    const int slot = k % stages;
+    const uint32_t ph = (uint32_t)((k / stages) & 1);
+    const int64_t p = g.p0 + n;
+    const float* xp = x + (int64_t)b_base * g.x_batch + patch_origin(g, p);
+    float acc[BB][4];
+#pragma unroll
+    for (int b = 0; b < BB; ++b) { acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.f; }
+    mbar_wait(full + slot, ph);
+    const float4* w4 = reinterpret_cast<const float4*>(smem_raw + (size_t)slot * blk_stride);
+#pragma unroll 6
+    for (int i = lane; i < n4; i += 32) {
+      const float4 wv = w4[i];
+      const int off = s_jmap[i >> cq_log2];
+#pragma unroll
+      for (int b = 0; b < BB; ++b) {
+        const float xv = __ldg(xp + (int64_t)b * g.x_batch + off);
+        acc[b][0] = fmaf(xv, wv.x, acc[b][0]);
+        acc[b][1] = fmaf(xv, wv.y, acc[b][1]);
+        acc[b][2] = fmaf(xv, wv.z, acc[b][2]);
+        acc[b][3] = fmaf(xv, wv.w, acc[b][3]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {                             // slot free: every lane has read its share
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(empty + slot)) : "memory");
+    }
+    // fold the 32/CQ lanes that share an output quad
+#pragma unroll
+    for (int b = 0; b < BB; ++b)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        for (int o = 16; o >= CQ; o >>= 1) acc[b][q] += __shfl_xor_sync(0xffffffffu, acc[b][q], o);
+    if (lane < CQ) {
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + n * g.Cout) + fq);
+#pragma unroll
+      for (int b = 0; b < BB; ++b) {
+        float4 r;
+        r.x = activate(acc[b][0] + bv.x, g.activation);
+        r.y = activate(acc[b][1] + bv.y, g.activation);
+        r.z = activate(acc[b][2] + bv.z, g.activation);
+        r.w = activate(acc[b][3] + bv.w, g.activation);
+        reinterpret_cast<float4*>(out + ((int64_t)(b_base + b) * g.pn + n) * g.Cout)[fq] = r;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// generic kernel: one thread per (b, position, filter)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lc3d_generic_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
+                    const float* __restrict__ bias, float* __restrict__ out, LcGeo g) {
+  const int64_t total = (int64_t)g.B * g.pn * g.Cout;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(t % g.Cout);
+    const int64_t n = (t / g.Cout) % g.pn;
+    const int b = (int)(t / ((int64_t)g.Cout * g.pn));
+    const float* xp = x + (int64_t)b * g.x_batch + patch_origin(g, g.p0 + n);
+    const float* wp = kernel + n * (int64_t)g.F * g.Cout + f;
+    float acc = 0.f;
+    for (int j = 0; j < g.F; ++j) acc = fmaf(__ldg(xp + feature_offset(g, j)), __ldg(wp + (int64_t)j * g.Cout), acc);
+    if (bias) acc += __ldg(bias + n * g.Cout + f);
+    out[t] = activate(acc, g.activation);
+  }
+}
+
+template <int BB>
+static int launch_stream(const float* x, const float* kernel, const float* bias, float* out, const LcGeo& g,
+                         int b_base, int cq_log2, cudaStream_t st) {
+  const uint32_t blk_bytes = (uint32_t)g.F * g.Cout * sizeof(float);
+  const uint32_t blk_stride = (blk_bytes + 127u) & ~127u;
+  const size_t fixed = (size_t)g.F * sizeof(int) + 2 * kLcMaxStages * sizeof(uint64_t) + 128;
+  int stages = (int)((220 * 1024 - fixed) / (size_t)blk_stride);
+  if (stages < 2) return 1;                      // caller falls back to the generic kernel
+  if (stages > kLcMaxStages) stages = kLcMaxStages;
+  const size_t smem = (size_t)stages * blk_stride + (size_t)stages * 16 + (size_t)g.F * sizeof(int) + 16;
+  auto kern = lc3d_stream_kernel<BB>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return check_launch("cudaFuncSetAttribute(lc3d_stream)");
+  int grid = sm_count();
+  if (g.pn < grid) grid = (int)g.pn;
+  kern<<<grid, kLcThreads, smem, st>>>(x, kernel, bias, out, g, b_base, stages, cq_log2);
+  return check_launch("lc3d_stream_kernel");
+}
+
+}  // namespace nrt
+
+using namespace nrt;
+
+extern "C" int nrt_lc3d_fwd_f32(const float* x, const float* kernel, const float* bias, float* out, int B,
+                                const int32_t* in_shape, int Cin, int Cout, const int32_t* ksize,
+                                const int32_t* strides, int feature_order, int activation, int64_t p0,
+                                int64_t p_count, void* stream) {
+  NRT_REQUIRE(x && kernel && out && in_shape && ksize && strides, NRT_E_ARG, "null pointer");
+  NRT_REQUIRE(B >= 0 && Cin >= 1 && Cout >= 1, NRT_E_ARG, "bad B/Cin/Cout");
+  NRT_REQUIRE(feature_order == 0 || feature_order == 1, NRT_E_ARG, "feature_order must be 0 or 1");
+  NRT_REQUIRE(activation >= NRT_ACT_LINEAR && activation <= NRT_ACT_TANH, NRT_E_ARG, "unknown activation %d", activation);
+  LcGeo g;
+  g.B = B; g.Cin = Cin; g.Cout = Cout; g.feature_order = feature_order; g.activation = activation;
+  g.P = 1; g.x_batch = Cin;
+  int64_t F = Cin;
+  for (int d = 0; d < 3; ++d) {
+    g.I[d] = in_shape[d]; g.K[d] = ksize[d]; g.St[d] = strides[d];
+    NRT_REQUIRE(g.I[d] >= 1 && g.K[d] >= 1 && g.St[d] >= 1 && g.K[d] <= g.I[d], NRT_E_ARG,
+                "bad input/kernel/stride at axis %d", d);
+    g.O[d] = (g.I[d] - g.K[d]) / g.St[d] + 1;            // conv_output_length, 'valid'
+    g.P *= g.O[d]; g.x_batch *= g.I[d]; F *= g.K[d];
+  }
+  NRT_REQUIRE(F <= 1 << 20 && g.x_batch <= 0x7fffffffLL, NRT_E_SIZE, "patch or input too large");
+  g.F = (int)F;
+  NRT_REQUIRE(p0 >= 0 && p_count >= 0 && p0 + p_count <= g.P, NRT_E_ARG,
+              "positions [%lld,%lld) outside [0,%lld)", (long long)p0, (long long)(p0 + p_count), (long long)g.P);
+  g.p0 = p0; g.pn = p_count;
+  if (B == 0 || p_count == 0) return NRT_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  const int cq = Cout / 4;
+  const bool fast = (Cout % 4 == 0) && cq <= 32 && (cq & (cq - 1)) == 0 && aligned16(kernel) && aligned16(out) &&
+                    (!bias || aligned16(bias)) && ((int64_t)g.F * Cout * 4) % 16 == 0 && g.F <= 8192 &&
+                    getenv("NRT_LC3D_GENERIC") == nullptr;
+  if (fast) {
+    int cq_log2 = 0;
+    while ((1 << cq_log2) < cq) ++cq_log2;
+    int b = 0, rc = NRT_OK;
+    while (b < B && rc == NRT_OK) {
+      const int left = B - b;
+      if (left >= 8) { rc = launch_stream<8>(x, kernel, bias, out, g, b, cq_log2, st); b += 8; }
+      else if (left >= 4) { rc = launch_stream<4>(x, kernel, bias, out, g, b, cq_log2, st); b += 4; }
+      else if (left >= 2) { rc = launch_stream<2>(x, kernel, bias, out, g, b, cq_log2, st); b += 2; }
+      else { rc = launch_stream<1>(x, kernel, bias, out, g, b, cq_log2, st); b += 1; }
+    }
+    if (rc <= 0) return rc;       // rc == 1: weight block does not fit the ring -> generic
+  }
+  const int64_t total = (int64_t)B * g.pn * Cout;
+  const int grid = (int)imin64((total + 255) / 256, (int64_t)sm_count() * 32);
+  lc3d_generic_kernel<<<grid, 256, 0, st>>>(x, kernel, bias, out, g);
+  return check_launch("lc3d_generic_kernel");
+}

@@ -1,0 +1,351 @@
+"""
+neurite_b200.layers -- drop-ins for the hot-path layers of neurite.layers
+(/root/reference/neurite/tf/layers.py) as torch.nn.Modules on channels-last CUDA tensors.
+
+    Resize / Zoom           layers.py:91-185
+    SpatialTransformer      voxelmorph.layers.SpatialTransformer (call sites models.py:806, 1157)
+    LocallyConnected3D      layers.py:811-1197  (implementation 1)
+
+Constructor arguments, defaults, `get_config()` keys, `compute_output_shape`, weight names
+(`kernel`, `bias`) and weight shapes/orderings follow the reference, so configs and
+trained weights carry over.  Inputs are [batch, *spatial, channels] like Keras' default.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, utils
+from ._lib import lib, check, ptr, stream_ptr, i32_array, require_cuda
+
+
+class _Layer(torch.nn.Module):
+    """The slice of the Keras Layer protocol the reference relies on: lazy build on first
+    call, get_config round trip, `name`."""
+
+    def __init__(self, name=None, **kwargs):
+        super().__init__()
+        if kwargs:
+            raise TypeError('Keyword argument not understood: %s' % list(kwargs)[0])
+        self.name = name or type(self).__name__.lower()
+        self.built = False
+
+    def build(self, input_shape):
+        self.built = True
+
+    def get_config(self):
+        return {'name': self.name}
+
+    @classmethod
+    def from_config(cls, config):
+        return cls(**config)
+
+    def forward(self, inputs):
+        if not self.built:
+            shp = [tuple(i.shape) for i in inputs] if isinstance(inputs, (list, tuple)) else tuple(inputs.shape)
+            self.build(shp)
+        return self.call(inputs)
+
+
+# ---------------------------------------------------------------------------------------
+class Resize(_Layer):
+    """N-D Resize (scipy-zoom-like), reference layers.py:91-185."""
+
+    def __init__(self, zoom_factor, interp_method='linear', **kwargs):
+        self.zoom_factor = zoom_factor
+        self.interp_method = interp_method
+        self.ndims = None
+        self.inshape = None
+        super().__init__(**kwargs)
+
+    def get_config(self):
+        config = super().get_config().copy()
+        config.update({'zoom_factor': self.zoom_factor, 'interp_method': self.interp_method})
+        return config
+
+    def build(self, input_shape):
+        if isinstance(input_shape[0], (list, tuple)) and len(input_shape) > 1:
+            raise Exception('Resize must be called on a list of length 1.')            # :133-134
+        if isinstance(input_shape[0], (list, tuple)):
+            input_shape = input_shape[0]
+        self.ndims = len(input_shape) - 2
+        self.inshape = input_shape
+        if not isinstance(self.zoom_factor, (list, tuple)):
+            self.zoom_factor = [self.zoom_factor] * self.ndims
+        else:
+            assert len(self.zoom_factor) == self.ndims, \
+                'zoom factor length {} does not match number of dimensions {}'.format(
+                    len(self.zoom_factor), self.ndims)                                  # :145-147
+        self.built = True
+
+    def call(self, inputs):
+        if isinstance(inputs, (list, tuple)):
+            assert len(inputs) == 1, "inputs has to be len 1. found: %d" % len(inputs)  # :162
+            vol = inputs[0]
+        else:
+            vol = inputs
+        vol = vol.reshape((-1,) + tuple(self.inshape[1:]))                              # :168
+        if all(z == 1 for z in self.zoom_factor):                                       # utils.py:250-251
+            return vol
+        # the reference maps utils.resize over the batch serially (:171); one launch here
+        return utils._resize_batched(vol, list(self.zoom_factor), self.interp_method)
+
+    def compute_output_shape(self, input_shape):
+        output_shape = [input_shape[0]]
+        output_shape += [int(input_shape[1:-1][f] * self.zoom_factor[f]) for f in range(self.ndims)]
+        output_shape += [input_shape[-1]]
+        return tuple(output_shape)
+
+
+Zoom = Resize
+
+
+# ---------------------------------------------------------------------------------------
+class SpatialTransformer(_Layer):
+    """Dense-shift spatial transformer with the voxelmorph call signature
+    (SpatialTransformer(interp_method, indexing, single_transform, fill_value, shift_center,
+    shape)([vol, trf])).  The reference calls it as vxm.layers.SpatialTransformer at
+    neurite/tf/models.py:806-807 and 1157-1159; the arithmetic is
+    out[b] = neurite.utils.interpn(vol[b], ndgrid + trf[b]).
+
+    Affine transforms ([B, N, N+1]) are expanded to a dense shift first (thin torch code);
+    `halo` is a tiling hint for the shared-memory kernel (expected max |shift| in voxels) and
+    never changes results."""
+
+    def __init__(self, interp_method='linear', indexing='ij', single_transform=False,
+                 fill_value=None, shift_center=True, shape=None, halo=0, **kwargs):
+        self.interp_method = interp_method
+        assert indexing in ['ij', 'xy'], "indexing has to be 'ij' (matrix) or 'xy' (cartesian)"
+        self.indexing = indexing
+        self.single_transform = single_transform
+        self.fill_value = fill_value
+        self.shift_center = shift_center
+        self.shape = shape
+        self.halo = halo
+        super().__init__(**kwargs)
+
+    def get_config(self):
+        config = super().get_config().copy()
+        config.update({'interp_method': self.interp_method, 'indexing': self.indexing,
+                       'single_transform': self.single_transform, 'fill_value': self.fill_value,
+                       'shift_center': self.shift_center, 'shape': self.shape})
+        return config
+
+    def build(self, input_shape):
+        if len(input_shape) != 2 or not isinstance(input_shape[0], (list, tuple)):
+            raise Exception('Spatial Transformer must be called on a list of length 2: '
+                            'first argument is the image, second is the transform.')
+        self.ndims = len(input_shape[0]) - 2
+        self.built = True
+
+    def _affine_to_dense(self, mat, volshape):
+        """[B, N, N+1] affine -> dense shift [B, *volshape, N] (vxm.utils.affine_to_dense_shift)."""
+        nd = len(volshape)
+        dev = mat.device
+        grid = torch.stack(torch.meshgrid(*[torch.arange(s, dtype=torch.float32, device=dev) for s in volshape],
+                                          indexing='ij'), -1)                    # [*S, N]
+        g = grid
+        if self.shift_center:
+            g = g - torch.tensor([(s - 1) / 2 for s in volshape], dtype=torch.float32, device=dev)
+        flat = torch.cat([g.reshape(-1, nd), torch.ones(g.numel() // nd, 1, device=dev)], 1)   # [V, N+1]
+        loc = torch.einsum('bij,vj->bvi', mat[:, :nd, :].to(torch.float32), flat)              # [B, V, N]
+        if self.shift_center:
+            loc = loc + torch.tensor([(s - 1) / 2 for s in volshape], dtype=torch.float32, device=dev)
+        return loc.reshape((mat.shape[0],) + tuple(volshape) + (nd,)) - grid
+
+    def call(self, inputs):
+        assert len(inputs) == 2, 'inputs has to be len 2, found: %d' % len(inputs)
+        vol, trf = inputs
+        nd = vol.dim() - 2
+        if trf.dim() == 3:                                                     # affine [B, N, N+1]
+            trf = self._affine_to_dense(trf, tuple(vol.shape[1:-1]) if self.shape is None else tuple(self.shape))
+        if self.indexing == 'xy':                                              # swap the first two shift channels
+            trf = torch.cat([trf[..., 1:2], trf[..., 0:1], trf[..., 2:]], -1)
+        if self.single_transform and trf.shape[0] == 1 and vol.shape[0] > 1:
+            trf = trf.expand((vol.shape[0],) + tuple(trf.shape[1:]))
+        if tuple(trf.shape[1:-1]) != tuple(vol.shape[1:-1]):
+            # output grid differs from the volume grid: go through interpn per batch item
+            outs = []
+            for b in range(vol.shape[0]):
+                mesh = utils.volshape_to_ndgrid(trf.shape[1:-1], device=trf.device)
+                loc = torch.stack([mesh[d].to(torch.float32) + trf[b, ..., d] for d in range(nd)], -1)
+                outs.append(utils.interpn(vol[b], loc, self.interp_method, self.fill_value))
+            return torch.stack(outs, 0)
+        return utils._warp_batched(vol, trf, self.interp_method, self.fill_value, halo=self.halo)
+
+
+# ---------------------------------------------------------------------------------------
+def _normalize_tuple(value, n, name):
+    if isinstance(value, int):
+        return (value,) * n
+    value = tuple(value)
+    if len(value) != n:
+        raise ValueError('The `%s` argument must be a tuple of %d integers. Received: %s' % (name, n, value))
+    return tuple(int(v) for v in value)
+
+
+def conv_output_length(input_length, filter_size, padding, stride):
+    """keras conv_utils.conv_output_length for 'valid'/'same' (layers.py:963-968)."""
+    if input_length is None:
+        return None
+    out = input_length if padding == 'same' else input_length - filter_size + 1
+    return (out + stride - 1) // stride
+
+
+class LocallyConnected3D(_Layer):
+    """Unshared-weight 3-D convolution, reference layers.py:811-1197, implementation 1.
+
+    kernel: [P, k0*k1*k2*Cin, filters] with P = o0*o1*o2 row-major (layers.py:974-984);
+    bias:   [o0, o1, o2, filters] (layers.py:1034-1040)."""
+
+    def __init__(self, filters, kernel_size, strides=(1, 1, 1), padding='valid', data_format=None,
+                 activation=None, use_bias=True, kernel_initializer='glorot_uniform',
+                 bias_initializer='zeros', kernel_regularizer=None, bias_regularizer=None,
+                 activity_regularizer=None, kernel_constraint=None, bias_constraint=None,
+                 implementation=1, **kwargs):
+        super().__init__(**kwargs)
+        self.filters = filters
+        self.kernel_size = _normalize_tuple(kernel_size, 3, 'kernel_size')
+        self.strides = _normalize_tuple(strides, 3, 'strides')
+        self.padding = padding.lower()
+        if self.padding != 'valid' and implementation == 1:
+            raise ValueError('Invalid border mode for LocallyConnected3D '
+                             '(only "valid" is supported if implementation is 1): ' + padding)   # :934-936
+        self.data_format = 'channels_last' if data_format is None else data_format.lower()
+        if self.data_format not in ('channels_last', 'channels_first'):
+            raise ValueError('Unknown data_format: ' + str(data_format))
+        if activation is not None and not callable(activation) and activation not in _lib.ACTIVATIONS:
+            raise ValueError('Unknown activation function: %s' % activation)
+        self.activation = activation
+        self.use_bias = use_bias
+        self.kernel_initializer = kernel_initializer
+        self.bias_initializer = bias_initializer
+        self.kernel_regularizer = kernel_regularizer
+        self.bias_regularizer = bias_regularizer
+        self.activity_regularizer = activity_regularizer
+        self.kernel_constraint = kernel_constraint
+        self.bias_constraint = bias_constraint
+        if implementation not in (1, 2, 3):
+            raise ValueError('Unrecognized implementation mode: %d.' % implementation)            # :1030-1032
+        if implementation != 1:
+            raise NotImplementedError('neurite_b200 builds implementation 1 (the reference default); '
+                                      'implementations 2/3 are storage variants of the same map')
+        self.implementation = implementation
+        self.kernel = None
+        self.bias = None
+
+    def build(self, input_shape):
+        input_shape = tuple(input_shape)
+        if len(input_shape) != 5:
+            raise ValueError('LocallyConnected3D expects a 5D input, got shape ' + str(input_shape))
+        if self.data_format == 'channels_last':
+            input_row, input_col, input_z = input_shape[1:-1]
+            input_filter = input_shape[4]
+        else:
+            input_row, input_col, input_z = input_shape[2:]
+            input_filter = input_shape[1]
+        if input_row is None or input_col is None or input_z is None:
+            raise ValueError('The spatial dimensions of the inputs to  a LocallyConnected3D layer '
+                             'should be fully-defined, but layer received the inputs shape ' + str(input_shape))
+        self.output_row = conv_output_length(input_row, self.kernel_size[0], self.padding, self.strides[0])
+        self.output_col = conv_output_length(input_col, self.kernel_size[1], self.padding, self.strides[1])
+        self.output_z = conv_output_length(input_z, self.kernel_size[2], self.padding, self.strides[2])
+        self.input_filter = input_filter
+        self.kernel_shape = (self.output_row * self.output_col * self.output_z,
+                             self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2] * input_filter,
+                             self.filters)                                                        # :974-977
+        if self.kernel is None:
+            kernel = torch.empty(self.kernel_shape, dtype=torch.float32)
+            self._init(kernel, self.kernel_initializer, fan_in=self.kernel_shape[1], fan_out=self.kernel_shape[2])
+            self.kernel = torch.nn.Parameter(kernel)
+        if self.use_bias and self.bias is None:
+            bias = torch.empty((self.output_row, self.output_col, self.output_z, self.filters), dtype=torch.float32)
+            self._init(bias, self.bias_initializer, fan_in=1, fan_out=1)
+            self.bias = torch.nn.Parameter(bias)
+        self.built = True
+
+    @staticmethod
+    def _init(t, initializer, fan_in, fan_out):
+        if callable(initializer):
+            initializer(t)
+        elif initializer == 'zeros':
+            t.zero_()
+        elif initializer == 'ones':
+            t.fill_(1.)
+        elif initializer == 'glorot_uniform':
+            # keras VarianceScaling(scale=1, mode='fan_avg', 'uniform') with keras' fan
+            # computation for rank-3 shapes: receptive field = shape[0]
+            rf = t.shape[0] if t.dim() == 3 else 1
+            limit = math.sqrt(6.0 / (rf * fan_in + rf * fan_out)) if t.dim() == 3 else math.sqrt(6.0 / (fan_in + fan_out))
+            t.uniform_(-limit, limit)
+        else:
+            raise ValueError('Unknown initializer: %s' % initializer)
+
+    def compute_output_shape(self, input_shape):
+        if self.data_format == 'channels_first':
+            rows, cols, z = input_shape[2], input_shape[3], input_shape[4]
+        else:
+            rows, cols, z = input_shape[1], input_shape[2], input_shape[3]
+        rows = conv_output_length(rows, self.kernel_size[0], self.padding, self.strides[0])
+        cols = conv_output_length(cols, self.kernel_size[1], self.padding, self.strides[1])
+        z = conv_output_length(z, self.kernel_size[2], self.padding, self.strides[2])
+        if self.data_format == 'channels_first':
+            return (input_shape[0], self.filters, rows, cols, z)
+        return (input_shape[0], rows, cols, z, self.filters)
+
+    def call(self, inputs):
+        return local_conv3d(inputs, self.kernel, self.bias if self.use_bias else None, self.kernel_size,
+                            self.strides, (self.output_row, self.output_col, self.output_z),
+                            self.data_format, self.activation)
+
+    def get_config(self):
+        config = {
+            'filters': self.filters, 'kernel_size': self.kernel_size, 'strides': self.strides,
+            'padding': self.padding, 'data_format': self.data_format, 'activation': self.activation,
+            'use_bias': self.use_bias, 'kernel_initializer': self.kernel_initializer,
+            'bias_initializer': self.bias_initializer, 'kernel_regularizer': self.kernel_regularizer,
+            'bias_regularizer': self.bias_regularizer, 'activity_regularizer': self.activity_regularizer,
+            'kernel_constraint': self.kernel_constraint, 'bias_constraint': self.bias_constraint,
+            'implementation': self.implementation,
+        }
+        base_config = super().get_config()
+        return dict(list(base_config.items()) + list(config.items()))
+
+
+def local_conv3d(inputs, kernel, bias, kernel_size, strides, output_shape, data_format='channels_last',
+                 activation=None, p0=0, p_count=None):
+    """LocallyConnected3D.local_conv + bias + activation (layers.py:1126-1197, 1098-1101).
+
+    inputs [B,I0,I1,I2,Cin] (channels_last) or [B,Cin,I0,I1,I2] (channels_first);
+    kernel [P,F,Cout]; bias [o0,o1,o2,Cout] or None.  p0/p_count select a contiguous range
+    of output positions (position sharding; kernel/bias then hold only that range)."""
+    if data_format not in {'channels_first', 'channels_last'}:
+        raise ValueError('Unknown data_format: ' + str(data_format))
+    require_cuda(inputs, kernel, bias)
+    fused_act = activation if (activation is None or isinstance(activation, str)) else None
+    x = inputs.to(torch.float32)
+    if data_format == 'channels_first':
+        x = x.permute(0, 2, 3, 4, 1)
+    x = x.contiguous()
+    k = kernel.detach().to(torch.float32).contiguous()
+    B, Cin = x.shape[0], x.shape[-1]
+    Cout = k.shape[-1]
+    P = int(np.prod(output_shape))
+    if p_count is None:
+        p_count = P - p0
+    b = None
+    if bias is not None:
+        b = bias.detach().to(torch.float32).contiguous().reshape(-1, Cout)
+    out = torch.empty((B, p_count, Cout), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.nrt_lc3d_fwd_f32(ptr(x), ptr(k), ptr(b), ptr(out), B, i32_array(x.shape[1:4]), Cin, Cout,
+                                   i32_array(kernel_size), i32_array(strides),
+                                   1 if data_format == 'channels_first' else 0,
+                                   _lib.ACTIVATIONS[fused_act], int(p0), int(p_count), stream_ptr(x.device)))
+    if p_count == P:
+        out = out.reshape((B,) + tuple(output_shape) + (Cout,))
+        if data_format == 'channels_first':
+            out = out.permute(0, 4, 1, 2, 3).contiguous()
+    if callable(activation):
+        out = activation(out)
+    return out

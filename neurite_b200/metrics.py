@@ -1,0 +1,243 @@
+"""
+neurite_b200.metrics -- drop-ins for Dice / SoftDice / HardDice / CategoricalCrossentropy of
+neurite.metrics (/root/reference/neurite/tf/metrics.py:339-650) on torch CUDA tensors.
+
+Same constructor arguments, defaults, assertions and method names (`dice`, `mean_dice`,
+`loss`, `cce`, `__call__`).  tf.debugging asserts become `InvalidArgumentError`
+(a ValueError) carrying the reference's messages 'value outside range' / 'metric not finite'.
+
+`group`, when given, is a torch.distributed process group over which the voxel range of
+every batch item is sharded: each rank passes its own voxel slab and the [B,L,3] partial
+sums (768 B at cfg 3) are all-reduced before the finalize kernel.
+"""
+import warnings
+
+import numpy as np
+import torch
+
+from ._lib import lib, check, ptr, stream_ptr, require_cuda
+
+
+class InvalidArgumentError(ValueError):
+    """Raised where the reference's tf.debugging asserts raise tf.errors.InvalidArgumentError."""
+
+
+_WS = {}
+
+
+def _workspace(device, nbytes):
+    key = (device.type, device.index)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+def dice_sums(y_true, y_pred, normalize=False, check_input_limits=True, group=None):
+    """[B,*S,L] x2 -> sums [B,L,3] = (sum t*p, sum t*t, sum p*p) and a range flag tensor."""
+    require_cuda(y_true, y_pred)
+    if y_true.shape != y_pred.shape:
+        raise ValueError('y_true %s and y_pred %s differ in shape' % (tuple(y_true.shape), tuple(y_pred.shape)))
+    t = y_true.to(torch.float32).contiguous()
+    p = y_pred.to(torch.float32).contiguous()
+    B, L = t.shape[0], t.shape[-1]
+    V = t.numel() // max(B * L, 1)
+    sums = torch.empty((B, L, 3), dtype=torch.float32, device=t.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=t.device)
+    ws_bytes = lib.nrt_dice_workspace_bytes(B, L)
+    ws = _workspace(t.device, ws_bytes)
+    with torch.cuda.device(t.device):
+        check(lib.nrt_dice_sums_f32(ptr(t), ptr(p), B, V, L, 0, V, int(bool(normalize)), int(bool(check_input_limits)),
+                                    ptr(sums), ptr(flag), ptr(ws), ws_bytes, stream_ptr(t.device)))
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(sums, group=group)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    return sums, flag
+
+
+def dice_label_sums(t_lab, p_lab, nb_labels, group=None):
+    """integer label maps [B,*S] x2 -> sums [B,L,3] (exact counts)."""
+    require_cuda(t_lab, p_lab)
+    t = t_lab.to(torch.int32).contiguous()
+    p = p_lab.to(torch.int32).contiguous()
+    B = t.shape[0]
+    V = t.numel() // max(B, 1)
+    sums = torch.empty((B, nb_labels, 3), dtype=torch.float32, device=t.device)
+    ws_bytes = lib.nrt_dice_workspace_bytes(B, nb_labels)
+    ws = _workspace(t.device, ws_bytes)
+    with torch.cuda.device(t.device):
+        check(lib.nrt_dice_label_sums_i32(ptr(t), ptr(p), B, V, nb_labels, 0, V, ptr(sums), ptr(ws), ws_bytes,
+                                          stream_ptr(t.device)))
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(sums, group=group)
+    return sums
+
+
+def argmax_labels(x):
+    """[..., L] float -> [...] int32, first maximum wins (tf.argmax)."""
+    require_cuda(x)
+    x32 = x.to(torch.float32).contiguous()
+    L = x32.shape[-1]
+    n = x32.numel() // L
+    idx = torch.empty(x32.shape[:-1], dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.nrt_argmax_f32(ptr(x32), n, L, ptr(idx), stream_ptr(x.device)))
+    return idx
+
+
+def dice_finalize(sums, laplace_smoothing=0.):
+    B, L = sums.shape[0], sums.shape[1]
+    out = torch.empty((B, L), dtype=torch.float32, device=sums.device)
+    with torch.cuda.device(sums.device):
+        check(lib.nrt_dice_finalize_f32(ptr(sums), B, L, float(laplace_smoothing), ptr(out), stream_ptr(sums.device)))
+    return out
+
+
+class Dice:
+    """Dice of two Tensors -- reference metrics.py:339-519."""
+
+    def __init__(self, dice_type='soft', input_type='prob', nb_labels=None, weights=None,
+                 check_input_limits=True, laplace_smoothing=0., normalize=False, group=None):
+        self.dice_type = dice_type
+        self.input_type = input_type
+        self.nb_labels = nb_labels
+        self.weights = weights
+        self.normalize = normalize
+        self.check_input_limits = check_input_limits
+        self.laplace_smoothing = laplace_smoothing
+        self.group = group
+        assert self.input_type in ['prob', 'max_label']                                   # :406
+        if self.dice_type == 'hard' and self.input_type == 'max_label':
+            assert self.nb_labels is not None, 'If doing hard Dice need nb_labels'       # :408-409
+        if self.dice_type == 'soft':
+            assert self.input_type in ['prob', 'one_hot'], \
+                'if doing soft Dice, must use probabilistic (one_hot)encoding'           # :411-413
+
+    def dice(self, y_true, y_pred):
+        """[batch, ..., nb_labels] (prob) or [batch, ...] (max_label) -> [batch, nb_labels]."""
+        if self.dice_type == 'hard':
+            if self.input_type == 'prob':
+                warnings.warn('You are using ne.metrics.Dice with probabilistic inputs'
+                              'and computing *hard* dice. \n For this, we use argmax to'
+                              'get the optimal label at each location, which is not'
+                              'differentiable. Do not use expecting gradients.')          # :455-458
+                if self.check_input_limits or self.normalize:
+                    # the reference checks / renormalises the probabilistic inputs first (:434-444)
+                    _, flag = dice_sums(y_true, y_pred, self.normalize, self.check_input_limits, self.group)
+                    if self.check_input_limits and int(flag.item()) != 0:
+                        raise InvalidArgumentError('value outside range')
+                if self.nb_labels is None:
+                    self.nb_labels = int(y_pred.shape[-1])                                # :460-461
+                y_pred = argmax_labels(y_pred)                                            # :463-464
+                y_true = argmax_labels(y_true)
+            sums = dice_label_sums(y_true, y_pred, self.nb_labels, self.group)           # :467-477 fused
+        else:
+            sums, flag = dice_sums(y_true, y_pred, self.normalize, self.check_input_limits, self.group)
+            if self.check_input_limits and int(flag.item()) != 0:                         # :439-444
+                raise InvalidArgumentError('value outside range')
+        return dice_finalize(sums, self.laplace_smoothing)                                # :476-482
+
+    def mean_dice(self, y_true, y_pred):
+        dice_metric = self.dice(y_true, y_pred)                                           # :499
+        if self.weights is not None:                                                      # :502-505
+            w = self.weights
+            assert len(w.shape) == 2, \
+                'weights should be a matrix broadcastable to [batch_size, nb_labels]'
+            w = torch.as_tensor(np.asarray(w) if not torch.is_tensor(w) else w, dtype=torch.float32,
+                                device=dice_metric.device)
+            dice_metric = dice_metric * w
+        mean_dice_metric = dice_metric.mean()                                             # :508
+        if not bool(torch.isfinite(mean_dice_metric)):
+            raise InvalidArgumentError('metric not finite')                               # :509
+        return mean_dice_metric
+
+    def loss(self, y_true, y_pred):
+        """deprecated alias kept by the reference (metrics.py:512-519)."""
+        warnings.warn('ne.metrics.*.loss functions are deprecated.'
+                      'Please use the ne.losses.*.loss functions.')
+        return -self.mean_dice(y_true, y_pred)
+
+
+class SoftDice(Dice):
+    """reference metrics.py:522-560."""
+
+    def __init__(self, weights=None, check_input_limits=True, laplace_smoothing=0., normalize=False, group=None):
+        super().__init__(dice_type='soft', input_type='prob', weights=weights,
+                         check_input_limits=check_input_limits, laplace_smoothing=laplace_smoothing,
+                         normalize=normalize, group=group)
+
+
+class HardDice(Dice):
+    """reference metrics.py:563-616."""
+
+    def __init__(self, nb_labels, input_type='max_label', weights=None, check_input_limits=True,
+                 laplace_smoothing=0., normalize=False, group=None):
+        super().__init__(dice_type='hard', input_type=input_type, nb_labels=nb_labels, weights=weights,
+                         check_input_limits=check_input_limits, laplace_smoothing=laplace_smoothing,
+                         normalize=normalize, group=group)
+
+
+class CategoricalCrossentropy:
+    """Label-weighted categorical cross-entropy -- reference metrics.py:619-650 wrapping
+    tf.keras.losses.CategoricalCrossentropy (kwargs from_logits, label_smoothing, axis,
+    reduction pass through; axis must be -1)."""
+
+    def __init__(self, label_weights=None, from_logits=False, label_smoothing=0., axis=-1,
+                 reduction='sum_over_batch_size', name='categorical_crossentropy', group=None):
+        self.label_weights = None
+        if label_weights is not None:
+            self.label_weights = torch.as_tensor(np.asarray(label_weights) if not torch.is_tensor(label_weights)
+                                                 else label_weights)
+        if axis != -1:
+            raise NotImplementedError('CategoricalCrossentropy: only axis=-1 (channels-last) is built')
+        if reduction in ('auto', 'sum_over_batch_size'):
+            reduction = 'sum_over_batch_size'
+        if reduction not in ('sum_over_batch_size', 'sum', 'none'):
+            raise ValueError('Invalid Reduction Key: %s' % reduction)
+        self.from_logits = from_logits
+        self.label_smoothing = label_smoothing
+        self.reduction = reduction
+        self.name = name
+        self.group = group
+
+    def __call__(self, y_true, y_pred, sample_weight=None):
+        return self.cce(y_true, y_pred, sample_weight=sample_weight)
+
+    def cce(self, y_true, y_pred, sample_weight=None):
+        lw = None
+        if self.label_weights is not None:
+            yf = y_pred.shape[-1]
+            lf = self.label_weights.shape[-1]
+            if yf != lf:
+                raise ValueError(f'Label weights must be of len {yf}, but got {lf}.')     # :642-645
+            lw = self.label_weights.to(device=y_pred.device, dtype=torch.float32).contiguous()
+        require_cuda(y_true, y_pred)
+        t = y_true.to(torch.float32).contiguous()
+        p = y_pred.to(torch.float32).contiguous()
+        C = p.shape[-1]
+        n = p.numel() // C
+        sw = None
+        if sample_weight is not None:
+            sw = torch.as_tensor(sample_weight, dtype=torch.float32, device=p.device)
+            sw = sw.expand(p.shape[:-1]).contiguous() if sw.dim() > 0 else sw.expand(p.shape[:-1]).contiguous()
+        per = torch.empty(p.shape[:-1], dtype=torch.float32, device=p.device) if self.reduction == 'none' else None
+        total = torch.empty(1, dtype=torch.float32, device=p.device)
+        ws_bytes = lib.nrt_cce_workspace_bytes()
+        ws = _workspace(p.device, ws_bytes)
+        with torch.cuda.device(p.device):
+            check(lib.nrt_cce_f32(ptr(t), ptr(p), ptr(lw), ptr(sw), n, C, int(bool(self.from_logits)),
+                                  float(self.label_smoothing), ptr(per), ptr(total), ptr(ws), ws_bytes,
+                                  stream_ptr(p.device)))
+        if self.reduction == 'none':
+            return per
+        count = torch.tensor([float(n)], device=p.device)
+        if self.group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(total, group=self.group)
+            dist.all_reduce(count, group=self.group)
+        if self.reduction == 'sum':
+            return total[0]
+        return (total / count)[0]

@@ -1,0 +1,246 @@
+"""
+neurite_b200.utils -- drop-in for the interpolation part of neurite.utils
+(/root/reference/neurite/tf/utils/utils.py), on torch CUDA tensors, channels-last.
+
+    interpn(vol, loc, interp_method='linear', fill_value=None)     utils.py:73-220
+    resize(vol, zoom_factor, interp_method='linear') / zoom        utils.py:223-265
+    transform(vol, loc_shift, interp_method, indexing, fill_value) voxelmorph.utils.transform contract
+    sub2ind2d, prod_n, ndgrid, meshgrid, volshape_to_ndgrid, volshape_to_meshgrid,
+    batch_channel_flatten, flatten_axes                            utils.py:333-476, 1068-1226
+
+Same names, argument order, defaults and exception classes as the reference.  The
+arithmetic runs in the hand-written CUDA kernels behind the C ABI (include/neurite_b200.h);
+the helpers that only build index grids stay thin torch code for API parity -- the fused
+kernels never materialise them.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr, i32_array, method_id, require_cuda
+
+MAX_DIMS = 3
+
+
+def _as_f32(t):
+    return t if t.dtype == torch.float32 else t.to(torch.float32)
+
+
+# ---------------------------------------------------------------------------------------
+# interpn
+# ---------------------------------------------------------------------------------------
+def interpn(vol, loc, interp_method='linear', fill_value=None):
+    """N-D gridded interpolation (reference utils.py:73-220).
+
+    vol: [*vol_shape] or [*vol_shape, C]; loc: list of D tensors or a [*new_shape, D] tensor.
+    Edge-clamped ('nearest' extrapolation) unless fill_value is given."""
+    if isinstance(loc, (list, tuple)):
+        loc = torch.stack(list(loc), -1)                                # :106-107
+    nb_dims = loc.shape[-1]
+    input_vol_ndim = vol.dim()
+    if vol.dim() not in [nb_dims, nb_dims + 1]:                         # :111-113
+        raise Exception("Number of loc Tensors %d does not match volume dimension %d"
+                        % (nb_dims, len(vol.shape[:-1])))
+    if nb_dims > vol.dim():                                             # :115-117
+        raise Exception("Loc dimension %d does not match volume dimension %d" % (nb_dims, vol.dim()))
+    method = method_id(interp_method)                                   # AssertionError, :194-195
+    if nb_dims > MAX_DIMS:
+        raise NotImplementedError('neurite_b200.interpn supports up to %d spatial dims (got %d)'
+                                  % (MAX_DIMS, nb_dims))
+    require_cuda(vol, loc)
+    if vol.dim() == nb_dims:                                            # :119-120
+        vol = vol.unsqueeze(-1)
+    out_dtype = vol.dtype
+    if not vol.dtype.is_floating_point and method == _lib.NRT_LINEAR:
+        raise TypeError('linear interpolation needs a floating-point volume (reference: dtype error in wt * vol_val)')
+    vol32 = _as_f32(vol).contiguous()
+    loc32 = _as_f32(loc).contiguous()                                   # :123-127
+    C = vol32.shape[-1]
+    out_shape = tuple(loc32.shape[:-1])
+    n_out = int(np.prod(out_shape)) if len(out_shape) else 1
+    out = torch.empty(out_shape + (C,), dtype=torch.float32, device=vol32.device)
+    with torch.cuda.device(vol32.device):
+        check(lib.nrt_interpn_f32(ptr(vol32), i32_array(vol32.shape[:-1]), nb_dims, C, ptr(loc32), n_out, method,
+                                  0 if fill_value is None else 1, 0.0 if fill_value is None else float(fill_value),
+                                  ptr(out), stream_ptr(vol32.device)))
+    if out.dtype != out_dtype:
+        out = out.to(out_dtype)
+    if input_vol_ndim == nb_dims:                                       # :216-218
+        out = out[..., 0]
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# resize / zoom
+# ---------------------------------------------------------------------------------------
+def _resize_batched(x, zoom_factor, interp_method, out_z0=0, out_n0=None):
+    """x [B,*S,C] -> [B,*int(S*zoom),C] (one launch for the whole batch)."""
+    method = method_id(interp_method)
+    require_cuda(x)
+    ndims = x.dim() - 2
+    if ndims > MAX_DIMS:
+        raise NotImplementedError('resize supports up to %d spatial dims' % MAX_DIMS)
+    in_shape = [int(s) for s in x.shape[1:-1]]
+    new_shape = [int(in_shape[f] * zoom_factor[f]) for f in range(ndims)]   # :256-257
+    x32 = _as_f32(x).contiguous()
+    B, C = x32.shape[0], x32.shape[-1]
+    if out_n0 is None:
+        out_n0 = new_shape[0]
+    out = torch.empty((B, out_n0) + tuple(new_shape[1:]) + (C,), dtype=torch.float32, device=x.device)
+    if out.numel():
+        with torch.cuda.device(x.device):
+            check(lib.nrt_resize_f32(ptr(x32), ptr(out), B, i32_array(in_shape), i32_array(new_shape), ndims, C,
+                                     method, out_z0, out_n0, stream_ptr(x.device)))
+    return out if x.dtype == torch.float32 else out.to(x.dtype)
+
+
+def resize(vol, zoom_factor, interp_method='linear'):
+    """reference utils.py:223-265: zoom a single volume [*S, C] (or [*S] with a zoom list)."""
+    if isinstance(zoom_factor, (list, tuple)):
+        ndims = len(zoom_factor)
+        vol_shape = vol.shape[:ndims]
+        assert len(vol_shape) in (ndims, ndims + 1), \
+            "zoom_factor length %d does not match ndims %d" % (len(vol_shape), ndims)      # :241-242
+        zoom_factor = list(zoom_factor)
+    else:
+        vol_shape = vol.shape[:-1]
+        ndims = len(vol_shape)
+        zoom_factor = [zoom_factor] * ndims
+    if all(z == 1 for z in zoom_factor):                                 # :250-251
+        return vol
+    squeeze = vol.dim() == ndims
+    v = vol.unsqueeze(-1) if squeeze else vol
+    out = _resize_batched(v.unsqueeze(0), zoom_factor, interp_method)[0]
+    return out[..., 0] if squeeze else out
+
+
+zoom = resize
+
+
+# ---------------------------------------------------------------------------------------
+# dense warp (voxelmorph.utils.transform contract)
+# ---------------------------------------------------------------------------------------
+def _warp_batched(vol, flow, interp_method='linear', fill_value=None, halo=0,
+                  src_z0=0, full_s0=None, out_z0=0, err_flag=None):
+    """vol [B, src_n0, *S_rest, C], flow [B, out_n0, *S_rest, D] -> [B, out_n0, *S_rest, C].
+
+    With the defaults this is the whole-volume warp; the slab arguments are used by
+    neurite_b200.dist for z-slab sharding (vol holds planes [src_z0, src_z0+src_n0) of a
+    volume of full extent full_s0; flow/out are planes [out_z0, out_z0+out_n0))."""
+    method = method_id(interp_method)
+    require_cuda(vol, flow)
+    D = flow.shape[-1]
+    if vol.dim() != D + 2 or flow.dim() != D + 2:
+        raise Exception("Number of loc Tensors %d does not match volume dimension %d" % (D, vol.dim() - 2))
+    if D > MAX_DIMS:
+        raise NotImplementedError('warp supports up to %d spatial dims' % MAX_DIMS)
+    if not vol.dtype.is_floating_point and method == _lib.NRT_LINEAR:
+        raise TypeError('linear interpolation needs a floating-point volume')
+    vol32 = _as_f32(vol).contiguous()
+    flow32 = _as_f32(flow).contiguous()
+    B, C = vol32.shape[0], vol32.shape[-1]
+    src_n0, out_n0 = vol32.shape[1], flow32.shape[1]
+    if full_s0 is None:
+        full_s0 = src_n0
+    if tuple(vol32.shape[2:-1]) != tuple(flow32.shape[2:-1]) or flow32.shape[0] != B:
+        raise ValueError('vol %s and flow %s disagree on batch / trailing spatial dims'
+                         % (tuple(vol.shape), tuple(flow.shape)))
+    shape = [int(full_s0)] + [int(s) for s in vol32.shape[2:-1]]
+    out = torch.empty(tuple(flow32.shape[:-1]) + (C,), dtype=torch.float32, device=vol.device)
+    if out.numel():
+        with torch.cuda.device(vol.device):
+            check(lib.nrt_warp_f32(ptr(vol32), ptr(flow32), ptr(out), B, i32_array(shape), D, C, method,
+                                   0 if fill_value is None else 1, 0.0 if fill_value is None else float(fill_value),
+                                   int(src_z0), int(src_n0), int(out_z0), int(out_n0), int(halo),
+                                   ptr(err_flag), stream_ptr(vol.device)))
+    return out if vol.dtype == torch.float32 else out.to(vol.dtype)
+
+
+def transform(vol, loc_shift, interp_method='linear', indexing='ij', fill_value=None):
+    """voxelmorph.utils.transform: interpn(vol, ndgrid + loc_shift).  vol [*S, C], shift [*S, D]."""
+    if indexing not in ('ij', 'xy'):
+        raise ValueError("indexing parameter must be either 'xy' or 'ij'")
+    if indexing == 'xy' and loc_shift.shape[-1] > 1:
+        # meshgrid 'xy' swaps which axis carries grid 0/1 (utils.py:460-464); equivalent to
+        # adding the transposed identity grid -- rarely used, so go through interpn directly
+        mesh = volshape_to_meshgrid(loc_shift.shape[:-1], indexing='xy', device=loc_shift.device)
+        loc = [mesh[d].to(torch.float32) + loc_shift[..., d] for d in range(loc_shift.shape[-1])]
+        return interpn(vol, loc, interp_method=interp_method, fill_value=fill_value)
+    squeeze = vol.dim() == loc_shift.shape[-1]
+    v = vol.unsqueeze(-1) if squeeze else vol
+    out = _warp_batched(v.unsqueeze(0), loc_shift.unsqueeze(0), interp_method, fill_value)[0]
+    return out[..., 0] if squeeze else out
+
+
+# ---------------------------------------------------------------------------------------
+# thin helpers kept for API parity (the kernels fuse them away)
+# ---------------------------------------------------------------------------------------
+def sub2ind2d(siz, subs, **kwargs):
+    """utils.py:1068-1082 (row-major despite the reference docstring)."""
+    assert len(siz) == len(subs), 'found inconsistent siz and subs: %d %d' % (len(siz), len(subs))
+    k = np.cumprod(siz[::-1])
+    ndx = subs[-1]
+    for i, v in enumerate(subs[:-1][::-1]):
+        ndx = ndx + v * int(k[i])
+    return ndx
+
+
+def prod_n(lst):
+    """utils.py:1085-1092."""
+    prod = lst[0]
+    for p in lst[1:]:
+        prod = prod * p
+    return prod
+
+
+def meshgrid(*args, **kwargs):
+    """utils.py:398-476."""
+    indexing = kwargs.pop('indexing', 'xy')
+    if kwargs:
+        key = list(kwargs.keys())[0]
+        raise TypeError("'{}' is an invalid keyword argument for this function".format(key))
+    if indexing not in ('xy', 'ij'):
+        raise ValueError("indexing parameter must be either 'xy' or 'ij'")
+    args = [torch.as_tensor(a) for a in args]
+    return list(torch.meshgrid(*args, indexing=indexing))
+
+
+def ndgrid(*args, **kwargs):
+    """utils.py:382-395."""
+    return meshgrid(*args, indexing='ij', **kwargs)
+
+
+def volshape_to_ndgrid(volshape, device=None, **kwargs):
+    """utils.py:333-353."""
+    if not all(float(d).is_integer() for d in volshape):
+        raise ValueError("volshape needs to be a list of integers")
+    return ndgrid(*[torch.arange(0, int(d), device=device) for d in volshape], **kwargs)
+
+
+def volshape_to_meshgrid(volshape, device=None, **kwargs):
+    """utils.py:356-379."""
+    if not all(float(d).is_integer() for d in volshape):
+        raise ValueError("volshape needs to be a list of integers")
+    return meshgrid(*[torch.arange(0, int(d), device=device) for d in volshape], **kwargs)
+
+
+def flatten_axes(x, axes):
+    """utils.py:1195-1226."""
+    assert isinstance(axes, (list, tuple, range)), 'axes must be list or tuple of axes to be flattened'
+    assert np.all(np.diff(axes) == 1), 'axes need to be contiguous'
+    if axes[0] < 0:
+        assert axes[-1] < 0, 'if one axis is negative, all have to be negative'
+    assert axes[-1] < x.dim(), 'axis %d outside max axis %d' % (axes[-1], x.dim() - 1)
+    shp = list(x.shape)
+    new = shp[:axes[0]] + [-1]
+    if axes[-1] < x.dim() - 1 and not (axes[-1] == -1):
+        new += shp[axes[-1] + 1:]
+    return x.reshape(new)
+
+
+def batch_channel_flatten(x):
+    """utils.py:1175-1188."""
+    return flatten_axes(x, range(1, x.dim() - 1))
+
+
+flatten_batch_channel = batch_channel_flatten

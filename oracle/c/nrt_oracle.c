@@ -1,0 +1,186 @@
+/*
+ * oracle/c/nrt_oracle.c -- C99 + OpenMP restatement of the reference's hot path.
+ * TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): the checker for full-size parity and
+ * the multi-threaded CPU baseline of bench.py.  Never linked into the product.
+ *
+ * Same arithmetic, op for op, as oracle/interp.py (which is pinned bit-exactly to the
+ * reference's own source run on tools/tfshim): one fp32 rounding per operation -- compile
+ * with -ffp-contract=off so the compiler cannot fuse a*b+c.
+ *
+ *   oracle_warp_f32      voxelmorph SpatialTransformer contract = identity grid + flow ->
+ *                        interpn, reference neurite/tf/utils/utils.py:73-220
+ *   oracle_interpn_f32   reference neurite/tf/utils/utils.py:73-220 (explicit loc)
+ *   oracle_dice_sums_f32 reference neurite/tf/metrics.py:471-477 (the three reductions)
+ *   oracle_cce_f32       reference neurite/tf/metrics.py:640-650 + Keras CCE formula
+ *   oracle_lc3d_f32      reference neurite/tf/layers.py:1126-1197, 1098-1099
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define MAXD 3
+
+int oracle_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+static inline float clipf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* one output point; vol [S.., C] resident in full; loc[D] */
+static void sample_point(const float* vol, const int* S, int D, int C, const float* loc, int method,
+                         int has_fill, float fill, float* out) {
+  if (method == 0) {
+    int i0[MAXD], i1[MAXD];
+    float wlo[MAXD], whi[MAXD];
+    for (int d = 0; d < D; ++d) {
+      const float mx = (float)(S[d] - 1);
+      const float x = clipf(loc[d], 0.0f, mx);                 /* utils.py:142 */
+      const float f0 = clipf(floorf(loc[d]), 0.0f, mx);        /* :139, :143   */
+      const float f1 = clipf(f0 + 1.0f, 0.0f, mx);             /* :146         */
+      i0[d] = (int)f0; i1[d] = (int)f1;                        /* :147         */
+      wlo[d] = f1 - x;                                         /* :152 diff_loc1 -> corner bit 0 */
+      whi[d] = 1.0f - wlo[d];                                  /* :153 diff_loc0 -> corner bit 1 */
+    }
+    for (int c = 0; c < C; ++c) out[c] = 0.0f;                 /* :160 */
+    for (int corner = 0; corner < (1 << D); ++corner) {        /* itertools.product order, :159 */
+      int idx = 0;
+      float w = 0.0f;
+      for (int d = 0; d < D; ++d) {
+        const int bit = (corner >> (D - 1 - d)) & 1;
+        idx = idx * S[d] + (bit ? i1[d] : i0[d]);              /* sub2ind2d :1068-1082 */
+        const float wd = bit ? whi[d] : wlo[d];
+        w = d == 0 ? wd : w * wd;                              /* prod_n :1085-1092 */
+      }
+      const float* v = vol + (size_t)idx * C;
+      for (int c = 0; c < C; ++c) {
+        const float prod = w * v[c];
+        out[c] = out[c] + prod;                                /* :191 */
+      }
+    }
+  } else {
+    int idx = 0;
+    for (int d = 0; d < D; ++d) {
+      int r = (int)nearbyintf(loc[d]);                         /* tf.round half-to-even, then cast, :196 */
+      r = r < 0 ? 0 : (r > S[d] - 1 ? S[d] - 1 : r);           /* :197 */
+      idx = idx * S[d] + r;
+    }
+    const float* v = vol + (size_t)idx * C;
+    for (int c = 0; c < C; ++c) out[c] = v[c];
+  }
+  if (has_fill) {                                              /* :206-213 */
+    int oob = 0;
+    for (int d = 0; d < D; ++d) oob |= (loc[d] < 0.0f) || (loc[d] > (float)(S[d] - 1));
+    const float keep = oob ? 0.0f : 1.0f, o = oob ? 1.0f : 0.0f;
+    for (int c = 0; c < C; ++c) {
+      const float a = out[c] * keep, b = o * fill;
+      out[c] = a + b;
+    }
+  }
+}
+
+void oracle_interpn_f32(const float* vol, const int* S, int D, int C, const float* loc, int64_t n,
+                        int method, int has_fill, float fill, float* out) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i)
+    sample_point(vol, S, D, C, loc + i * D, method, has_fill, fill, out + i * C);
+}
+
+/* vol [B, S.., C], flow [B, S.., D] -> out [B, S.., C] */
+void oracle_warp_f32(const float* vol, const float* flow, float* out, int B, const int* S, int D, int C,
+                     int method, int has_fill, float fill) {
+  int64_t nvox = 1;
+  for (int d = 0; d < D; ++d) nvox *= S[d];
+  for (int b = 0; b < B; ++b) {
+    const float* vb = vol + (size_t)b * nvox * C;
+#pragma omp parallel for schedule(static)
+    for (int64_t v = 0; v < nvox; ++v) {
+      int64_t rem = v;
+      float loc[MAXD];
+      int coord[MAXD];
+      for (int d = D - 1; d >= 0; --d) { coord[d] = (int)(rem % S[d]); rem /= S[d]; }
+      const float* f = flow + ((size_t)b * nvox + v) * D;
+      for (int d = 0; d < D; ++d) loc[d] = (float)coord[d] + f[d];
+      sample_point(vb, S, D, C, loc, method, has_fill, fill, out + ((size_t)b * nvox + v) * C);
+    }
+  }
+}
+
+/* sums[b][l][3] = {sum t*p, sum t*t, sum p*p}; double accumulation, one rounding */
+void oracle_dice_sums_f32(const float* t, const float* p, int B, int64_t V, int L, float* sums) {
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < B; ++b)
+    for (int l = 0; l < L; ++l) {
+      double tp = 0, tt = 0, pp = 0;
+      const float* tb = t + (size_t)b * V * L + l;
+      const float* pb = p + (size_t)b * V * L + l;
+      for (int64_t v = 0; v < V; ++v) {
+        const float a = tb[v * L], c = pb[v * L];
+        tp += (double)(a * c); tt += (double)(a * a); pp += (double)(c * c);
+      }
+      sums[((size_t)b * L + l) * 3 + 0] = (float)tp;
+      sums[((size_t)b * L + l) * 3 + 1] = (float)tt;
+      sums[((size_t)b * L + l) * 3 + 2] = (float)pp;
+    }
+}
+
+/* returns sum over rows of -sum_c (w_c t_c) log(clip(p_c / sum p)) as double */
+double oracle_cce_f32(const float* t, const float* p, const float* lw, int64_t n, int C) {
+  double total = 0.0;
+#pragma omp parallel for reduction(+ : total) schedule(static)
+  for (int64_t r = 0; r < n; ++r) {
+    const float* tr = t + r * C;
+    const float* pr = p + r * C;
+    double s = 0.0;
+    for (int c = 0; c < C; ++c) s += pr[c];
+    const float sf = (float)s;
+    double l = 0.0;
+    for (int c = 0; c < C; ++c) {
+      float q = pr[c] / sf;
+      q = clipf(q, 1e-7f, 1.0f - 1e-7f);
+      const float tv = lw ? lw[c] * tr[c] : tr[c];
+      l += (double)tv * log((double)q);
+    }
+    total += (double)(float)(-l);
+  }
+  return total;
+}
+
+/* x [B,I0,I1,I2,Cin], kernel [P,F,Cout], bias [P,Cout] or NULL -> out [B,P,Cout]; channels_last order */
+void oracle_lc3d_f32(const float* x, const float* kernel, const float* bias, float* out, int B, const int* I,
+                     int Cin, int Cout, const int* K, const int* St) {
+  int O[3];
+  for (int d = 0; d < 3; ++d) O[d] = (I[d] - K[d]) / St[d] + 1;
+  const int64_t P = (int64_t)O[0] * O[1] * O[2];
+  const int F = K[0] * K[1] * K[2] * Cin;
+  const int64_t xb = (int64_t)I[0] * I[1] * I[2] * Cin;
+#pragma omp parallel for schedule(static)
+  for (int64_t p = 0; p < P; ++p) {
+    const int o2 = (int)(p % O[2]), o1 = (int)((p / O[2]) % O[1]), o0 = (int)(p / ((int64_t)O[2] * O[1]));
+    const float* w = kernel + p * (int64_t)F * Cout;
+    for (int b = 0; b < B; ++b) {
+      double acc[256];
+      for (int f = 0; f < Cout; ++f) acc[f] = 0.0;
+      int j = 0;
+      for (int i0 = 0; i0 < K[0]; ++i0)
+        for (int i1 = 0; i1 < K[1]; ++i1)
+          for (int i2 = 0; i2 < K[2]; ++i2)
+            for (int c = 0; c < Cin; ++c, ++j) {
+              const float xv = x[b * xb + ((((int64_t)(o0 * St[0] + i0) * I[1]) + (o1 * St[1] + i1)) * I[2] + (o2 * St[2] + i2)) * Cin + c];
+              const float* wr = w + (int64_t)j * Cout;
+              for (int f = 0; f < Cout; ++f) acc[f] += (double)xv * (double)wr[f];
+            }
+      for (int f = 0; f < Cout; ++f) {
+        float r = (float)acc[f];
+        if (bias) r = r + bias[p * Cout + f];
+        out[((int64_t)b * P + p) * Cout + f] = r;
+      }
+    }
+  }
+}

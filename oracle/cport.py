@@ -1,0 +1,113 @@
+"""
+ctypes binding of oracle/c/liboracle.so (C99 + OpenMP restatement; TEST INFRASTRUCTURE --
+see oracle/__init__.py).  Used for full-size parity checks and as the multi-threaded CPU
+baseline in bench.py.  tests/test_oracle_c.py pins it bit-exactly to oracle/interp.py.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, 'c', 'liboracle.so')
+F32 = np.float32
+
+
+def build(force=False):
+    src = os.path.join(_HERE, 'c', 'nrt_oracle.c')
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(['make', '-s', '-C', os.path.join(_HERE, 'c')])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = ctypes.CDLL(_SO)
+        _lib.oracle_cce_f32.restype = ctypes.c_double
+        _lib.oracle_num_threads.restype = ctypes.c_int
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _ints(v):
+    return (ctypes.c_int * len(v))(*[int(x) for x in v])
+
+
+def num_threads():
+    return int(lib().oracle_num_threads())
+
+
+def warp(vol, flow, interp_method='linear', fill_value=None):
+    """vol [B,*S,C], flow [B,*S,D] -> [B,*S,C]"""
+    vol = np.ascontiguousarray(vol, dtype=F32)
+    flow = np.ascontiguousarray(flow, dtype=F32)
+    D = flow.shape[-1]
+    out = np.empty(flow.shape[:-1] + (vol.shape[-1],), dtype=F32)
+    lib().oracle_warp_f32(_p(vol), _p(flow), _p(out), ctypes.c_int(vol.shape[0]), _ints(vol.shape[1:-1]),
+                          ctypes.c_int(D), ctypes.c_int(vol.shape[-1]),
+                          ctypes.c_int(0 if interp_method == 'linear' else 1),
+                          ctypes.c_int(fill_value is not None), ctypes.c_float(fill_value or 0.0))
+    return out
+
+
+def interpn(vol, loc, interp_method='linear', fill_value=None):
+    """vol [*S, C], loc [*O, D] -> [*O, C]"""
+    vol = np.ascontiguousarray(vol, dtype=F32)
+    loc = np.ascontiguousarray(loc, dtype=F32)
+    D = loc.shape[-1]
+    out = np.empty(loc.shape[:-1] + (vol.shape[-1],), dtype=F32)
+    lib().oracle_interpn_f32(_p(vol), _ints(vol.shape[:-1]), ctypes.c_int(D), ctypes.c_int(vol.shape[-1]), _p(loc),
+                             ctypes.c_int64(loc.size // D), ctypes.c_int(0 if interp_method == 'linear' else 1),
+                             ctypes.c_int(fill_value is not None), ctypes.c_float(fill_value or 0.0), _p(out))
+    return out
+
+
+def dice_sums(t, p):
+    t = np.ascontiguousarray(t, dtype=F32)
+    p = np.ascontiguousarray(p, dtype=F32)
+    B, L = t.shape[0], t.shape[-1]
+    V = t.size // (B * L)
+    sums = np.empty((B, L, 3), dtype=F32)
+    lib().oracle_dice_sums_f32(_p(t), _p(p), ctypes.c_int(B), ctypes.c_int64(V), ctypes.c_int(L), _p(sums))
+    return sums
+
+
+def dice(t, p):
+    s = dice_sums(t, p)
+    top = F32(2) * s[..., 0]
+    bottom = s[..., 1] + s[..., 2]
+    out = np.zeros_like(top)
+    np.divide(top, bottom, out=out, where=bottom != 0)
+    return out
+
+
+def cce(t, p, label_weights=None):
+    t = np.ascontiguousarray(t, dtype=F32)
+    p = np.ascontiguousarray(p, dtype=F32)
+    C = t.shape[-1]
+    lw = None if label_weights is None else np.ascontiguousarray(label_weights, dtype=F32)
+    n = t.size // C
+    tot = lib().oracle_cce_f32(_p(t), _p(p), None if lw is None else _p(lw), ctypes.c_int64(n), ctypes.c_int(C))
+    return F32(tot / n)
+
+
+def lc3d(x, kernel, bias, kernel_size, strides=(1, 1, 1)):
+    x = np.ascontiguousarray(x, dtype=F32)
+    kernel = np.ascontiguousarray(kernel, dtype=F32)
+    B, Cin, Cout = x.shape[0], x.shape[-1], kernel.shape[-1]
+    O = [(x.shape[1 + d] - kernel_size[d]) // strides[d] + 1 for d in range(3)]
+    out = np.empty((B, O[0], O[1], O[2], Cout), dtype=F32)
+    b = None if bias is None else np.ascontiguousarray(bias, dtype=F32)
+    lib().oracle_lc3d_f32(_p(x), _p(kernel), None if b is None else _p(b), _p(out), ctypes.c_int(B),
+                          _ints(x.shape[1:4]), ctypes.c_int(Cin), ctypes.c_int(Cout), _ints(kernel_size), _ints(strides))
+    return out

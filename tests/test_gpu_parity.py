@@ -1,0 +1,327 @@
+"""
+GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything goes through the public
+python API -> ctypes -> the C ABI of libneurite_b200.so.  Checked against
+  * tests/golden/*.npz   (outputs of the reference's own source, see tools/gen_golden.py)
+  * the numpy oracle      (oracle/, same seeded inputs, incl. BASELINE.json's full 160x192x224)
+  * size-independent properties (identity warp, slab == whole, tile path == gather path).
+
+Tolerances: interpolation family is BIT-EXACT (np.array_equal) -- the kernels round every
+multiply/add separately like the reference's unfused TF ops.  Reductions (Dice, CCE, LC3D)
+use rtol 1e-5 (north_star), because TF's reduction order is unspecified.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from oracle import interp as ointerp, lc3d as olc3d, metrics as ometrics
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _fill(g):
+    f = float(g['fill'])
+    return None if np.isnan(f) else f
+
+
+@pytest.fixture(scope='module')
+def ne(cuda):
+    import neurite_b200
+    return neurite_b200
+
+
+# ------------------------------------------------------------------ golden: interpn / resize / warp
+@pytest.mark.parametrize('name', golden_names('interpn_'))
+def test_interpn_golden(ne, name):
+    g = load_golden(name)
+    loc = dev(g['loc'])
+    if '_list_' in name:
+        loc = [loc[..., d] for d in range(loc.shape[-1])]
+    fill = _fill(g) if 'fill' in g.files else None
+    out = ne.utils.interpn(dev(g['vol']), loc, str(g['method']), fill).cpu().numpy()
+    assert out.shape == g['out'].shape
+    np.testing.assert_array_equal(out, g['out'])
+
+
+@pytest.mark.parametrize('name', golden_names('resize_'))
+def test_resize_golden(ne, name):
+    g = load_golden(name)
+    z = g['zoom']
+    z = float(z) if z.ndim == 0 else [float(v) for v in z]
+    if isinstance(z, float) and z.is_integer():
+        z = int(z)
+    if name.startswith('resize_layer'):
+        out = ne.layers.Resize(z, interp_method=str(g['method']))(dev(g['x']))
+    else:
+        out = ne.utils.resize(dev(g['vol']), z, interp_method=str(g['method']))
+    np.testing.assert_array_equal(out.cpu().numpy(), g['out'])
+
+
+@pytest.mark.parametrize('name', golden_names('st_'))
+def test_spatial_transformer_golden(ne, name):
+    g = load_golden(name)
+    lay = ne.layers.SpatialTransformer(interp_method=str(g['method']), fill_value=_fill(g))
+    out = lay([dev(g['vol']), dev(g['flow'])]).cpu().numpy()
+    np.testing.assert_array_equal(out, g['out'])
+
+
+# ------------------------------------------------------------------ tiled (TMA) path vs oracle
+def _rand_case(shape, amp, seed, smooth=False):
+    rng = np.random.default_rng(seed)
+    vol = rng.standard_normal((1,) + shape + (1,)).astype(F32)
+    flow = rng.uniform(-amp, amp, (1,) + shape + (3,)).astype(F32)
+    return vol, flow
+
+
+@pytest.mark.parametrize('cfg', [0, 1, 2, 3])
+@pytest.mark.parametrize('shape,amp,halo', [((20, 40, 64), 3.0, 3), ((17, 23, 36), 6.0, 3), ((9, 16, 32), 2.0, 5),
+                                            ((33, 18, 100), 3.0, 0)])
+@pytest.mark.parametrize('method,fill', [('linear', None), ('linear', -2.5), ('nearest', 0.0)])
+def test_warp_tile_configs_bit_exact(ne, monkeypatch, cfg, shape, amp, halo, method, fill):
+    monkeypatch.setenv('NRT_WARP_TILE_CFG', str(cfg))
+    vol, flow = _rand_case(shape, amp, seed=cfg)
+    flow[0, 0, 0, :4] = [[0, 0, 0], [0.5, 1.5, -0.5], [-40, 50, 3], [1, 1, 1]]
+    ref = ointerp.spatial_transformer(vol, flow, method, 'ij', fill)
+    lay = ne.layers.SpatialTransformer(interp_method=method, fill_value=fill, halo=halo)
+    out = lay([dev(vol), dev(flow)]).cpu().numpy()
+    np.testing.assert_array_equal(out, ref)
+    monkeypatch.setenv('NRT_WARP_TILE', '0')                 # generic gather kernel
+    out2 = lay([dev(vol), dev(flow)]).cpu().numpy()
+    np.testing.assert_array_equal(out2, ref)
+
+
+def test_warp_batch_and_channels(ne):
+    rng = np.random.default_rng(5)
+    for C in (1, 2, 4, 16):
+        vol = rng.standard_normal((3, 12, 16, 32, C)).astype(F32)
+        flow = rng.uniform(-3, 3, (3, 12, 16, 32, 3)).astype(F32)
+        ref = ointerp.spatial_transformer(vol, flow)
+        out = ne.layers.SpatialTransformer()([dev(vol), dev(flow)]).cpu().numpy()
+        np.testing.assert_array_equal(out, ref)
+    # xy indexing swaps the first two shift channels
+    vol = rng.standard_normal((1, 8, 9, 12, 1)).astype(F32)
+    flow = rng.uniform(-2, 2, (1, 8, 9, 12, 3)).astype(F32)
+    ref = ointerp.spatial_transformer(vol, flow, indexing='xy')
+    out = ne.layers.SpatialTransformer(indexing='xy')([dev(vol), dev(flow)]).cpu().numpy()
+    np.testing.assert_array_equal(out, ref)
+
+
+def test_warp_full_size_cfg2_bit_exact_vs_oracle(ne):
+    """BASELINE.json configs[1]: 160x192x224 fp32, random dense flow (SURVEY.md 8d seeds)."""
+    S = (160, 192, 224)
+    vol = np.random.default_rng(0).standard_normal((1,) + S + (1,)).astype(F32)
+    flow = np.random.default_rng(1).uniform(-3, 3, (1,) + S + (3,)).astype(F32)
+    dv, df = dev(vol), dev(flow)
+    out = ne.layers.SpatialTransformer()([dv, df])
+    ref = ointerp.spatial_transformer(vol, flow)
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    # identity warp returns the input bit for bit
+    ident = ne.layers.SpatialTransformer()([dv, torch.zeros_like(df)])
+    assert torch.equal(ident, dv)
+    # the reference's in-repo usage: nearest + fill 0 on label maps (models.py:806-809)
+    lab = np.random.default_rng(2).integers(0, 16, vol.shape).astype(F32)
+    out = ne.layers.SpatialTransformer(interp_method='nearest', fill_value=0)([dev(lab), df]).cpu().numpy()
+    np.testing.assert_array_equal(out, ointerp.spatial_transformer(lab, flow, 'nearest', 'ij', 0))
+
+
+def test_warp_slabs_equal_whole(ne):
+    """z-slab sharding arithmetic on one GPU: each 'rank' warps its slab against only the
+    source window it would hold; concatenation == whole-volume warp, bit for bit."""
+    from neurite_b200 import dist as nd, utils
+    rng = np.random.default_rng(7)
+    S = (24, 20, 32)
+    vol = dev(rng.standard_normal((2,) + S + (1,)).astype(F32))
+    flow = dev(rng.uniform(-3, 3, (2,) + S + (3,)).astype(F32))
+    whole = utils._warp_batched(vol, flow)
+    for world in (2, 3, 8):
+        parts = []
+        for r in range(world):
+            z0, nz = nd.slab_bounds(S[0], world, r)
+            h = nd.required_halo(flow[:, z0:z0 + nz])
+            lo, hi = nd.source_window(z0, nz, h, S[0])
+            err = torch.zeros(1, dtype=torch.int32, device='cuda')
+            parts.append(utils._warp_batched(vol[:, lo:hi].contiguous(), flow[:, z0:z0 + nz].contiguous(),
+                                             src_z0=lo, full_s0=S[0], out_z0=z0, err_flag=err))
+            assert int(err.item()) == 0
+        assert torch.equal(torch.cat(parts, 1), whole)
+    # a window that is too small is reported, not silently wrong
+    err = torch.zeros(1, dtype=torch.int32, device='cuda')
+    utils._warp_batched(vol[:, 8:12].contiguous(), flow[:, 8:12].contiguous() * 4, src_z0=8, full_s0=S[0], out_z0=8,
+                        err_flag=err)
+    assert int(err.item()) == 1
+
+
+def test_resize_full_size_and_slabs(ne):
+    from neurite_b200 import utils
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((1, 80, 96, 112, 3)).astype(F32)           # half-res flow -> full res (models.py:803-804)
+    out = ne.layers.Resize(2)(dev(x))
+    assert tuple(out.shape) == (1, 160, 192, 224, 3)
+    ref = ointerp.resize_layer(x, 2)
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    a = utils._resize_batched(dev(x), [2, 2, 2], 'linear', out_z0=0, out_n0=70)
+    b = utils._resize_batched(dev(x), [2, 2, 2], 'linear', out_z0=70, out_n0=90)
+    assert torch.equal(torch.cat([a, b], 1), out)
+
+
+# ------------------------------------------------------------------ Dice / CCE
+@pytest.mark.parametrize('name', ['dice_soft_default', 'dice_soft_laplace_weights', 'dice_soft_normalize',
+                                  'dice_hard_prob', 'dice_hard_max_label', 'dice_soft_disjoint_L5'])
+def test_dice_golden(ne, name):
+    import warnings
+    g = load_golden(name)
+    kw = {}
+    if name == 'dice_soft_laplace_weights':
+        kw = dict(weights=g['weights'], laplace_smoothing=0.1)
+    elif name == 'dice_soft_normalize':
+        kw = dict(normalize=True)
+    elif name == 'dice_hard_prob':
+        kw = dict(dice_type='hard', input_type='prob')
+    elif name == 'dice_hard_max_label':
+        kw = dict(dice_type='hard', input_type='max_label', nb_labels=int(g['nb_labels']))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        d = ne.losses.Dice(**kw)
+        t, p = dev(g['y_true']), dev(g['y_pred'])
+        np.testing.assert_allclose(d.dice(t, p).cpu().numpy(), g['dice'], rtol=1e-5, atol=1e-7)
+        for k, fn in (('loss', d.loss), ('mean_dice', d.mean_dice), ('mean_loss', d.mean_loss)):
+            if k in g.files:
+                np.testing.assert_allclose(fn(t, p).cpu().numpy(), g[k], rtol=1e-5, atol=1e-7)
+
+
+def test_dice_range_check_and_properties(ne):
+    g = load_golden('dice_range_error')
+    with pytest.raises(ne.metrics.InvalidArgumentError, match='value outside range'):
+        ne.losses.Dice().dice(dev(g['y_true']), dev(g['y_pred']))
+    ne.losses.Dice(check_input_limits=False).dice(dev(g['y_true']), dev(g['y_pred']))
+    nan = g['y_pred'].copy()
+    nan[0, 0, 0, 0, 0] = np.nan
+    with pytest.raises(ne.metrics.InvalidArgumentError):
+        ne.losses.Dice().dice(dev(g['y_true']), dev(nan))
+    rng = np.random.default_rng(0)
+    for L in (1, 3, 4, 5, 8, 16, 20, 64):
+        lab = rng.integers(0, L, (2, 7, 9, 11))
+        t = np.eye(L, dtype=F32)[lab]
+        p = rng.uniform(0, 1, t.shape).astype(F32)
+        d = ne.losses.Dice()
+        one = d.dice(dev(t), dev(t)).cpu().numpy()
+        present = np.stack([[np.any(lab[b] == l) for l in range(L)] for b in range(2)])
+        np.testing.assert_array_equal(one, present.astype(F32))          # Dice(x,x) = 1, absent label 0/0 -> 0
+        a = d.dice(dev(t), dev(p)).cpu().numpy()
+        np.testing.assert_allclose(a, d.dice(dev(p), dev(t)).cpu().numpy(), rtol=1e-6)     # symmetric
+        np.testing.assert_allclose(a, ometrics.Dice().dice(t, p), rtol=1e-5, atol=1e-7)
+
+
+def test_dice_cfg3_scale_vs_oracle(ne):
+    """cfg 3 shape per batch item (16 labels on 160x192x224), batch 1 to keep the oracle in seconds."""
+    rng = np.random.default_rng(3)
+    S, L = (160, 192, 224), 16
+    lab = rng.integers(0, L, (1,) + S)
+    t = torch.nn.functional.one_hot(torch.from_numpy(lab).cuda(), L).float()
+    logits = torch.randn((1,) + S + (L,), device='cuda', generator=torch.Generator('cuda').manual_seed(1))
+    p = torch.softmax(logits, -1)
+    d = ne.losses.Dice()
+    out = d.loss(t, p).cpu().numpy()
+    tt, pp = t.cpu().numpy(), p.cpu().numpy()
+    ref = ometrics.Dice().loss(tt, pp)
+    np.testing.assert_allclose(out, ref, rtol=1e-5)
+    np.testing.assert_allclose(float(d.mean_loss(t, p)), ometrics.Dice().mean_loss(tt, pp), rtol=1e-5)
+    c = ne.losses.CategoricalCrossentropy(label_weights=np.linspace(0.5, 2, L))
+    np.testing.assert_allclose(float(c.loss(t, p)),
+                               ometrics.categorical_crossentropy(tt, pp, np.linspace(0.5, 2, L).astype(F32)), rtol=1e-5)
+
+
+@pytest.mark.parametrize('name', ['cce_label_weights', 'cce_plain'])
+def test_cce_golden(ne, name):
+    g = load_golden(name)
+    lw = g['label_weights'] if 'label_weights' in g.files else None
+    c = ne.losses.CategoricalCrossentropy(label_weights=lw)
+    np.testing.assert_allclose(float(c.loss(dev(g['y_true']), dev(g['y_pred']))), g['loss'], rtol=1e-5)
+
+
+def test_cce_variants_vs_oracle(ne):
+    rng = np.random.default_rng(11)
+    for C in (2, 3, 4, 5, 16, 32, 128):
+        t = np.eye(C, dtype=F32)[rng.integers(0, C, (2, 6, 7))]
+        p = rng.uniform(0.01, 1, t.shape).astype(F32)
+        lw = rng.uniform(0.5, 2, C).astype(F32)
+        sw = rng.uniform(0.5, 2, t.shape[:-1]).astype(F32)
+        for kw in (dict(), dict(label_weights=lw), dict(label_weights=lw, sample_weight=sw),
+                   dict(from_logits=True), dict(label_smoothing=0.1), dict(reduction='sum')):
+            okw = dict(kw)
+            sample = okw.pop('sample_weight', None)
+            ref = ometrics.categorical_crossentropy(t, p, sample_weight=sample, **okw)
+            ckw = {k: v for k, v in okw.items()}
+            c = ne.losses.CategoricalCrossentropy(**ckw)
+            out = c(dev(t), dev(p), sample_weight=None if sample is None else dev(sample))
+            np.testing.assert_allclose(float(out), ref, rtol=2e-5)
+        per = ne.losses.CategoricalCrossentropy(reduction='none')(dev(t), dev(p)).cpu().numpy()
+        np.testing.assert_allclose(per, ometrics.categorical_crossentropy(t, p, reduction='none'), rtol=2e-5, atol=1e-6)
+    one = np.eye(3, dtype=F32)[[0, 1, 2, 1]][None]
+    np.testing.assert_allclose(float(ne.losses.CategoricalCrossentropy()(dev(one), dev(one))), -np.log(1 - 1e-7),
+                               rtol=1e-3, atol=2e-7)
+
+
+# ------------------------------------------------------------------ LocallyConnected3D
+@pytest.mark.parametrize('generic', [False, True])
+@pytest.mark.parametrize('name', golden_names('lc3d_'))
+def test_lc3d_golden(ne, monkeypatch, name, generic):
+    if generic:
+        monkeypatch.setenv('NRT_LC3D_GENERIC', '1')
+    g = load_golden(name)
+    fmt = str(g['data_format'])
+    use_bias = bool(g['bias'].size)
+    lay = ne.layers.LocallyConnected3D(int(g['filters']), tuple(int(k) for k in g['kernel_size']),
+                                       strides=tuple(int(s) for s in g['strides']), data_format=fmt, use_bias=use_bias)
+    lay.build(g['x'].shape)
+    assert tuple(lay.kernel.shape) == g['kernel'].shape
+    with torch.no_grad():
+        lay.kernel.copy_(torch.from_numpy(g['kernel']))
+        if use_bias:
+            lay.bias.copy_(torch.from_numpy(g['bias']))
+    lay.cuda()
+    out = lay(dev(g['x'])).cpu().numpy()
+    assert out.shape == g['out'].shape
+    np.testing.assert_allclose(out, g['out'], rtol=1e-5, atol=2e-5)
+
+
+def test_lc3d_vs_oracle_batches_activations_and_sharding(ne):
+    from neurite_b200.layers import local_conv3d
+    rng = np.random.default_rng(13)
+    x = rng.standard_normal((11, 8, 9, 10, 16)).astype(F32)
+    O = (6, 7, 8)
+    kernel = (rng.standard_normal((int(np.prod(O)), 27 * 16, 16)) * 0.05).astype(F32)
+    bias = rng.standard_normal(O + (16,)).astype(F32)
+    for act in (None, 'relu', 'tanh', 'sigmoid'):
+        ref = olc3d.locally_connected_3d(x, kernel, bias, (3, 3, 3), activation=act, literal=False)
+        out = local_conv3d(dev(x), dev(kernel), dev(bias), (3, 3, 3), (1, 1, 1), O, activation=act).cpu().numpy()
+        np.testing.assert_allclose(out, ref, rtol=1e-5, atol=2e-5)
+    # position sharding: two ranks each own half of the positions AND of the weights
+    ref = olc3d.locally_connected_3d(x, kernel, bias, (3, 3, 3), literal=False).reshape(11, -1, 16)
+    P = kernel.shape[0]
+    h = P // 2 + 3
+    a = local_conv3d(dev(x), dev(kernel[:h]), dev(bias.reshape(-1, 16)[:h]), (3, 3, 3), (1, 1, 1), O, p0=0, p_count=h)
+    b = local_conv3d(dev(x), dev(kernel[h:]), dev(bias.reshape(-1, 16)[h:]), (3, 3, 3), (1, 1, 1), O, p0=h, p_count=P - h)
+    np.testing.assert_allclose(torch.cat([a, b], 1).cpu().numpy(), ref, rtol=1e-5, atol=2e-5)
+
+
+def test_lc3d_shared_weights_equal_conv3d_cfg4_shape(ne):
+    """cfg 4 geometry (3^3 kernel, 16->16) on a 24^3 crop: with position-shared weights the
+    layer must equal a plain conv3d (independent implementation: cuDNN through torch)."""
+    rng = np.random.default_rng(17)
+    x = torch.from_numpy(rng.standard_normal((2, 24, 24, 24, 16)).astype(F32)).cuda()
+    w = torch.from_numpy((rng.standard_normal((3, 3, 3, 16, 16)) * 0.1).astype(F32)).cuda()
+    P = 22 ** 3
+    kernel = w.reshape(1, 432, 16).expand(P, 432, 16).contiguous()
+    from neurite_b200.layers import local_conv3d
+    out = local_conv3d(x, kernel, None, (3, 3, 3), (1, 1, 1), (22, 22, 22))
+    torch.backends.cudnn.allow_tf32 = False
+    ref = torch.nn.functional.conv3d(x.permute(0, 4, 1, 2, 3), w.permute(4, 3, 0, 1, 2)).permute(0, 2, 3, 4, 1)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=1e-4)
