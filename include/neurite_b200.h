@@ -152,6 +152,47 @@ NRT_API int nrt_lc3d_fwd_f32(const float* x, const float* kernel, const float* b
                      const int32_t* ksize, const int32_t* strides, int feature_order,
                      int activation, int64_t p0, int64_t p_count, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Gradients.  The reference obtains them from TensorFlow autodiff of
+ * the op graphs cited above; these entry points are that graph differentiated by hand
+ * (floor/round: zero gradient; clip_by_value: passes on the closed interval; gather:
+ * scatter-add).  grad_vol buffers are ACCUMULATED into (atomics) -- zero them first.
+ * Whole volumes only (no slab arguments).
+ * ------------------------------------------------------------------------------------- */
+/* backward of nrt_warp_f32: grad_out [B,S..,C] -> grad_vol [B,S..,C] (may be null),
+ * grad_flow [B,S..,D] (may be null; zeros for NRT_NEAREST) */
+NRT_API int nrt_warp_bwd_f32(const float* vol, const float* flow, const float* grad_out, float* grad_vol,
+                     float* grad_flow, int B, const int32_t* shape, int D, int C, int method,
+                     int has_fill, void* stream);
+/* backward of nrt_interpn_f32: grad_out [n_out,C] -> grad_vol [S..,C], grad_loc [n_out,D] */
+NRT_API int nrt_interpn_bwd_f32(const float* vol, const int32_t* vol_shape, int D, int C, const float* loc,
+                        int64_t n_out, int method, int has_fill, const float* grad_out,
+                        float* grad_vol, float* grad_loc, void* stream);
+/* backward of nrt_resize_f32 (sample positions are constants): grad_out [B,M..,C] -> grad_vol [B,S..,C] */
+NRT_API int nrt_resize_bwd_f32(const float* grad_out, float* grad_vol, int B, const int32_t* in_shape,
+                       const int32_t* out_shape, int D, int C, int method, void* stream);
+/* backward of Dice.dice: given sums [B,L,3] from nrt_dice_sums_f32 and grad_dice [B,L],
+ * grad_pred = a*t - c*p, grad_true = a*p - c*t with a = 2G/(bot+eps), c = 2G(top+eps)/(bot+eps)^2
+ * (both 0 where bot == 0 and eps == 0: divide_no_nan).  Either output may be null. */
+NRT_API int nrt_dice_bwd_f32(const float* y_true, const float* y_pred, const float* sums,
+                     const float* grad_dice, int B, int64_t V, int L, float laplace,
+                     float* grad_true, float* grad_pred, void* stream);
+/* backward of nrt_cce_f32 wrt y_pred: upstream = scale * (*grad_scalar if non-null) *
+ * (grad_per_elem[r] if non-null) * sample_w[r]. */
+NRT_API int nrt_cce_bwd_f32(const float* y_true, const float* y_pred, const float* label_w,
+                    const float* sample_w, int64_t n, int C, int from_logits, float label_smoothing,
+                    const float* grad_scalar, float scale, const float* grad_per_elem,
+                    float* grad_pred, void* stream);
+
+/* backward of nrt_lc3d_fwd_f32 (linear activation; apply the activation's derivative to
+ * grad_out first): grad_out [B,p_count,Cout] -> grad_kernel [p_count,F,Cout] (overwritten),
+ * grad_x [B,I0,I1,I2,Cin] (ACCUMULATED: overlapping patches, zero it first).  Either may be
+ * null.  grad_bias[p,f] = sum_b grad_out[b,p,f] is left to the caller. */
+NRT_API int nrt_lc3d_bwd_f32(const float* x, const float* kernel, const float* grad_out, float* grad_x,
+                     float* grad_kernel, int B, const int32_t* in_shape, int Cin, int Cout,
+                     const int32_t* ksize, const int32_t* strides, int feature_order,
+                     int64_t p0, int64_t p_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

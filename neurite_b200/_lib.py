@@ -38,9 +38,21 @@ SIGNATURES = {
     'nrt_cce_workspace_bytes': (c_i64, []),
     'nrt_cce_f32': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_f32,
                                     c_vp, c_vp, c_vp, c_i64, c_vp]),
+    'nrt_warp_bwd_f32': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, P_I32, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_int, c_vp]),
+    'nrt_interpn_bwd_f32': (ctypes.c_int, [c_vp, P_I32, ctypes.c_int, ctypes.c_int, c_vp, c_i64, ctypes.c_int,
+                                            ctypes.c_int, c_vp, c_vp, c_vp, c_vp]),
+    'nrt_resize_bwd_f32': (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, P_I32, P_I32, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, c_vp]),
+    'nrt_dice_bwd_f32': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_i64, ctypes.c_int, c_f32,
+                                         c_vp, c_vp, c_vp]),
+    'nrt_cce_bwd_f32': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_f32,
+                                        c_vp, c_f32, c_vp, c_vp, c_vp]),
     'nrt_lc3d_fwd_f32': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, P_I32, ctypes.c_int,
                                          ctypes.c_int, P_I32, P_I32, ctypes.c_int, ctypes.c_int,
                                          c_i64, c_i64, c_vp]),
+    'nrt_lc3d_bwd_f32': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, P_I32, ctypes.c_int,
+                                         ctypes.c_int, P_I32, P_I32, ctypes.c_int, c_i64, c_i64, c_vp]),
 }
 
 

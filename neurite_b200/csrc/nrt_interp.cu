@@ -57,11 +57,15 @@ __device__ __forceinline__ bool out_of_bounds(const Geo& g, const float (&loc)[D
   return oob;
 }
 
-// One output point, channels [c0, c0+VEC) -- generic global-memory gather.
-template <int D, int VEC, int METHOD>
-__device__ __forceinline__ void sample_point(const float* __restrict__ vol, const Geo& g,
-                                             const float (&loc)[D], int c0, float (&res)[VEC]) {
-  constexpr int NC = 1 << D;
+// Corner indices (flat, resident) and weights of one output point.
+template <int D, int METHOD>
+struct Corners {
+  int idx[METHOD == NRT_LINEAR ? (1 << D) : 1];
+  float w[METHOD == NRT_LINEAR ? (1 << D) : 1];
+};
+
+template <int D, int METHOD>
+__device__ __forceinline__ void setup_point(const Geo& g, const float (&loc)[D], Corners<D, METHOD>& k) {
   if (METHOD == NRT_LINEAR) {
     Axis a[D];
 #pragma unroll
@@ -69,9 +73,7 @@ __device__ __forceinline__ void sample_point(const float* __restrict__ vol, cons
     a[0].i0 = to_resident(g, a[0].i0);
     a[0].i1 = to_resident(g, a[0].i1);
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) res[v] = 0.0f;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
+    for (int c = 0; c < (1 << D); ++c) {
       int sub[D];
       float w = 0.f;
 #pragma unroll
@@ -81,7 +83,30 @@ __device__ __forceinline__ void sample_point(const float* __restrict__ vol, cons
         const float wd = bit ? a[d].whi : a[d].wlo;
         w = (d == 0) ? wd : __fmul_rn(w, wd);             // prod_n: ((w0*w1)*w2)
       }
-      const size_t off = (size_t)flat_index<D>(g, sub) * g.C + c0;
+      k.idx[c] = flat_index<D>(g, sub);
+      k.w[c] = w;
+    }
+  } else {
+    int sub[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) sub[d] = axis_nearest(loc[d], g.S[d] - 1);
+    sub[0] = to_resident(g, sub[0]);
+    k.idx[0] = flat_index<D>(g, sub);
+    k.w[0] = 1.f;
+  }
+}
+
+// channels [c0, c0+VEC) of one point from precomputed corners -- global-memory gather
+template <int D, int VEC, int METHOD>
+__device__ __forceinline__ void gather_point(const float* __restrict__ vol, const Geo& g,
+                                             const Corners<D, METHOD>& k, bool oob, int c0, float (&res)[VEC]) {
+  if (METHOD == NRT_LINEAR) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) res[v] = 0.0f;
+#pragma unroll
+    for (int c = 0; c < (1 << D); ++c) {
+      const size_t off = (size_t)k.idx[c] * g.C + c0;
+      const float w = k.w[c];
       if (VEC == 4) {
         const float4 q = __ldg(reinterpret_cast<const float4*>(vol + off));
         res[0] = __fadd_rn(res[0], __fmul_rn(w, q.x));
@@ -93,11 +118,7 @@ __device__ __forceinline__ void sample_point(const float* __restrict__ vol, cons
       }
     }
   } else {
-    int sub[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) sub[d] = axis_nearest(loc[d], g.S[d] - 1);
-    sub[0] = to_resident(g, sub[0]);
-    const size_t off = (size_t)flat_index<D>(g, sub) * g.C + c0;
+    const size_t off = (size_t)k.idx[0] * g.C + c0;
     if (VEC == 4) {
       const float4 q = __ldg(reinterpret_cast<const float4*>(vol + off));
       res[0] = q.x; res[1 % VEC] = q.y; res[2 % VEC] = q.z; res[3 % VEC] = q.w;
@@ -106,16 +127,30 @@ __device__ __forceinline__ void sample_point(const float* __restrict__ vol, cons
     }
   }
   if (g.has_fill) {
-    const bool oob = out_of_bounds<D>(g, loc);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) res[v] = apply_fill(res[v], oob, g.fill);
   }
 }
 
-template <int VEC>
-__device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&r)[VEC]) {
-  if (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]);
-  else p[0] = r[0];
+// One output point: VEC == 4 -> this thread's 4-channel chunk [c0, c0+4);
+//                   VEC == 1 -> all C channels (corner setup is done once per point).
+template <int D, int VEC, int METHOD>
+__device__ __forceinline__ void sample_store(const float* __restrict__ vol, const Geo& g,
+                                             const float (&loc)[D], int c0, float* __restrict__ dst) {
+  Corners<D, METHOD> k;
+  setup_point<D, METHOD>(g, loc, k);
+  const bool oob = g.has_fill ? out_of_bounds<D>(g, loc) : false;
+  if (VEC == 4) {
+    float r[VEC];
+    gather_point<D, VEC, METHOD>(vol, g, k, oob, c0, r);
+    *reinterpret_cast<float4*>(dst + c0) = make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]);
+  } else {
+    for (int c = 0; c < g.C; ++c) {
+      float r[VEC];
+      gather_point<D, VEC, METHOD>(vol, g, k, oob, c, r);
+      dst[c] = r[0];
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -125,7 +160,7 @@ template <int D, int VEC, int METHOD>
 __global__ void __launch_bounds__(256)
 interpn_kernel(const float* __restrict__ vol, Geo g, const float* __restrict__ loc_t,
                int64_t n_out, float* __restrict__ out) {
-  const int cv_n = g.C / VEC;
+  const int cv_n = VEC == 4 ? g.C / 4 : 1;
   const int64_t total = n_out * cv_n;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -134,9 +169,7 @@ interpn_kernel(const float* __restrict__ vol, Geo g, const float* __restrict__ l
     float loc[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) loc[d] = __ldg(loc_t + pt * D + d);
-    float r[VEC];
-    sample_point<D, VEC, METHOD>(vol, g, loc, c0, r);
-    store_vec<VEC>(out + pt * g.C + c0, r);
+    sample_store<D, VEC, METHOD>(vol, g, loc, c0, out + pt * g.C);
   }
 }
 
@@ -152,7 +185,7 @@ __global__ void __launch_bounds__(256)
 warp_generic_kernel(const float* __restrict__ vol, const float* __restrict__ flow,
                     float* __restrict__ out, WarpGeo w) {
   const Geo& g = w.g;
-  const int cv_n = g.C / VEC;
+  const int cv_n = VEC == 4 ? g.C / 4 : 1;
   const int64_t total = (int64_t)w.B * w.out_vox * cv_n;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -167,9 +200,7 @@ warp_generic_kernel(const float* __restrict__ vol, const float* __restrict__ flo
     float loc[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) loc[d] = __fadd_rn((float)coord[d], __ldg(flow + pv * D + d));
-    float r[VEC];
-    sample_point<D, VEC, METHOD>(vol + (size_t)b * w.src_batch_stride, g, loc, c0, r);
-    store_vec<VEC>(out + pv * g.C + c0, r);
+    sample_store<D, VEC, METHOD>(vol + (size_t)b * w.src_batch_stride, g, loc, c0, out + pv * g.C);
   }
 }
 
@@ -186,7 +217,7 @@ template <int D, int VEC, int METHOD>
 __global__ void __launch_bounds__(256)
 resize_kernel(const float* __restrict__ vol, float* __restrict__ out, ResizeGeo w) {
   const Geo& g = w.g;
-  const int cv_n = g.C / VEC;
+  const int cv_n = VEC == 4 ? g.C / 4 : 1;
   const int64_t total = (int64_t)w.B * w.out_vox * cv_n;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -205,9 +236,7 @@ resize_kernel(const float* __restrict__ vol, float* __restrict__ out, ResizeGeo 
       const int i = coord[d];
       loc[d] = (i == w.M[d] - 1 && w.M[d] > 1) ? (float)(g.S[d] - 1) : __fmul_rn(w.delta[d], (float)i);
     }
-    float r[VEC];
-    sample_point<D, VEC, METHOD>(vol + (size_t)b * w.src_batch_stride, g, loc, c0, r);
-    store_vec<VEC>(out + pv * g.C + c0, r);
+    sample_store<D, VEC, METHOD>(vol + (size_t)b * w.src_batch_stride, g, loc, c0, out + pv * g.C);
   }
 }
 
@@ -218,128 +247,291 @@ struct TileGeo {
   Geo g;                 // S = {full_s0, H, W}
   int out_z0, out_n0;
   int B;
-  int BZ, BY, BX;        // source box extent (elements)
-  int hz, hy, hx;        // box origin = tile origin - h
   int ntz, nty, ntx;     // tiles per axis
   int64_t src_batch_stride, out_vox;
 };
 
-template <int TZ, int TY, int METHOD>
+// Compile-time tile / box geometry.  HZ = HY = HALO; the x halo is rounded up to 4 voxels
+// because the TMA needs the innermost start coordinate 16-byte aligned.
+template <int TZ, int TY, int HALO>
+struct TileCfg {
+  static constexpr int TX = 32, NW = 8;
+  static constexpr int HX = (HALO + 3) & ~3;
+  static constexpr int BZ = TZ + 2 * HALO, BY = TY + 2 * HALO, BX = TX + 2 * HX;
+  static constexpr int ROWS = TY / NW;                  // rows of 32 voxels per warp per plane
+  static constexpr int FLOW_ELEMS = TZ * TY * TX * 3, BOX_ELEMS = BZ * BY * BX;
+  static constexpr size_t SMEM = (size_t)(FLOW_ELEMS + BOX_ELEMS) * sizeof(float) + 16;
+  static_assert(TY % NW == 0, "TY must be a multiple of the warp count");
+  static_assert(BX <= 256 && BY <= 256 && BZ <= 256, "TMA box limit");
+};
+
+// the 8 corner products and the accumulation, in the reference's order (utils.py:159-191)
+__device__ __forceinline__ float trilerp(const float (&v)[8], float wz0, float wz1, float wy0, float wy1,
+                                         float wx0, float wx1) {
+  const float w00 = __fmul_rn(wz0, wy0), w01 = __fmul_rn(wz0, wy1);
+  const float w10 = __fmul_rn(wz1, wy0), w11 = __fmul_rn(wz1, wy1);
+  float r = __fadd_rn(0.f, __fmul_rn(__fmul_rn(w00, wx0), v[0]));
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(w00, wx1), v[1]));
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(w01, wx0), v[2]));
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(w01, wx1), v[3]));
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(w10, wx0), v[4]));
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(w10, wx1), v[5]));
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(w11, wx0), v[6]));
+  r = __fadd_rn(r, __fmul_rn(__fmul_rn(w11, wx1), v[7]));
+  return r;
+}
+
+// general (any position, any flow) sample through global memory -- the semantics baseline
+template <int METHOD>
+__device__ __forceinline__ float sample_global3(const float* __restrict__ volb, const Geo& g,
+                                                float lz, float ly, float lx) {
+  if (METHOD == NRT_LINEAR) {
+    Axis az = axis_linear(lz, (float)(g.S[0] - 1), g.S[0] - 1);
+    const Axis ay = axis_linear(ly, (float)(g.S[1] - 1), g.S[1] - 1);
+    const Axis ax = axis_linear(lx, (float)(g.S[2] - 1), g.S[2] - 1);
+    az.i0 = to_resident(g, az.i0);
+    az.i1 = to_resident(g, az.i1);
+    const int r00 = (az.i0 * g.S[1] + ay.i0) * g.S[2], r01 = (az.i0 * g.S[1] + ay.i1) * g.S[2];
+    const int r10 = (az.i1 * g.S[1] + ay.i0) * g.S[2], r11 = (az.i1 * g.S[1] + ay.i1) * g.S[2];
+    float v[8];
+    v[0] = __ldg(volb + r00 + ax.i0); v[1] = __ldg(volb + r00 + ax.i1);
+    v[2] = __ldg(volb + r01 + ax.i0); v[3] = __ldg(volb + r01 + ax.i1);
+    v[4] = __ldg(volb + r10 + ax.i0); v[5] = __ldg(volb + r10 + ax.i1);
+    v[6] = __ldg(volb + r11 + ax.i0); v[7] = __ldg(volb + r11 + ax.i1);
+    return trilerp(v, az.wlo, az.whi, ay.wlo, ay.whi, ax.wlo, ax.whi);
+  } else {
+    const int iz = to_resident(g, axis_nearest(lz, g.S[0] - 1));
+    const int iy = axis_nearest(ly, g.S[1] - 1), ix = axis_nearest(lx, g.S[2] - 1);
+    return __ldg(volb + (iz * g.S[1] + iy) * g.S[2] + ix);
+  }
+}
+
+// one voxel from a box that lies fully inside the resident volume: no clipping needed
+template <int BX, int BY, int BZ, int METHOD>
+__device__ __forceinline__ float sample_box_interior(const float* __restrict__ s_box, int oz, int oy, int ox,
+                                                     const float* __restrict__ volb, const Geo& g,
+                                                     float lz, float ly, float lx) {
+  if (METHOD == NRT_LINEAR) {
+    const int iz = __float2int_rd(lz), iy = __float2int_rd(ly), ix = __float2int_rd(lx);
+    const unsigned rz = (unsigned)(iz - oz), ry = (unsigned)(iy - oy), rx = (unsigned)(ix - ox);
+    if ((rz < (unsigned)(BZ - 1)) & (ry < (unsigned)(BY - 1)) & (rx < (unsigned)(BX - 1))) {
+      // inside an interior box 0 <= loc < max on every axis, so clip() is the identity and
+      // i1 = i0 + 1: same values as axis_linear, without the min/max chain
+      const float wz0 = __fsub_rn(__fadd_rn((float)iz, 1.f), lz), wz1 = __fsub_rn(1.f, wz0);
+      const float wy0 = __fsub_rn(__fadd_rn((float)iy, 1.f), ly), wy1 = __fsub_rn(1.f, wy0);
+      const float wx0 = __fsub_rn(__fadd_rn((float)ix, 1.f), lx), wx1 = __fsub_rn(1.f, wx0);
+      const float* p = s_box + ((int)rz * BY + (int)ry) * BX + (int)rx;
+      float v[8];
+      v[0] = p[0];            v[1] = p[1];
+      v[2] = p[BX];           v[3] = p[BX + 1];
+      v[4] = p[BY * BX];      v[5] = p[BY * BX + 1];
+      v[6] = p[BY * BX + BX]; v[7] = p[BY * BX + BX + 1];
+      return trilerp(v, wz0, wz1, wy0, wy1, wx0, wx1);
+    }
+    return sample_global3<METHOD>(volb, g, lz, ly, lx);
+  } else {
+    const int iz = __float2int_rn(lz), iy = __float2int_rn(ly), ix = __float2int_rn(lx);
+    const unsigned rz = (unsigned)(iz - oz), ry = (unsigned)(iy - oy), rx = (unsigned)(ix - ox);
+    if ((rz < (unsigned)BZ) & (ry < (unsigned)BY) & (rx < (unsigned)BX))
+      return s_box[((int)rz * BY + (int)ry) * BX + (int)rx];
+    return sample_global3<METHOD>(volb, g, lz, ly, lx);
+  }
+}
+
+// one voxel from a box that overhangs the volume / the resident planes (zero-filled by the
+// TMA there, never read): clip first, then test against the valid part of the box
+struct BoxBounds { int lo_z, hi_z, lo_y, hi_y, lo_x, hi_x; };
+
+template <int BX, int BY, int BZ, int METHOD>
+__device__ __forceinline__ float sample_box_border(const float* __restrict__ s_box, int oz, int oy, int ox,
+                                                   const BoxBounds& bb, const float* __restrict__ volb,
+                                                   const Geo& g, float lz, float ly, float lx) {
+  if (METHOD == NRT_LINEAR) {
+    const float mz = (float)(g.S[0] - 1), my = (float)(g.S[1] - 1), mx = (float)(g.S[2] - 1);
+    const float cz = fminf(fmaxf(lz, 0.f), mz), cy = fminf(fmaxf(ly, 0.f), my), cx = fminf(fmaxf(lx, 0.f), mx);
+    const float f0z = floorf(cz), f0y = floorf(cy), f0x = floorf(cx);
+    const int iz = __float2int_rz(f0z), iy = __float2int_rz(f0y), ix = __float2int_rz(f0x);
+    if ((iz >= bb.lo_z) & (iz < bb.hi_z) & (iy >= bb.lo_y) & (iy < bb.hi_y) & (ix >= bb.lo_x) & (ix < bb.hi_x)) {
+      const float wz0 = __fsub_rn(__fadd_rn(f0z, 1.f), cz), wz1 = __fsub_rn(1.f, wz0);
+      const float wy0 = __fsub_rn(__fadd_rn(f0y, 1.f), cy), wy1 = __fsub_rn(1.f, wy0);
+      const float wx0 = __fsub_rn(__fadd_rn(f0x, 1.f), cx), wx1 = __fsub_rn(1.f, wx0);
+      const float* p = s_box + ((iz - oz) * BY + (iy - oy)) * BX + (ix - ox);
+      float v[8];
+      v[0] = p[0];            v[1] = p[1];
+      v[2] = p[BX];           v[3] = p[BX + 1];
+      v[4] = p[BY * BX];      v[5] = p[BY * BX + 1];
+      v[6] = p[BY * BX + BX]; v[7] = p[BY * BX + BX + 1];
+      return trilerp(v, wz0, wz1, wy0, wy1, wx0, wx1);
+    }
+    return sample_global3<METHOD>(volb, g, lz, ly, lx);
+  } else {
+    const int iz = axis_nearest(lz, g.S[0] - 1), iy = axis_nearest(ly, g.S[1] - 1), ix = axis_nearest(lx, g.S[2] - 1);
+    if ((iz >= bb.lo_z) & (iz <= bb.hi_z) & (iy >= bb.lo_y) & (iy <= bb.hi_y) & (ix >= bb.lo_x) & (ix <= bb.hi_x))
+      return s_box[((iz - oz) * BY + (iy - oy)) * BX + (ix - ox)];
+    return sample_global3<METHOD>(volb, g, lz, ly, lx);
+  }
+}
+
+__device__ __forceinline__ float fill_if_oob(const Geo& g, float res, float lz, float ly, float lx) {
+  const bool oob = (lz < 0.f) | (lz > (float)(g.S[0] - 1)) | (ly < 0.f) | (ly > (float)(g.S[1] - 1)) |
+                   (lx < 0.f) | (lx > (float)(g.S[2] - 1));
+  return apply_fill(res, oob, g.fill);
+}
+
+// Process one staged tile.  Warp w owns row y = w % TY of planes z = w / TY, + NW/TY, ...
+template <int TZ, int TY, int HALO, int NW, int METHOD>
+__device__ __forceinline__ void compute_tile(const float* __restrict__ s_flow, const float* __restrict__ s_box,
+                                             const float* __restrict__ volb, float* __restrict__ outb,
+                                             const TileGeo& w, int x0, int y0, int z0l) {
+  using Cfg = TileCfg<TZ, TY, HALO>;
+  constexpr int TX = Cfg::TX, BX = Cfg::BX, BY = Cfg::BY, BZ = Cfg::BZ;
+  static_assert(NW % TY == 0 || TY % NW == 0, "warps must tile the rows of a plane");
+  constexpr int ZSTEP = NW >= TY ? NW / TY : 1;          // planes between a warp's rows
+  constexpr int YROWS = NW >= TY ? 1 : TY / NW;          // rows per plane per warp
+  const Geo& g = w.g;
+  const int H = g.S[1], W = g.S[2];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int zs = NW >= TY ? wid / TY : 0;
+  const int gz0 = w.out_z0 + z0l;
+  const int ox = x0 - Cfg::HX, oy = y0 - HALO, oz = gz0 - HALO;
+  const int gx = x0 + lane;
+  const float fx = (float)gx;
+  // interior tile: the whole box lies inside the resident part of the volume and the whole
+  // tile inside the produced output -> no clipping, no masking, 3 unsigned compares per voxel
+  const bool interior = (oz >= g.src_z0) && (oz + BZ <= g.src_z0 + g.src_n0) && (oy >= 0) && (oy + BY <= H) &&
+                        (ox >= 0) && (ox + BX <= W) && (z0l + TZ <= w.out_n0);
+  BoxBounds bb;
+  bb.lo_z = max(oz, g.src_z0); bb.hi_z = min(oz + BZ - 1, g.src_z0 + g.src_n0 - 1);
+  bb.lo_y = max(oy, 0); bb.hi_y = min(oy + BY - 1, H - 1);
+  bb.lo_x = max(ox, 0); bb.hi_x = min(ox + BX - 1, W - 1);
+#pragma unroll
+  for (int yr = 0; yr < YROWS; ++yr) {
+    const int yy = (NW >= TY ? wid % TY : wid) + yr * NW;
+    const int gy = y0 + yy;
+    const float fy = (float)gy;
+    const float* fl = s_flow + ((zs * TY + yy) * TX + lane) * 3;
+    float* op = outb + ((size_t)(z0l + zs) * H + gy) * W + gx;
+    if (interior) {
+#pragma unroll 2
+      for (int z = zs; z < TZ; z += ZSTEP, fl += ZSTEP * TY * TX * 3, op += (size_t)ZSTEP * H * W) {
+        const float lz = __fadd_rn((float)(gz0 + z), fl[0]);
+        const float ly = __fadd_rn(fy, fl[1]);
+        const float lx = __fadd_rn(fx, fl[2]);
+        float res = sample_box_interior<BX, BY, BZ, METHOD>(s_box, oz, oy, ox, volb, g, lz, ly, lx);
+        if (g.has_fill) res = fill_if_oob(g, res, lz, ly, lx);
+        *op = res;
+      }
+    } else if (gx < W && gy < H) {
+      for (int z = zs; z < TZ && z0l + z < w.out_n0; z += ZSTEP, fl += ZSTEP * TY * TX * 3, op += (size_t)ZSTEP * H * W) {
+        const float lz = __fadd_rn((float)(gz0 + z), fl[0]);
+        const float ly = __fadd_rn(fy, fl[1]);
+        const float lx = __fadd_rn(fx, fl[2]);
+        float res = sample_box_border<BX, BY, BZ, METHOD>(s_box, oz, oy, ox, bb, volb, g, lz, ly, lx);
+        if (g.has_fill) res = fill_if_oob(g, res, lz, ly, lx);
+        *op = res;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void decode_tile(const TileGeo& w, int tile, int TXc, int TYc, int TZc,
+                                            int& b, int& x0, int& y0, int& z0l) {
+  const int tx = tile % w.ntx; tile /= w.ntx;
+  const int ty = tile % w.nty; tile /= w.nty;
+  const int tz = tile % w.ntz;
+  b = tile / w.ntz;
+  x0 = tx * TXc; y0 = ty * TYc; z0l = tz * TZc;
+}
+
+// v1: one tile per CTA, several CTAs per SM overlap each other's load phase
+template <int TZ, int TY, int HALO, int METHOD>
 __global__ void __launch_bounds__(256)
 warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
                    const __grid_constant__ CUtensorMap tm_flow,
                    const float* __restrict__ vol, float* __restrict__ out, TileGeo w) {
-  constexpr int TX = 32;
-  constexpr int NW = 8;                       // warps per CTA; warp = one x-row of 32 voxels
-  static_assert(TY % NW == 0, "TY must be a multiple of the warp count");
+  using Cfg = TileCfg<TZ, TY, HALO>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* s_flow = reinterpret_cast<float*>(smem_raw);                       // [TZ][TY][TX][3]
-  float* s_box = s_flow + TZ * TY * TX * 3;                                 // [BZ][BY][BX]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(s_box + w.BZ * w.BY * w.BX);
-
-  const Geo& g = w.g;
-  int tile = blockIdx.x;
-  const int tx = tile % w.ntx; tile /= w.ntx;
-  const int ty = tile % w.nty; tile /= w.nty;
-  const int tz = tile % w.ntz;
-  const int b = tile / w.ntz;
-  const int x0 = tx * TX, y0 = ty * TY, z0l = tz * TZ;      // z0l: plane within the output slab
-  const int gz0 = w.out_z0 + z0l;                           // global z of the tile's first plane
-  const int ox = x0 - w.hx, oy = y0 - w.hy, oz = gz0 - w.hz;   // global coords of box origin
-
+  float* s_box = s_flow + Cfg::FLOW_ELEMS;                                  // [BZ][BY][BX]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_box + Cfg::BOX_ELEMS);
+  int b, x0, y0, z0l;
+  decode_tile(w, blockIdx.x, Cfg::TX, TY, TZ, b, x0, y0, z0l);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
-    const uint32_t bytes = (uint32_t)((TZ * TY * TX * 3 + w.BZ * w.BY * w.BX) * sizeof(float));
-    mbar_expect_tx(bar, bytes);
+    mbar_expect_tx(bar, (uint32_t)((Cfg::FLOW_ELEMS + Cfg::BOX_ELEMS) * sizeof(float)));
     tma_load_4d(s_flow, &tm_flow, bar, x0 * 3, y0, z0l, b);
-    tma_load_4d(s_box, &tm_vol, bar, ox, oy, oz - g.src_z0, b);
+    tma_load_4d(s_box, &tm_vol, bar, x0 - Cfg::HX, y0 - HALO, w.out_z0 + z0l - HALO - w.g.src_z0, b);
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+  compute_tile<TZ, TY, HALO, 8, METHOD>(s_flow, s_box, vol + (size_t)b * w.src_batch_stride,
+                                        out + (size_t)b * w.out_vox, w, x0, y0, z0l);
+}
+
+// v2: persistent CTAs, NSTAGE-deep TMA ring.  Thread 0 prefetches tile i+NSTAGE-1 while all
+// warps gather tile i; full[] barriers carry the TMA transaction bytes, empty[] barriers
+// collect one arrival per warp when a stage has been consumed (no CTA-wide __syncthreads
+// in the steady state).
+template <int TZ, int TY, int HALO, int NW, int NSTAGE, int CPS, int METHOD>
+__global__ void __launch_bounds__(NW * 32, CPS)
+warp3d_persist_kernel(const __grid_constant__ CUtensorMap tm_vol,
+                      const __grid_constant__ CUtensorMap tm_flow,
+                      const float* __restrict__ vol, float* __restrict__ out, TileGeo w, int ntiles) {
+  using Cfg = TileCfg<TZ, TY, HALO>;
+  constexpr int STAGE_ELEMS = Cfg::FLOW_ELEMS + Cfg::BOX_ELEMS;
+  static_assert((Cfg::FLOW_ELEMS * 4) % 128 == 0 && (STAGE_ELEMS * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* s_base = reinterpret_cast<float*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_base + NSTAGE * STAGE_ELEMS);
+  uint64_t* empty = full + NSTAGE;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NW); }
+    fence_mbar_init();
   }
   __syncthreads();
 
-  // region of the box that holds real (resident, in-volume) voxels, in global coordinates
-  const int lo_z = max(oz, g.src_z0), hi_z = min(oz + w.BZ - 1, g.src_z0 + g.src_n0 - 1);
-  const int lo_y = max(oy, 0), hi_y = min(oy + w.BY - 1, g.S[1] - 1);
-  const int lo_x = max(ox, 0), hi_x = min(ox + w.BX - 1, g.S[2] - 1);
-  const float mz = (float)(g.S[0] - 1), my = (float)(g.S[1] - 1), mx = (float)(g.S[2] - 1);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int gx = x0 + lane;
-  const float fx = (float)gx;
-  const bool x_ok = gx < g.S[2];
-  const float* volb = vol + (size_t)b * w.src_batch_stride;
-  float* outb = out + (size_t)b * w.out_vox;
-  const int sBY = w.BY, sBX = w.BX;
-  const int box_base = -((oz * sBY + oy) * sBX + ox);
+  auto issue = [&](int tile, int stage) {
+    int b, x0, y0, z0l;
+    decode_tile(w, tile, Cfg::TX, TY, TZ, b, x0, y0, z0l);
+    float* sf = s_base + stage * STAGE_ELEMS;
+    mbar_expect_tx(full + stage, (uint32_t)(STAGE_ELEMS * sizeof(float)));
+    tma_load_4d(sf, &tm_flow, full + stage, x0 * 3, y0, z0l, b);
+    tma_load_4d(sf + Cfg::FLOW_ELEMS, &tm_vol, full + stage, x0 - Cfg::HX, y0 - HALO,
+                w.out_z0 + z0l - HALO - w.g.src_z0, b);
+  };
 
-  mbar_wait(bar, 0);
-
-#pragma unroll 1
-  for (int z = 0; z < TZ; ++z) {
-    const int gz = gz0 + z;
-    const float fz = (float)gz;
-#pragma unroll 2
-    for (int yy = wid; yy < TY; yy += NW) {
-      const int gy = y0 + yy;
-      const float* fl = s_flow + ((z * TY + yy) * TX + lane) * 3;
-      const float lz = __fadd_rn(fz, fl[0]);
-      const float ly = __fadd_rn((float)gy, fl[1]);
-      const float lx = __fadd_rn(fx, fl[2]);
-      float res;
-      if (METHOD == NRT_LINEAR) {
-        const float cz = fminf(fmaxf(lz, 0.f), mz), cy = fminf(fmaxf(ly, 0.f), my), cx = fminf(fmaxf(lx, 0.f), mx);
-        const float f0z = floorf(cz), f0y = floorf(cy), f0x = floorf(cx);
-        const int iz = __float2int_rz(f0z), iy = __float2int_rz(f0y), ix = __float2int_rz(f0x);
-        float v[8];
-        float wz0, wz1, wy0, wy1, wx0, wx1;
-        const bool fast = (iz >= lo_z) & (iz < hi_z) & (iy >= lo_y) & (iy < hi_y) & (ix >= lo_x) & (ix < hi_x);
-        if (fast) {
-          // i1 = i0 + 1 needs no clip here; weights exactly as axis_linear computes them
-          wz0 = __fsub_rn(__fadd_rn(f0z, 1.f), cz); wz1 = __fsub_rn(1.f, wz0);
-          wy0 = __fsub_rn(__fadd_rn(f0y, 1.f), cy); wy1 = __fsub_rn(1.f, wy0);
-          wx0 = __fsub_rn(__fadd_rn(f0x, 1.f), cx); wx1 = __fsub_rn(1.f, wx0);
-          const float* p = s_box + (box_base + (iz * sBY + iy) * sBX + ix);
-          const int dy = sBX, dz = sBY * sBX;
-          v[0] = p[0];       v[1] = p[1];
-          v[2] = p[dy];      v[3] = p[dy + 1];
-          v[4] = p[dz];      v[5] = p[dz + 1];
-          v[6] = p[dz + dy]; v[7] = p[dz + dy + 1];
-        } else {
-          Axis az = axis_linear(lz, mz, g.S[0] - 1);
-          const Axis ay = axis_linear(ly, my, g.S[1] - 1);
-          const Axis ax = axis_linear(lx, mx, g.S[2] - 1);
-          az.i0 = to_resident(g, az.i0);
-          az.i1 = to_resident(g, az.i1);
-          wz0 = az.wlo; wz1 = az.whi; wy0 = ay.wlo; wy1 = ay.whi; wx0 = ax.wlo; wx1 = ax.whi;
-          const int r00 = (az.i0 * g.S[1] + ay.i0) * g.S[2], r01 = (az.i0 * g.S[1] + ay.i1) * g.S[2];
-          const int r10 = (az.i1 * g.S[1] + ay.i0) * g.S[2], r11 = (az.i1 * g.S[1] + ay.i1) * g.S[2];
-          v[0] = __ldg(volb + r00 + ax.i0); v[1] = __ldg(volb + r00 + ax.i1);
-          v[2] = __ldg(volb + r01 + ax.i0); v[3] = __ldg(volb + r01 + ax.i1);
-          v[4] = __ldg(volb + r10 + ax.i0); v[5] = __ldg(volb + r10 + ax.i1);
-          v[6] = __ldg(volb + r11 + ax.i0); v[7] = __ldg(volb + r11 + ax.i1);
-        }
-        const float w00 = __fmul_rn(wz0, wy0), w01 = __fmul_rn(wz0, wy1);
-        const float w10 = __fmul_rn(wz1, wy0), w11 = __fmul_rn(wz1, wy1);
-        res = __fadd_rn(0.f, __fmul_rn(__fmul_rn(w00, wx0), v[0]));
-        res = __fadd_rn(res, __fmul_rn(__fmul_rn(w00, wx1), v[1]));
-        res = __fadd_rn(res, __fmul_rn(__fmul_rn(w01, wx0), v[2]));
-        res = __fadd_rn(res, __fmul_rn(__fmul_rn(w01, wx1), v[3]));
-        res = __fadd_rn(res, __fmul_rn(__fmul_rn(w10, wx0), v[4]));
-        res = __fadd_rn(res, __fmul_rn(__fmul_rn(w10, wx1), v[5]));
-        res = __fadd_rn(res, __fmul_rn(__fmul_rn(w11, wx0), v[6]));
-        res = __fadd_rn(res, __fmul_rn(__fmul_rn(w11, wx1), v[7]));
-      } else {
-        const int iz = axis_nearest(lz, g.S[0] - 1), iy = axis_nearest(ly, g.S[1] - 1), ix = axis_nearest(lx, g.S[2] - 1);
-        const bool fast = (iz >= lo_z) & (iz <= hi_z) & (iy >= lo_y) & (iy <= hi_y) & (ix >= lo_x) & (ix <= hi_x);
-        if (fast) res = s_box[box_base + (iz * sBY + iy) * sBX + ix];
-        else res = __ldg(volb + (to_resident(g, iz) * g.S[1] + iy) * g.S[2] + ix);
-      }
-      if (g.has_fill) {
-        const bool oob = (lz < 0.f) | (lz > mz) | (ly < 0.f) | (ly > my) | (lx < 0.f) | (lx > mx);
-        res = apply_fill(res, oob, g.fill);
-      }
-      if (x_ok && gy < g.S[1] && (z0l + z) < w.out_n0)
-        outb[((size_t)(z0l + z) * g.S[1] + gy) * g.S[2] + gx] = res;
+  // prologue: fill NSTAGE-1 stages
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE - 1; ++s) {
+      const int t = blockIdx.x + s * gridDim.x;
+      if (t < ntiles) issue(t, s);
     }
+  }
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int stage = it % NSTAGE;
+    if (threadIdx.x == 0) {
+      // prefetch the tile NSTAGE-1 iterations ahead into the stage consumed last iteration
+      const int pf_it = it + NSTAGE - 1;
+      const int pf_tile = tile + (NSTAGE - 1) * gridDim.x;
+      if (pf_tile < ntiles) {
+        const int ps = pf_it % NSTAGE;
+        const int round = pf_it / NSTAGE;               // how many times stage ps has been filled before
+        if (round >= 1) mbar_wait(empty + ps, (uint32_t)((round - 1) & 1));
+        issue(pf_tile, ps);
+      }
+    }
+    mbar_wait(full + stage, (uint32_t)((it / NSTAGE) & 1));
+    int b, x0, y0, z0l;
+    decode_tile(w, tile, Cfg::TX, TY, TZ, b, x0, y0, z0l);
+    const float* sf = s_base + stage * STAGE_ELEMS;
+    compute_tile<TZ, TY, HALO, NW, METHOD>(sf, sf + Cfg::FLOW_ELEMS, vol + (size_t)b * w.src_batch_stride,
+                                           out + (size_t)b * w.out_vox, w, x0, y0, z0l);
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(empty + stage)) : "memory");
   }
 }
 
@@ -387,25 +579,68 @@ static int env_int(const char* name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
-template <int TZ, int TY, int METHOD>
-static int launch_tile(const CUtensorMap& tmv, const CUtensorMap& tmf, const float* vol, float* out,
-                       const TileGeo& tg, size_t smem, cudaStream_t st) {
-  auto kern = warp3d_tile_kernel<TZ, TY, METHOD>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+template <int TZ, int TY, int HALO, int METHOD>
+static int launch_tile(const float* vol, const float* flow, float* out, TileGeo tg, int H, int W, int src_n0,
+                       int out_n0, cudaStream_t st) {
+  using Cfg = TileCfg<TZ, TY, HALO>;
+  tg.ntz = (out_n0 + TZ - 1) / TZ; tg.nty = (H + TY - 1) / TY; tg.ntx = (W + Cfg::TX - 1) / Cfg::TX;
+  const int64_t grid = (int64_t)tg.B * tg.ntz * tg.nty * tg.ntx;
+  if (grid > 0x7fffffffLL || Cfg::SMEM > 227 * 1024) return 1;   // caller falls back to the gather kernel
+  CUtensorMap tmv, tmf;
+  const uint64_t vd[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)src_n0, (uint64_t)tg.B};
+  const uint32_t vb[4] = {(uint32_t)Cfg::BX, (uint32_t)Cfg::BY, (uint32_t)Cfg::BZ, 1};
+  const uint64_t fd[4] = {(uint64_t)W * 3, (uint64_t)H, (uint64_t)out_n0, (uint64_t)tg.B};
+  const uint32_t fb[4] = {(uint32_t)Cfg::TX * 3, (uint32_t)TY, (uint32_t)TZ, 1};
+  int rc = encode_f32_4d(&tmv, vol, vd, vb);
+  if (rc != NRT_OK) return rc;
+  rc = encode_f32_4d(&tmf, flow, fd, fb);
+  if (rc != NRT_OK) return rc;
+  auto kern = warp3d_tile_kernel<TZ, TY, HALO, METHOD>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(warp3d_tile)");
-    configured = smem;
+    configured = true;
   }
-  const int grid = tg.B * tg.ntz * tg.nty * tg.ntx;
-  kern<<<grid, 256, smem, st>>>(tmv, tmf, vol, out, tg);
+  kern<<<(int)grid, 256, Cfg::SMEM, st>>>(tmv, tmf, vol, out, tg);
   return check_launch("warp3d_tile_kernel");
+}
+
+template <int TZ, int TY, int HALO, int NW, int NSTAGE, int CPS, int METHOD>
+static int launch_persist(const float* vol, const float* flow, float* out, TileGeo tg, int H, int W, int src_n0,
+                          int out_n0, cudaStream_t st) {
+  constexpr int ctas_per_sm = CPS;
+  using Cfg = TileCfg<TZ, TY, HALO>;
+  constexpr size_t SMEM = (size_t)NSTAGE * (Cfg::FLOW_ELEMS + Cfg::BOX_ELEMS) * sizeof(float) + 2 * NSTAGE * 8 + 16;
+  tg.ntz = (out_n0 + TZ - 1) / TZ; tg.nty = (H + TY - 1) / TY; tg.ntx = (W + Cfg::TX - 1) / Cfg::TX;
+  const int64_t ntiles = (int64_t)tg.B * tg.ntz * tg.nty * tg.ntx;
+  if (ntiles > 0x7fffffffLL || SMEM > 227 * 1024) return 1;
+  CUtensorMap tmv, tmf;
+  const uint64_t vd[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)src_n0, (uint64_t)tg.B};
+  const uint32_t vb[4] = {(uint32_t)Cfg::BX, (uint32_t)Cfg::BY, (uint32_t)Cfg::BZ, 1};
+  const uint64_t fd[4] = {(uint64_t)W * 3, (uint64_t)H, (uint64_t)out_n0, (uint64_t)tg.B};
+  const uint32_t fb[4] = {(uint32_t)Cfg::TX * 3, (uint32_t)TY, (uint32_t)TZ, 1};
+  int rc = encode_f32_4d(&tmv, vol, vd, vb);
+  if (rc != NRT_OK) return rc;
+  rc = encode_f32_4d(&tmf, flow, fd, fb);
+  if (rc != NRT_OK) return rc;
+  auto kern = warp3d_persist_kernel<TZ, TY, HALO, NW, NSTAGE, CPS, METHOD>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM) != cudaSuccess)
+      return check_launch("cudaFuncSetAttribute(warp3d_persist)");
+    configured = true;
+  }
+  int grid = sm_count() * ctas_per_sm;
+  if (ntiles < grid) grid = (int)ntiles;
+  kern<<<grid, NW * 32, SMEM, st>>>(tmv, tmf, vol, out, tg, (int)ntiles);
+  return check_launch("warp3d_persist_kernel");
 }
 
 template <int D, int METHOD>
 static int launch_warp_generic(const float* vol, const float* flow, float* out, const WarpGeo& wg, cudaStream_t st) {
   const bool vec = (wg.g.C % 4 == 0) && aligned16(vol) && aligned16(out);
-  const int64_t total = (int64_t)wg.B * wg.out_vox * (vec ? wg.g.C / 4 : wg.g.C);
+  const int64_t total = (int64_t)wg.B * wg.out_vox * (vec ? wg.g.C / 4 : 1);
   if (total == 0) return NRT_OK;
   const int grid = (int)imin64((total + 255) / 256, (int64_t)sm_count() * 32);
   if (vec) warp_generic_kernel<D, 4, METHOD><<<grid, 256, 0, st>>>(vol, flow, out, wg);
@@ -416,7 +651,7 @@ static int launch_warp_generic(const float* vol, const float* flow, float* out, 
 template <int D, int METHOD>
 static int launch_interpn(const float* vol, const Geo& g, const float* loc, int64_t n_out, float* out, cudaStream_t st) {
   const bool vec = (g.C % 4 == 0) && aligned16(vol) && aligned16(out);
-  const int64_t total = n_out * (vec ? g.C / 4 : g.C);
+  const int64_t total = n_out * (vec ? g.C / 4 : 1);
   if (total == 0) return NRT_OK;
   const int grid = (int)imin64((total + 255) / 256, (int64_t)sm_count() * 32);
   if (vec) interpn_kernel<D, 4, METHOD><<<grid, 256, 0, st>>>(vol, g, loc, n_out, out);
@@ -427,7 +662,7 @@ static int launch_interpn(const float* vol, const Geo& g, const float* loc, int6
 template <int D, int METHOD>
 static int launch_resize(const float* vol, float* out, const ResizeGeo& rg, cudaStream_t st) {
   const bool vec = (rg.g.C % 4 == 0) && aligned16(vol) && aligned16(out);
-  const int64_t total = (int64_t)rg.B * rg.out_vox * (vec ? rg.g.C / 4 : rg.g.C);
+  const int64_t total = (int64_t)rg.B * rg.out_vox * (vec ? rg.g.C / 4 : 1);
   if (total == 0) return NRT_OK;
   const int grid = (int)imin64((total + 255) / 256, (int64_t)sm_count() * 32);
   if (vec) resize_kernel<D, 4, METHOD><<<grid, 256, 0, st>>>(vol, out, rg);
@@ -463,53 +698,51 @@ static int try_tile_path(const float* vol, const float* flow, float* out, int B,
   const int H = shape[1], W = shape[2];
   if (env_int("NRT_WARP_TILE", 1) == 0) return NRT_OK;
   if (W % 4 != 0 || !aligned16(vol) || !aligned16(flow) || W < 32) return NRT_OK;
-  int cfg = env_int("NRT_WARP_TILE_CFG", 0);         // 0: 8x16x32, 1: 16x16x32, 2: 8x8x32, 3: 4x8x32
-  const int TZs[4] = {8, 16, 8, 4}, TYs[4] = {16, 16, 8, 8};
-  if (cfg < 0 || cfg > 3) cfg = 0;
+  // tile shapes (TZ x TY x 32) and halos built: the default 8x8x32 runs 4 CTAs per SM (best
+  // measured on B200, profiles/); `halo` picks the smallest built halo that covers it.
+  int cfg = env_int("NRT_WARP_TILE_CFG", 2);         // 0: 8x16x32, 1: 16x16x32, 2: 8x8x32, 3: 4x8x32
+  if (cfg < 0 || cfg > 3) cfg = 2;
   if (halo <= 0) halo = 3;
-  const int TX = 32;
+  const int hsel = halo <= 3 ? 3 : (halo <= 4 ? 4 : (halo <= 6 ? 6 : 8));
   TileGeo tg;
-  int TZ, TY;
-  size_t smem;
-  for (;;) {        // shrink the halo until tile + box fit in shared memory
-    TZ = TZs[cfg]; TY = TYs[cfg];
-    tg.hz = halo; tg.hy = halo; tg.hx = halo;
-    tg.BZ = TZ + 2 * halo; tg.BY = TY + 2 * halo;
-    tg.BX = (TX + 2 * halo + 3) & ~3;
-    smem = (size_t)(TZ * TY * TX * 3 + tg.BZ * tg.BY * tg.BX) * sizeof(float) + 16;
-    if ((smem <= 227 * 1024 && tg.BX <= 256 && tg.BY <= 256 && tg.BZ <= 256) || halo == 1) break;
-    --halo;
-  }
-  if (smem > 227 * 1024) return NRT_OK;
   tg.g.S[0] = shape[0]; tg.g.S[1] = H; tg.g.S[2] = W;
   tg.g.src_z0 = src_z0; tg.g.src_n0 = src_n0; tg.g.C = 1;
   tg.g.has_fill = has_fill; tg.g.fill = fill; tg.g.err = err_flag;
   tg.out_z0 = out_z0; tg.out_n0 = out_n0; tg.B = B;
-  tg.ntz = (out_n0 + TZ - 1) / TZ; tg.nty = (H + TY - 1) / TY; tg.ntx = (W + TX - 1) / TX;
+  tg.ntz = tg.nty = tg.ntx = 0;
   tg.src_batch_stride = (int64_t)src_n0 * H * W;
   tg.out_vox = (int64_t)out_n0 * H * W;
-  if ((int64_t)tg.B * tg.ntz * tg.nty * tg.ntx > 0x7fffffffLL) return NRT_OK;
-
-  CUtensorMap tmv, tmf;
-  const uint64_t vd[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)src_n0, (uint64_t)B};
-  const uint32_t vb[4] = {(uint32_t)tg.BX, (uint32_t)tg.BY, (uint32_t)tg.BZ, 1};
-  const uint64_t fd[4] = {(uint64_t)W * 3, (uint64_t)H, (uint64_t)out_n0, (uint64_t)B};
-  const uint32_t fb[4] = {(uint32_t)TX * 3, (uint32_t)TY, (uint32_t)TZ, 1};
-  int rc = encode_f32_4d(&tmv, vol, vd, vb);
-  if (rc != NRT_OK) return rc;
-  rc = encode_f32_4d(&tmf, flow, fd, fb);
-  if (rc != NRT_OK) return rc;
-  *used = true;
-#define NRT_TILE_CASE(i, tz, ty)                                                                   \
-  if (cfg == (i))                                                                                  \
-    return method == NRT_LINEAR ? launch_tile<tz, ty, NRT_LINEAR>(tmv, tmf, vol, out, tg, smem, st) \
-                                : launch_tile<tz, ty, NRT_NEAREST>(tmv, tmf, vol, out, tg, smem, st);
-  NRT_TILE_CASE(0, 8, 16)
-  NRT_TILE_CASE(1, 16, 16)
-  NRT_TILE_CASE(2, 8, 8)
-  NRT_TILE_CASE(3, 4, 8)
+  int rc = 1;
+  // persistent TMA-ring kernels (v2).  pcfg: 1 = 8x16x32 tile, 32 warps, 2 stages, 1 CTA/SM;
+  // 2 = 8x8x32 tile, 16 warps, 2 stages, 2 CTAs/SM; 3 = 8x8x32, 16 warps, 3 stages, 1 CTA/SM
+  const int pcfg = env_int("NRT_WARP_PERSIST", 0);
+  if (pcfg > 0 && hsel == 3) {
+#define NRT_PERSIST_CASE(i, tz, ty, nw, ns, cps)                                                          \
+    if (pcfg == (i))                                                                                     \
+      rc = method == NRT_LINEAR                                                                          \
+               ? launch_persist<tz, ty, 3, nw, ns, cps, NRT_LINEAR>(vol, flow, out, tg, H, W, src_n0, out_n0, st)   \
+               : launch_persist<tz, ty, 3, nw, ns, cps, NRT_NEAREST>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
+    NRT_PERSIST_CASE(1, 8, 16, 32, 2, 1)
+    NRT_PERSIST_CASE(2, 8, 8, 16, 2, 2)
+    NRT_PERSIST_CASE(3, 8, 8, 16, 3, 1)
+    NRT_PERSIST_CASE(4, 8, 8, 32, 3, 1)
+    NRT_PERSIST_CASE(5, 4, 8, 16, 3, 2)
+#undef NRT_PERSIST_CASE
+    if (rc != 1) { *used = true; return rc; }
+  }
+#define NRT_TILE_CASE(i, tz, ty, hh)                                                                     \
+  if (cfg == (i) && hsel == (hh))                                                                        \
+    rc = method == NRT_LINEAR                                                                            \
+             ? launch_tile<tz, ty, hh, NRT_LINEAR>(vol, flow, out, tg, H, W, src_n0, out_n0, st)         \
+             : launch_tile<tz, ty, hh, NRT_NEAREST>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
+  NRT_TILE_CASE(0, 8, 16, 3) NRT_TILE_CASE(0, 8, 16, 4) NRT_TILE_CASE(0, 8, 16, 6) NRT_TILE_CASE(0, 8, 16, 8)
+  NRT_TILE_CASE(1, 16, 16, 3) NRT_TILE_CASE(1, 16, 16, 4) NRT_TILE_CASE(1, 16, 16, 6) NRT_TILE_CASE(1, 16, 16, 8)
+  NRT_TILE_CASE(2, 8, 8, 3) NRT_TILE_CASE(2, 8, 8, 4) NRT_TILE_CASE(2, 8, 8, 6) NRT_TILE_CASE(2, 8, 8, 8)
+  NRT_TILE_CASE(3, 4, 8, 3) NRT_TILE_CASE(3, 4, 8, 4) NRT_TILE_CASE(3, 4, 8, 6) NRT_TILE_CASE(3, 4, 8, 8)
 #undef NRT_TILE_CASE
-  return set_error(NRT_E_ARG, "bad tile config");
+  if (rc == 1) return NRT_OK;                              // not launched: fall back
+  *used = true;
+  return rc;
 }
 
 }  // namespace nrt

@@ -9,7 +9,7 @@
 //
 //   lc3d_stream_kernel : persistent CTAs; a producer thread streams whole per-position
 //       weight blocks into a shared-memory ring with cp.async.bulk (TMA 1-D bulk copy)
-//       completing on mbarriers; 8 consumer warps contract a staged block against the
+//       completing on mbarriers; 4 consumer warps contract a staged block against the
 //       position's input patch (gathered from L2 into registers through a shared index
 //       table) and release the slot.  One warp owns one position; lanes own fixed
 //       4-wide output-channel quads so no weight is read twice.
@@ -67,12 +67,11 @@ __device__ __forceinline__ int64_t patch_origin(const LcGeo& g, int64_t p) {
 // ---------------------------------------------------------------------------------------
 // streaming kernel.  CQ = Cout/4 (power of two <= 32), BB = batch items per pass.
 // ---------------------------------------------------------------------------------------
-constexpr int kLcWarps = 4;                 // consumer warps (one position each at a time)
-constexpr int kLcThreads = (kLcWarps + 1) * 32;   // + 1 producer warp
+constexpr int kLcMaxWarps = 8;              // consumer warps (one position each at a time) + 1 producer warp
 constexpr int kLcMaxStages = 8;
 
 template <int BB>
-__global__ void __launch_bounds__(kLcThreads, 1)
+__global__ void __launch_bounds__((kLcMaxWarps + 1) * 32, 1)
 lc3d_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
                    const float* __restrict__ bias, float* __restrict__ out, LcGeo g, int b_base,
                    int stages, int cq_log2) {
@@ -85,7 +84,8 @@ lc3d_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel
   int* s_jmap = reinterpret_cast<int*>(empty + stages);                          // [F]
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-  for (int j = tid; j < g.F; j += kLcThreads) s_jmap[j] = feature_offset(g, j);
+  const int kLcWarps = (int)(blockDim.x >> 5) - 1;
+  for (int j = tid; j < g.F; j += (int)blockDim.x) s_jmap[j] = feature_offset(g, j);
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     fence_mbar_init();
@@ -113,55 +113,69 @@ lc3d_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel
   }
 
   // ===== consumer warps =====
-  const int n4 = g.F * CQ;                      // float4s per block
-  const int fq = lane & (CQ - 1);               // this lane's output-channel quad
+  // lane -> (j-slice, batch item, output-channel quad): fq = lane % CQ, b = (lane / CQ) % BB,
+  // slice = lane / (CQ*BB).  The BB batch items of a position are contracted at the same time
+  // by different lanes (weights are read once per position from shared memory, broadcast
+  // across the batch lanes); the 32/(CQ*BB) slices split the F patch features.
+  constexpr int BB_LOG2 = BB == 1 ? 0 : (BB == 2 ? 1 : (BB == 4 ? 2 : 3));
+  const int fq = lane & (CQ - 1);
+  const int bl = (lane >> cq_log2) & (BB - 1);
+  const int js = lane >> (cq_log2 + BB_LOG2);
+  const int JS = 32 >> (cq_log2 + BB_LOG2);
+  const int iters = (g.F + JS - 1) / JS;
+  constexpr int CH = 27;
   int k = wid;
   for (int64_t n = (int64_t)blockIdx.x + (int64_t)wid * gridDim.x; n < g.pn;
        n += (int64_t)kLcWarps * gridDim.x, k += kLcWarps) {
     const int slot = k % stages;
     const uint32_t ph = (uint32_t)((k / stages) & 1);
     const int64_t p = g.p0 + n;
-    const float* xp = x + (int64_t)b_base * g.x_batch + patch_origin(g, p);
-    float acc[BB][4];
-#pragma unroll
-    for (int b = 0; b < BB; ++b) { acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.f; }
-    mbar_wait(full + slot, ph);
+    const float* xp = x + (int64_t)(b_base + bl) * g.x_batch + patch_origin(g, p);
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
     const float4* w4 = reinterpret_cast<const float4*>(smem_raw + (size_t)slot * blk_stride);
-#pragma unroll 6
-    for (int i = lane; i < n4; i += 32) {
-      const float4 wv = w4[i];
-      const int off = s_jmap[i >> cq_log2];
+    // The input values a lane needs do not depend on the weights: gather a chunk of them from
+    // L1/L2 into registers first (CH independent loads in flight; the first chunk is issued
+    // before waiting for the TMA), then run the LDS.128 + FFMA chain with no global latency in it.
+    for (int i0 = 0; i0 < iters; i0 += CH) {
+      float xv[CH];
 #pragma unroll
-      for (int b = 0; b < BB; ++b) {
-        const float xv = __ldg(xp + (int64_t)b * g.x_batch + off);
-        acc[b][0] = fmaf(xv, wv.x, acc[b][0]);
-        acc[b][1] = fmaf(xv, wv.y, acc[b][1]);
-        acc[b][2] = fmaf(xv, wv.z, acc[b][2]);
-        acc[b][3] = fmaf(xv, wv.w, acc[b][3]);
+      for (int c = 0; c < CH; ++c) {
+        const int j = js + (i0 + c) * JS;
+        xv[c] = (j < g.F) ? __ldg(xp + s_jmap[j]) : 0.f;
+      }
+      if (i0 == 0) mbar_wait(full + slot, ph);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int j = js + (i0 + c) * JS;
+        if (j < g.F) {
+          const float4 wv = w4[(j << cq_log2) + fq];
+          acc0 = fmaf(xv[c], wv.x, acc0);
+          acc1 = fmaf(xv[c], wv.y, acc1);
+          acc2 = fmaf(xv[c], wv.z, acc2);
+          acc3 = fmaf(xv[c], wv.w, acc3);
+        }
       }
     }
     __syncwarp();
     if (lane == 0) {                             // slot free: every lane has read its share
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(empty + slot)) : "memory");
     }
-    // fold the 32/CQ lanes that share an output quad
-#pragma unroll
-    for (int b = 0; b < BB; ++b)
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        for (int o = 16; o >= CQ; o >>= 1) acc[b][q] += __shfl_xor_sync(0xffffffffu, acc[b][q], o);
-    if (lane < CQ) {
+    // fold the j-slices
+    for (int o = 16; o >= (CQ << BB_LOG2); o >>= 1) {
+      acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+      acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+      acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
+      acc3 += __shfl_xor_sync(0xffffffffu, acc3, o);
+    }
+    if (js == 0) {
       float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
       if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + n * g.Cout) + fq);
-#pragma unroll
-      for (int b = 0; b < BB; ++b) {
-        float4 r;
-        r.x = activate(acc[b][0] + bv.x, g.activation);
-        r.y = activate(acc[b][1] + bv.y, g.activation);
-        r.z = activate(acc[b][2] + bv.z, g.activation);
-        r.w = activate(acc[b][3] + bv.w, g.activation);
-        reinterpret_cast<float4*>(out + ((int64_t)(b_base + b) * g.pn + n) * g.Cout)[fq] = r;
-      }
+      float4 r;
+      r.x = activate(acc0 + bv.x, g.activation);
+      r.y = activate(acc1 + bv.y, g.activation);
+      r.z = activate(acc2 + bv.z, g.activation);
+      r.w = activate(acc3 + bv.w, g.activation);
+      reinterpret_cast<float4*>(out + ((int64_t)(b_base + bl) * g.pn + n) * g.Cout)[fq] = r;
     }
   }
 }
@@ -186,6 +200,64 @@ lc3d_generic_kernel(const float* __restrict__ x, const float* __restrict__ kerne
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// backward: one warp per output position, lanes own fixed output-channel quads like the
+// forward.  In one pass over the position's weight block:
+//   grad_kernel[p,j,f] = sum_b patch[b,p,j] * dy[b,p,f]          (6.59 GB write stream at cfg 4)
+//   grad_x[b, patch(p,j)] += sum_f dy[b,p,f] * kernel[p,j,f]     (scatter: patches overlap -> atomics)
+// grad_bias[p,f] = sum_b dy[b,p,f] is a plain reduction done by the caller.
+// ---------------------------------------------------------------------------------------
+template <int BB>
+__global__ void __launch_bounds__(256)
+lc3d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel, const float* __restrict__ dy,
+                float* __restrict__ gx, float* __restrict__ gk, LcGeo g, int b_base, int cq_log2, int accumulate_gk) {
+  extern __shared__ int s_jmap[];
+  const int CQ = 1 << cq_log2;
+  for (int j = threadIdx.x; j < g.F; j += blockDim.x) s_jmap[j] = feature_offset(g, j);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int fq = lane & (CQ - 1);
+  const int n4 = g.F * CQ;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); n < g.pn; n += warps) {
+    const int64_t po = patch_origin(g, g.p0 + n);
+    float4 d4[BB];
+#pragma unroll
+    for (int b = 0; b < BB; ++b)
+      d4[b] = __ldg(reinterpret_cast<const float4*>(dy + ((int64_t)(b_base + b) * g.pn + n) * g.Cout) + fq);
+    const float4* w4 = reinterpret_cast<const float4*>(kernel + n * (int64_t)g.F * g.Cout);
+    float4* gk4 = gk ? reinterpret_cast<float4*>(gk + n * (int64_t)g.F * g.Cout) : nullptr;
+    for (int i0 = 0; i0 < n4; i0 += 32) {              // warp-uniform trip count (shuffles inside)
+      const int i = i0 + lane;
+      const bool valid = i < n4;
+      const int off = valid ? s_jmap[i >> cq_log2] : 0;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gx && valid) wv = ld_stream_f4(w4 + i);
+#pragma unroll
+      for (int b = 0; b < BB; ++b) {
+        if (gk && valid) {
+          const float xv = __ldg(x + (int64_t)(b_base + b) * g.x_batch + po + off);
+          acc.x = fmaf(xv, d4[b].x, acc.x); acc.y = fmaf(xv, d4[b].y, acc.y);
+          acc.z = fmaf(xv, d4[b].z, acc.z); acc.w = fmaf(xv, d4[b].w, acc.w);
+        }
+        if (gx) {
+          float part = (wv.x * d4[b].x + wv.y * d4[b].y) + (wv.z * d4[b].z + wv.w * d4[b].w);
+          for (int o = CQ >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+          if (fq == 0 && valid) atomicAdd(gx + (int64_t)(b_base + b) * g.x_batch + po + off, part);
+        }
+      }
+      if (gk && valid) {
+        if (accumulate_gk) {
+          const float4 old = gk4[i];
+          acc.x += old.x; acc.y += old.y; acc.z += old.z; acc.w += old.w;
+        }
+        st_stream_f4(gk4 + i, acc);
+      }
+    }
+  }
+}
+
 template <int BB>
 static int launch_stream(const float* x, const float* kernel, const float* bias, float* out, const LcGeo& g,
                          int b_base, int cq_log2, cudaStream_t st) {
@@ -201,7 +273,12 @@ static int launch_stream(const float* x, const float* kernel, const float* bias,
     return check_launch("cudaFuncSetAttribute(lc3d_stream)");
   int grid = sm_count();
   if (g.pn < grid) grid = (int)g.pn;
-  kern<<<grid, kLcThreads, smem, st>>>(x, kernel, bias, out, g, b_base, stages, cq_log2);
+  int nw = kLcMaxWarps;                          // as many consumers as the ring allows (measured best)
+  if (const char* e = getenv("NRT_LC3D_WARPS")) nw = atoi(e);
+  if (nw < 1) nw = 1;
+  if (nw > kLcMaxWarps) nw = kLcMaxWarps;
+  if (nw > stages - 1) nw = stages - 1;
+  kern<<<grid, (nw + 1) * 32, smem, st>>>(x, kernel, bias, out, g, b_base, stages, cq_log2);
   return check_launch("lc3d_stream_kernel");
 }
 
@@ -244,11 +321,12 @@ extern "C" int nrt_lc3d_fwd_f32(const float* x, const float* kernel, const float
     int cq_log2 = 0;
     while ((1 << cq_log2) < cq) ++cq_log2;
     int b = 0, rc = NRT_OK;
+    const int max_bb = 32 / cq;                  // batch items that fit the lanes of one warp
     while (b < B && rc == NRT_OK) {
       const int left = B - b;
-      if (left >= 8) { rc = launch_stream<8>(x, kernel, bias, out, g, b, cq_log2, st); b += 8; }
-      else if (left >= 4) { rc = launch_stream<4>(x, kernel, bias, out, g, b, cq_log2, st); b += 4; }
-      else if (left >= 2) { rc = launch_stream<2>(x, kernel, bias, out, g, b, cq_log2, st); b += 2; }
+      if (left >= 8 && max_bb >= 8) { rc = launch_stream<8>(x, kernel, bias, out, g, b, cq_log2, st); b += 8; }
+      else if (left >= 4 && max_bb >= 4) { rc = launch_stream<4>(x, kernel, bias, out, g, b, cq_log2, st); b += 4; }
+      else if (left >= 2 && max_bb >= 2) { rc = launch_stream<2>(x, kernel, bias, out, g, b, cq_log2, st); b += 2; }
       else { rc = launch_stream<1>(x, kernel, bias, out, g, b, cq_log2, st); b += 1; }
     }
     if (rc <= 0) return rc;       // rc == 1: weight block does not fit the ring -> generic
@@ -257,4 +335,48 @@ extern "C" int nrt_lc3d_fwd_f32(const float* x, const float* kernel, const float
   const int grid = (int)imin64((total + 255) / 256, (int64_t)sm_count() * 32);
   lc3d_generic_kernel<<<grid, 256, 0, st>>>(x, kernel, bias, out, g);
   return check_launch("lc3d_generic_kernel");
+}
+
+extern "C" int nrt_lc3d_bwd_f32(const float* x, const float* kernel, const float* grad_out, float* grad_x,
+                                float* grad_kernel, int B, const int32_t* in_shape, int Cin, int Cout,
+                                const int32_t* ksize, const int32_t* strides, int feature_order, int64_t p0,
+                                int64_t p_count, void* stream) {
+  NRT_REQUIRE(x && kernel && grad_out && in_shape && ksize && strides && (grad_x || grad_kernel), NRT_E_ARG, "null pointer");
+  NRT_REQUIRE(B >= 0 && Cin >= 1 && Cout >= 1, NRT_E_ARG, "bad B/Cin/Cout");
+  NRT_REQUIRE(feature_order == 0 || feature_order == 1, NRT_E_ARG, "feature_order must be 0 or 1");
+  LcGeo g;
+  g.B = B; g.Cin = Cin; g.Cout = Cout; g.feature_order = feature_order; g.activation = 0;
+  g.P = 1; g.x_batch = Cin;
+  int64_t F = Cin;
+  for (int d = 0; d < 3; ++d) {
+    g.I[d] = in_shape[d]; g.K[d] = ksize[d]; g.St[d] = strides[d];
+    NRT_REQUIRE(g.I[d] >= 1 && g.K[d] >= 1 && g.St[d] >= 1 && g.K[d] <= g.I[d], NRT_E_ARG, "bad geometry at axis %d", d);
+    g.O[d] = (g.I[d] - g.K[d]) / g.St[d] + 1;
+    g.P *= g.O[d]; g.x_batch *= g.I[d]; F *= g.K[d];
+  }
+  NRT_REQUIRE(F <= 8192 && g.x_batch <= 0x7fffffffLL, NRT_E_SIZE, "patch or input too large");
+  g.F = (int)F;
+  NRT_REQUIRE(p0 >= 0 && p_count >= 0 && p0 + p_count <= g.P, NRT_E_ARG, "positions out of range");
+  g.p0 = p0; g.pn = p_count;
+  const int cq = Cout / 4;
+  NRT_REQUIRE(Cout % 4 == 0 && cq <= 32 && (cq & (cq - 1)) == 0 && aligned16(kernel) && aligned16(grad_out) &&
+              (!grad_kernel || aligned16(grad_kernel)), NRT_E_ARG,
+              "lc3d backward is built for Cout in {4,8,16,32,64,128} and 16-byte aligned buffers");
+  if (B == 0 || p_count == 0) return NRT_OK;
+  int cq_log2 = 0;
+  while ((1 << cq_log2) < cq) ++cq_log2;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (int)imin64((p_count + 7) / 8, (int64_t)sm_count() * 8);
+  const size_t smem = (size_t)g.F * sizeof(int);
+  int b = 0;
+  while (b < B) {
+    const int left = B - b;
+    const int acc = b > 0;
+    if (left >= 4) { lc3d_bwd_kernel<4><<<grid, 256, smem, st>>>(x, kernel, grad_out, grad_x, grad_kernel, g, b, cq_log2, acc); b += 4; }
+    else if (left >= 2) { lc3d_bwd_kernel<2><<<grid, 256, smem, st>>>(x, kernel, grad_out, grad_x, grad_kernel, g, b, cq_log2, acc); b += 2; }
+    else { lc3d_bwd_kernel<1><<<grid, 256, smem, st>>>(x, kernel, grad_out, grad_x, grad_kernel, g, b, cq_log2, acc); b += 1; }
+    int rc = check_launch("lc3d_bwd_kernel");
+    if (rc != NRT_OK) return rc;
+  }
+  return NRT_OK;
 }

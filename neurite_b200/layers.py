@@ -312,6 +312,46 @@ class LocallyConnected3D(_Layer):
         return dict(list(base_config.items()) + list(config.items()))
 
 
+_TORCH_ACT = {None: None, 'linear': None, 'relu': torch.relu, 'sigmoid': torch.sigmoid, 'tanh': torch.tanh}
+
+
+def _lc3d_raw(x, k, b, kernel_size, strides, feature_order, act_id, p0, p_count):
+    B, Cin, Cout = x.shape[0], x.shape[-1], k.shape[-1]
+    out = torch.empty((B, p_count, Cout), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.nrt_lc3d_fwd_f32(ptr(x), ptr(k), ptr(b), ptr(out), B, i32_array(x.shape[1:4]), Cin, Cout,
+                                   i32_array(kernel_size), i32_array(strides), feature_order, act_id,
+                                   int(p0), int(p_count), stream_ptr(x.device)))
+    return out
+
+
+class _LocalConv3dFn(torch.autograd.Function):
+    """autograd shell around nrt_lc3d_fwd_f32 / nrt_lc3d_bwd_f32 (linear activation inside;
+    the activation, if any, is applied by torch on the result so its derivative is torch's)."""
+
+    @staticmethod
+    def forward(ctx, x, k, b, kernel_size, strides, feature_order, p0, p_count):
+        ctx.save_for_backward(x, k)
+        ctx.args = (tuple(kernel_size), tuple(strides), feature_order, p0, p_count, b is not None)
+        return _lc3d_raw(x.detach(), k.detach(), None if b is None else b.detach(), kernel_size, strides,
+                         feature_order, 0, p0, p_count)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, k = ctx.saved_tensors
+        kernel_size, strides, feature_order, p0, p_count, has_bias = ctx.args
+        g = g.contiguous().to(torch.float32)
+        gx = torch.zeros_like(x) if ctx.needs_input_grad[0] else None
+        gk = torch.empty_like(k) if ctx.needs_input_grad[1] else None
+        if gx is not None or gk is not None:
+            with torch.cuda.device(x.device):
+                check(lib.nrt_lc3d_bwd_f32(ptr(x), ptr(k), ptr(g), ptr(gx), ptr(gk), x.shape[0], i32_array(x.shape[1:4]),
+                                           x.shape[-1], k.shape[-1], i32_array(kernel_size), i32_array(strides),
+                                           feature_order, int(p0), int(p_count), stream_ptr(x.device)))
+        gb = g.sum(0) if (has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gk, gb, None, None, None, None, None
+
+
 def local_conv3d(inputs, kernel, bias, kernel_size, strides, output_shape, data_format='channels_last',
                  activation=None, p0=0, p_count=None):
     """LocallyConnected3D.local_conv + bias + activation (layers.py:1126-1197, 1098-1101).
@@ -322,30 +362,30 @@ def local_conv3d(inputs, kernel, bias, kernel_size, strides, output_shape, data_
     if data_format not in {'channels_first', 'channels_last'}:
         raise ValueError('Unknown data_format: ' + str(data_format))
     require_cuda(inputs, kernel, bias)
-    fused_act = activation if (activation is None or isinstance(activation, str)) else None
     x = inputs.to(torch.float32)
     if data_format == 'channels_first':
         x = x.permute(0, 2, 3, 4, 1)
     x = x.contiguous()
-    k = kernel.detach().to(torch.float32).contiguous()
-    B, Cin = x.shape[0], x.shape[-1]
-    Cout = k.shape[-1]
+    k = kernel.to(torch.float32).contiguous()
+    B, Cout = x.shape[0], k.shape[-1]
     P = int(np.prod(output_shape))
     if p_count is None:
         p_count = P - p0
-    b = None
-    if bias is not None:
-        b = bias.detach().to(torch.float32).contiguous().reshape(-1, Cout)
-    out = torch.empty((B, p_count, Cout), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
-        check(lib.nrt_lc3d_fwd_f32(ptr(x), ptr(k), ptr(b), ptr(out), B, i32_array(x.shape[1:4]), Cin, Cout,
-                                   i32_array(kernel_size), i32_array(strides),
-                                   1 if data_format == 'channels_first' else 0,
-                                   _lib.ACTIVATIONS[fused_act], int(p0), int(p_count), stream_ptr(x.device)))
+    b = None if bias is None else bias.to(torch.float32).contiguous().reshape(-1, Cout)
+    feature_order = 1 if data_format == 'channels_first' else 0
+    needs_grad = torch.is_grad_enabled() and (x.requires_grad or k.requires_grad or (b is not None and b.requires_grad))
+    if needs_grad:
+        out = _LocalConv3dFn.apply(x, k, b, tuple(kernel_size), tuple(strides), feature_order, int(p0), int(p_count))
+        post = activation if callable(activation) else _TORCH_ACT[activation]
+    else:
+        fused = activation if (activation is None or isinstance(activation, str)) else None
+        out = _lc3d_raw(x, k.detach(), None if b is None else b.detach(), kernel_size, strides, feature_order,
+                        _lib.ACTIVATIONS[fused], p0, p_count)
+        post = activation if callable(activation) else None
     if p_count == P:
         out = out.reshape((B,) + tuple(output_shape) + (Cout,))
         if data_format == 'channels_first':
             out = out.permute(0, 4, 1, 2, 3).contiguous()
-    if callable(activation):
-        out = activation(out)
+    if post is not None:
+        out = post(out)
     return out

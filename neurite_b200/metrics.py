@@ -96,6 +96,69 @@ def dice_finalize(sums, laplace_smoothing=0.):
     return out
 
 
+class _DiceFn(torch.autograd.Function):
+    """autograd shell: nrt_dice_sums_f32 + nrt_dice_finalize_f32 forward, nrt_dice_bwd_f32 backward."""
+
+    @staticmethod
+    def forward(ctx, y_true, y_pred, check, laplace):
+        t = y_true.detach().to(torch.float32).contiguous()
+        p = y_pred.detach().to(torch.float32).contiguous()
+        sums, flag = dice_sums(t, p, False, check, None)
+        if check and int(flag.item()) != 0:
+            raise InvalidArgumentError('value outside range')
+        ctx.save_for_backward(t, p, sums)
+        ctx.laplace = laplace
+        return dice_finalize(sums, laplace)
+
+    @staticmethod
+    def backward(ctx, g):
+        t, p, sums = ctx.saved_tensors
+        g = g.contiguous().to(torch.float32)
+        B, L = sums.shape[0], sums.shape[1]
+        V = t.numel() // max(B * L, 1)
+        gt = torch.empty_like(t) if ctx.needs_input_grad[0] else None
+        gp = torch.empty_like(p) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(t.device):
+            check(lib.nrt_dice_bwd_f32(ptr(t), ptr(p), ptr(sums), ptr(g), B, V, L, ctx.laplace, ptr(gt), ptr(gp),
+                                       stream_ptr(t.device)))
+        return gt, gp, None, None
+
+
+class _CceFn(torch.autograd.Function):
+    """autograd shell: nrt_cce_f32 forward, nrt_cce_bwd_f32 backward (gradient wrt y_pred)."""
+
+    @staticmethod
+    def forward(ctx, t, p, lw, sw, from_logits, smoothing, reduction):
+        C = p.shape[-1]
+        n = p.numel() // C
+        per = torch.empty(p.shape[:-1], dtype=torch.float32, device=p.device) if reduction == 'none' else None
+        total = torch.empty(1, dtype=torch.float32, device=p.device)
+        ws_bytes = lib.nrt_cce_workspace_bytes()
+        ws = _workspace(p.device, ws_bytes)
+        with torch.cuda.device(p.device):
+            check(lib.nrt_cce_f32(ptr(t), ptr(p), ptr(lw), ptr(sw), n, C, int(from_logits), float(smoothing),
+                                  ptr(per), ptr(total), ptr(ws), ws_bytes, stream_ptr(p.device)))
+        ctx.save_for_backward(t, p, lw, sw)
+        ctx.args = (from_logits, smoothing, reduction, n, C)
+        if reduction == 'none':
+            return per
+        return total[0] if reduction == 'sum' else total[0] / n
+
+    @staticmethod
+    def backward(ctx, g):
+        t, p, lw, sw = ctx.saved_tensors
+        from_logits, smoothing, reduction, n, C = ctx.args
+        g = g.contiguous().to(torch.float32)
+        gp = torch.empty_like(p)
+        gper = g if reduction == 'none' else None
+        gscal = g.reshape(1) if reduction != 'none' else None
+        scale = 1.0 / n if reduction == 'sum_over_batch_size' else 1.0
+        with torch.cuda.device(p.device):
+            check(lib.nrt_cce_bwd_f32(ptr(t), ptr(p), ptr(lw), ptr(sw), n, C, int(from_logits), float(smoothing),
+                                      ptr(gscal), scale, ptr(gper), ptr(gp), stream_ptr(p.device)))
+        return None, gp, None, None, None, None, None
+
+
 class Dice:
     """Dice of two Tensors -- reference metrics.py:339-519."""
 
@@ -135,6 +198,11 @@ class Dice:
                 y_true = argmax_labels(y_true)
             sums = dice_label_sums(y_true, y_pred, self.nb_labels, self.group)           # :467-477 fused
         else:
+            needs_grad = torch.is_grad_enabled() and (y_pred.requires_grad or y_true.requires_grad)
+            if needs_grad:
+                if self.normalize or self.group is not None:
+                    raise NotImplementedError('Dice gradients are built for normalize=False on one device')
+                return _DiceFn.apply(y_true, y_pred, bool(self.check_input_limits), float(self.laplace_smoothing))
             sums, flag = dice_sums(y_true, y_pred, self.normalize, self.check_input_limits, self.group)
             if self.check_input_limits and int(flag.item()) != 0:                         # :439-444
                 raise InvalidArgumentError('value outside range')
@@ -223,6 +291,10 @@ class CategoricalCrossentropy:
         if sample_weight is not None:
             sw = torch.as_tensor(sample_weight, dtype=torch.float32, device=p.device)
             sw = sw.expand(p.shape[:-1]).contiguous() if sw.dim() > 0 else sw.expand(p.shape[:-1]).contiguous()
+        if torch.is_grad_enabled() and y_pred.requires_grad:
+            if self.group is not None:
+                raise NotImplementedError('CCE gradients are built for one device')
+            return _CceFn.apply(t, p, lw, sw, bool(self.from_logits), float(self.label_smoothing), self.reduction)
         per = torch.empty(p.shape[:-1], dtype=torch.float32, device=p.device) if self.reduction == 'none' else None
         total = torch.empty(1, dtype=torch.float32, device=p.device)
         ws_bytes = lib.nrt_cce_workspace_bytes()

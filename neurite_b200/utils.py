@@ -55,6 +55,19 @@ def interpn(vol, loc, interp_method='linear', fill_value=None):
         raise TypeError('linear interpolation needs a floating-point volume (reference: dtype error in wt * vol_val)')
     vol32 = _as_f32(vol).contiguous()
     loc32 = _as_f32(loc).contiguous()                                   # :123-127
+    if torch.is_grad_enabled() and (vol32.requires_grad or loc32.requires_grad):
+        out = _InterpnFn.apply(vol32, loc32, method, fill_value)
+    else:
+        out = _interpn_raw(vol32, loc32, method, fill_value)
+    if out.dtype != out_dtype:
+        out = out.to(out_dtype)
+    if input_vol_ndim == nb_dims:                                       # :216-218
+        out = out[..., 0]
+    return out
+
+
+def _interpn_raw(vol32, loc32, method, fill_value):
+    nb_dims = loc32.shape[-1]
     C = vol32.shape[-1]
     out_shape = tuple(loc32.shape[:-1])
     n_out = int(np.prod(out_shape)) if len(out_shape) else 1
@@ -63,11 +76,30 @@ def interpn(vol, loc, interp_method='linear', fill_value=None):
         check(lib.nrt_interpn_f32(ptr(vol32), i32_array(vol32.shape[:-1]), nb_dims, C, ptr(loc32), n_out, method,
                                   0 if fill_value is None else 1, 0.0 if fill_value is None else float(fill_value),
                                   ptr(out), stream_ptr(vol32.device)))
-    if out.dtype != out_dtype:
-        out = out.to(out_dtype)
-    if input_vol_ndim == nb_dims:                                       # :216-218
-        out = out[..., 0]
     return out
+
+
+class _InterpnFn(torch.autograd.Function):
+    """autograd shell around nrt_interpn_f32 / nrt_interpn_bwd_f32 (TF autodiff semantics)."""
+
+    @staticmethod
+    def forward(ctx, vol32, loc32, method, fill_value):
+        ctx.save_for_backward(vol32, loc32)
+        ctx.method, ctx.fill = method, fill_value
+        return _interpn_raw(vol32.detach(), loc32.detach(), method, fill_value)
+
+    @staticmethod
+    def backward(ctx, g):
+        vol32, loc32 = ctx.saved_tensors
+        g = g.contiguous().to(torch.float32)
+        D, C = loc32.shape[-1], vol32.shape[-1]
+        gvol = torch.zeros_like(vol32) if ctx.needs_input_grad[0] else None
+        gloc = torch.empty_like(loc32) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(vol32.device):
+            check(lib.nrt_interpn_bwd_f32(ptr(vol32), i32_array(vol32.shape[:-1]), D, C, ptr(loc32),
+                                          loc32.numel() // D, ctx.method, 0 if ctx.fill is None else 1, ptr(g),
+                                          ptr(gvol), ptr(gloc), stream_ptr(vol32.device)))
+        return gvol, gloc, None, None
 
 
 # ---------------------------------------------------------------------------------------
@@ -83,15 +115,42 @@ def _resize_batched(x, zoom_factor, interp_method, out_z0=0, out_n0=None):
     in_shape = [int(s) for s in x.shape[1:-1]]
     new_shape = [int(in_shape[f] * zoom_factor[f]) for f in range(ndims)]   # :256-257
     x32 = _as_f32(x).contiguous()
-    B, C = x32.shape[0], x32.shape[-1]
     if out_n0 is None:
         out_n0 = new_shape[0]
-    out = torch.empty((B, out_n0) + tuple(new_shape[1:]) + (C,), dtype=torch.float32, device=x.device)
-    if out.numel():
-        with torch.cuda.device(x.device):
-            check(lib.nrt_resize_f32(ptr(x32), ptr(out), B, i32_array(in_shape), i32_array(new_shape), ndims, C,
-                                     method, out_z0, out_n0, stream_ptr(x.device)))
+    if torch.is_grad_enabled() and x32.requires_grad:
+        if out_z0 != 0 or out_n0 != new_shape[0]:
+            raise NotImplementedError('gradients are built for whole-volume resize only')
+        out = _ResizeFn.apply(x32, tuple(in_shape), tuple(new_shape), method)
+    else:
+        out = _resize_raw(x32, in_shape, new_shape, method, out_z0, out_n0)
     return out if x.dtype == torch.float32 else out.to(x.dtype)
+
+
+def _resize_raw(x32, in_shape, new_shape, method, out_z0, out_n0):
+    B, C = x32.shape[0], x32.shape[-1]
+    ndims = len(in_shape)
+    out = torch.empty((B, out_n0) + tuple(new_shape[1:]) + (C,), dtype=torch.float32, device=x32.device)
+    if out.numel():
+        with torch.cuda.device(x32.device):
+            check(lib.nrt_resize_f32(ptr(x32), ptr(out), B, i32_array(in_shape), i32_array(new_shape), ndims, C,
+                                     method, out_z0, out_n0, stream_ptr(x32.device)))
+    return out
+
+
+class _ResizeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x32, in_shape, new_shape, method):
+        ctx.in_shape, ctx.new_shape, ctx.method, ctx.xshape = in_shape, new_shape, method, tuple(x32.shape)
+        return _resize_raw(x32.detach(), in_shape, new_shape, method, 0, new_shape[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().to(torch.float32)
+        gx = torch.zeros(ctx.xshape, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            check(lib.nrt_resize_bwd_f32(ptr(g), ptr(gx), ctx.xshape[0], i32_array(ctx.in_shape), i32_array(ctx.new_shape),
+                                         len(ctx.in_shape), ctx.xshape[-1], ctx.method, stream_ptr(g.device)))
+        return gx, None, None, None
 
 
 def resize(vol, zoom_factor, interp_method='linear'):
@@ -146,14 +205,48 @@ def _warp_batched(vol, flow, interp_method='linear', fill_value=None, halo=0,
         raise ValueError('vol %s and flow %s disagree on batch / trailing spatial dims'
                          % (tuple(vol.shape), tuple(flow.shape)))
     shape = [int(full_s0)] + [int(s) for s in vol32.shape[2:-1]]
-    out = torch.empty(tuple(flow32.shape[:-1]) + (C,), dtype=torch.float32, device=vol.device)
+    slab = (int(src_z0), int(src_n0), int(out_z0), int(out_n0))
+    if torch.is_grad_enabled() and (vol32.requires_grad or flow32.requires_grad):
+        if slab != (0, shape[0], 0, shape[0]):
+            raise NotImplementedError('gradients are built for whole-volume warps only')
+        out = _WarpFn.apply(vol32, flow32, tuple(shape), method, fill_value, int(halo))
+    else:
+        out = _warp_raw(vol32, flow32, shape, method, fill_value, slab, int(halo), err_flag)
+    return out if vol.dtype == torch.float32 else out.to(vol.dtype)
+
+
+def _warp_raw(vol32, flow32, shape, method, fill_value, slab, halo, err_flag):
+    B, C, D = vol32.shape[0], vol32.shape[-1], flow32.shape[-1]
+    out = torch.empty(tuple(flow32.shape[:-1]) + (C,), dtype=torch.float32, device=vol32.device)
     if out.numel():
-        with torch.cuda.device(vol.device):
+        with torch.cuda.device(vol32.device):
             check(lib.nrt_warp_f32(ptr(vol32), ptr(flow32), ptr(out), B, i32_array(shape), D, C, method,
                                    0 if fill_value is None else 1, 0.0 if fill_value is None else float(fill_value),
-                                   int(src_z0), int(src_n0), int(out_z0), int(out_n0), int(halo),
-                                   ptr(err_flag), stream_ptr(vol.device)))
-    return out if vol.dtype == torch.float32 else out.to(vol.dtype)
+                                   slab[0], slab[1], slab[2], slab[3], halo, ptr(err_flag), stream_ptr(vol32.device)))
+    return out
+
+
+class _WarpFn(torch.autograd.Function):
+    """autograd shell around nrt_warp_f32 / nrt_warp_bwd_f32."""
+
+    @staticmethod
+    def forward(ctx, vol32, flow32, shape, method, fill_value, halo):
+        ctx.save_for_backward(vol32, flow32)
+        ctx.shape, ctx.method, ctx.fill = shape, method, fill_value
+        return _warp_raw(vol32.detach(), flow32.detach(), list(shape), method, fill_value,
+                         (0, shape[0], 0, shape[0]), halo, None)
+
+    @staticmethod
+    def backward(ctx, g):
+        vol32, flow32 = ctx.saved_tensors
+        g = g.contiguous().to(torch.float32)
+        gvol = torch.zeros_like(vol32) if ctx.needs_input_grad[0] else None
+        gflow = torch.empty_like(flow32) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(vol32.device):
+            check(lib.nrt_warp_bwd_f32(ptr(vol32), ptr(flow32), ptr(g), ptr(gvol), ptr(gflow), vol32.shape[0],
+                                       i32_array(ctx.shape), flow32.shape[-1], vol32.shape[-1], ctx.method,
+                                       0 if ctx.fill is None else 1, stream_ptr(vol32.device)))
+        return gvol, gflow, None, None, None, None
 
 
 def transform(vol, loc_shift, interp_method='linear', indexing='ij', fill_value=None):

@@ -51,8 +51,10 @@ def main():
         for method in ('linear', 'nearest'):
             for label, env in [('generic', {'NRT_WARP_TILE': '0'})] + \
                               [('tile cfg%d halo%d' % (c, h), {'NRT_WARP_TILE': '1', 'NRT_WARP_TILE_CFG': str(c), 'H': h})
-                               for c in range(4) for h in ((3, 4) if fname != 'smooth8' else (3, 4, 6))]:
+                               for c in range(4) for h in ((3, 4) if fname != 'smooth8' else (3, 4, 6, 8))] + \
+                              [('persist %d' % pc, {'NRT_WARP_TILE': '1', 'NRT_WARP_PERSIST': str(pc), 'H': 3}) for pc in (1, 2, 3, 4, 5)]:
                 h = env.pop('H', 0)
+                os.environ['NRT_WARP_PERSIST'] = env.get('NRT_WARP_PERSIST', '0')
                 os.environ.update(env)
                 ms = timeit(lambda: utils._warp_batched(vol, flow, method, None, halo=h))
                 gbs = 20.0 * B * V / ms / 1e6
