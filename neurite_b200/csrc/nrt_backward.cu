@@ -228,7 +228,7 @@ cce_bwd_kernel(const float* __restrict__ t, const float* __restrict__ p, const f
         tv = tv * keep + add;
         const float q = pr[c] * rs;
         const float m = (q >= eps && q <= one_m_eps) ? 1.f : 0.f;
-        gp[r * C + c] = -up * rs * (tv * m / q - tsum);
+        gp[r * C + c] = -up * rs * ((m != 0.f ? tv / q : 0.f) - tsum);
       }
     } else {
       float mx = pr[0];

@@ -241,6 +241,88 @@ resize_kernel(const float* __restrict__ vol, float* __restrict__ out, ResizeGeo 
 }
 
 // ---------------------------------------------------------------------------------------
+// resize3d_kernel: D=3 zoom.  Sample coordinates are separable (one linspace per axis), so a
+// CTA first builds per-axis tables {offset(i0), offset(i1), wlo, whi} for its output tile in
+// shared memory (axis_linear on the linspace value: identical arithmetic to the generic
+// path), then every thread combines three table entries per voxel: no per-voxel floor/clip,
+// no div/mod, corner setup shared by all channels.
+// ---------------------------------------------------------------------------------------
+struct AxisEntry { int o0, o1; float wlo, whi; };
+
+template <int METHOD>
+__global__ void __launch_bounds__(256)
+resize3d_kernel(const float* __restrict__ vol, float* __restrict__ out, ResizeGeo w, int ntz, int nty, int ntx) {
+  constexpr int TZ = 8, TY = 8, TX = 32;
+  __shared__ AxisEntry s_ax[TZ + TY + TX];
+  const Geo& g = w.g;
+  const int C = g.C;
+  int tile = blockIdx.x;
+  const int tx = tile % ntx; tile /= ntx;
+  const int ty = tile % nty; tile /= nty;
+  const int tz = tile % ntz;
+  const int b = tile / ntz;
+  const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;            // z0 relative to the produced slab
+  if (threadIdx.x < TZ + TY + TX) {
+    const int t = threadIdx.x;
+    const int d = t < TZ ? 0 : (t < TZ + TY ? 1 : 2);
+    const int i = d == 0 ? w.out_z0 + z0 + t : (d == 1 ? y0 + (t - TZ) : x0 + (t - TZ - TY));
+    const int stride = d == 0 ? g.S[1] * g.S[2] * C : (d == 1 ? g.S[2] * C : C);
+    AxisEntry e;
+    if (i < w.M[d]) {
+      // tf.linspace(0, S-1, M): endpoints exact, interior 0 + delta*i  (utils.py:259)
+      const float loc = (i == w.M[d] - 1 && w.M[d] > 1) ? (float)(g.S[d] - 1) : __fmul_rn(w.delta[d], (float)i);
+      if (METHOD == NRT_LINEAR) {
+        const Axis a = axis_linear(loc, (float)(g.S[d] - 1), g.S[d] - 1);
+        e.o0 = a.i0 * stride; e.o1 = a.i1 * stride; e.wlo = a.wlo; e.whi = a.whi;
+      } else {
+        e.o0 = e.o1 = axis_nearest(loc, g.S[d] - 1) * stride; e.wlo = 1.f; e.whi = 0.f;
+      }
+    } else {
+      e.o0 = e.o1 = 0; e.wlo = e.whi = 0.f;
+    }
+    s_ax[t] = e;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int ox = x0 + lane, oy = y0 + wid;
+  if (ox >= w.M[2] || oy >= w.M[1]) return;
+  const AxisEntry ey = s_ax[TZ + wid], ex = s_ax[TZ + TY + lane];
+  const float* volb = vol + (size_t)b * w.src_batch_stride;
+  float* outb = out + ((size_t)b * w.out_vox + ((size_t)z0 * w.M[1] + oy) * w.M[2] + ox) * C;
+  const size_t plane = (size_t)w.M[1] * w.M[2] * C;
+#pragma unroll 2
+  for (int z = 0; z < TZ; ++z, outb += plane) {
+    if (z0 + z >= w.out_n0) break;
+    const AxisEntry ez = s_ax[z];
+    if (METHOD == NRT_LINEAR) {
+      const int b00 = ez.o0 + ey.o0, b01 = ez.o0 + ey.o1, b10 = ez.o1 + ey.o0, b11 = ez.o1 + ey.o1;
+      const float w00 = __fmul_rn(ez.wlo, ey.wlo), w01 = __fmul_rn(ez.wlo, ey.whi);
+      const float w10 = __fmul_rn(ez.whi, ey.wlo), w11 = __fmul_rn(ez.whi, ey.whi);
+      const float k0 = __fmul_rn(w00, ex.wlo), k1 = __fmul_rn(w00, ex.whi), k2 = __fmul_rn(w01, ex.wlo), k3 = __fmul_rn(w01, ex.whi);
+      const float k4 = __fmul_rn(w10, ex.wlo), k5 = __fmul_rn(w10, ex.whi), k6 = __fmul_rn(w11, ex.wlo), k7 = __fmul_rn(w11, ex.whi);
+      const float* p0 = volb + b00 + ex.o0; const float* p1 = volb + b00 + ex.o1;
+      const float* p2 = volb + b01 + ex.o0; const float* p3 = volb + b01 + ex.o1;
+      const float* p4 = volb + b10 + ex.o0; const float* p5 = volb + b10 + ex.o1;
+      const float* p6 = volb + b11 + ex.o0; const float* p7 = volb + b11 + ex.o1;
+      for (int c = 0; c < C; ++c) {
+        float r = __fadd_rn(0.f, __fmul_rn(k0, __ldg(p0 + c)));
+        r = __fadd_rn(r, __fmul_rn(k1, __ldg(p1 + c)));
+        r = __fadd_rn(r, __fmul_rn(k2, __ldg(p2 + c)));
+        r = __fadd_rn(r, __fmul_rn(k3, __ldg(p3 + c)));
+        r = __fadd_rn(r, __fmul_rn(k4, __ldg(p4 + c)));
+        r = __fadd_rn(r, __fmul_rn(k5, __ldg(p5 + c)));
+        r = __fadd_rn(r, __fmul_rn(k6, __ldg(p6 + c)));
+        r = __fadd_rn(r, __fmul_rn(k7, __ldg(p7 + c)));
+        outb[c] = r;
+      }
+    } else {
+      const float* p0 = volb + ez.o0 + ey.o0 + ex.o0;
+      for (int c = 0; c < C; ++c) outb[c] = __ldg(p0 + c);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // warp3d_tile_kernel: D=3, C=1, TMA-staged flow tile + source box in shared memory
 // ---------------------------------------------------------------------------------------
 struct TileGeo {
@@ -379,7 +461,7 @@ __device__ __forceinline__ float fill_if_oob(const Geo& g, float res, float lz, 
 }
 
 // Process one staged tile.  Warp w owns row y = w % TY of planes z = w / TY, + NW/TY, ...
-template <int TZ, int TY, int HALO, int NW, int METHOD>
+template <int TZ, int TY, int HALO, int NW, int METHOD, int U = 2>
 __device__ __forceinline__ void compute_tile(const float* __restrict__ s_flow, const float* __restrict__ s_box,
                                              const float* __restrict__ volb, float* __restrict__ outb,
                                              const TileGeo& w, int x0, int y0, int z0l) {
@@ -412,23 +494,124 @@ __device__ __forceinline__ void compute_tile(const float* __restrict__ s_flow, c
     const float* fl = s_flow + ((zs * TY + yy) * TX + lane) * 3;
     float* op = outb + ((size_t)(z0l + zs) * H + gy) * W + gx;
     if (interior) {
-#pragma unroll 2
-      for (int z = zs; z < TZ; z += ZSTEP, fl += ZSTEP * TY * TX * 3, op += (size_t)ZSTEP * H * W) {
+      // Branch-free main loop: a voxel whose corners are not all inside the staged box still
+      // runs the shared-memory arithmetic on a clamped (valid, meaningless) address and is
+      // recorded in `slow`; it is recomputed through global memory after the loop.  Without a
+      // divergent branch in the body the compiler can overlap the LDS latency of one
+      // iteration with the multiply/add chain of the previous one.
+      unsigned slow = 0;
+      const float* fl0 = fl;
+      float* op0 = op;
+#pragma unroll U
+      for (int z = zs, it = 0; z < TZ; z += ZSTEP, ++it, fl += ZSTEP * TY * TX * 3, op += (size_t)ZSTEP * H * W) {
         const float lz = __fadd_rn((float)(gz0 + z), fl[0]);
         const float ly = __fadd_rn(fy, fl[1]);
         const float lx = __fadd_rn(fx, fl[2]);
-        float res = sample_box_interior<BX, BY, BZ, METHOD>(s_box, oz, oy, ox, volb, g, lz, ly, lx);
+        float res;
+        if (METHOD == NRT_LINEAR) {
+          const int iz = __float2int_rd(lz), iy = __float2int_rd(ly), ix = __float2int_rd(lx);
+          const unsigned rz = (unsigned)(iz - oz), ry = (unsigned)(iy - oy), rx = (unsigned)(ix - ox);
+          const unsigned cz = min(rz, (unsigned)(BZ - 2)), cy = min(ry, (unsigned)(BY - 2)), cx = min(rx, (unsigned)(BX - 2));
+          const bool fast = (cz == rz) & (cy == ry) & (cx == rx);
+          // inside an interior box 0 <= loc < max on every axis, so clip() is the identity and
+          // i1 = i0 + 1: same values as axis_linear, without the min/max chain
+          const float wz0 = __fsub_rn(__fadd_rn((float)iz, 1.f), lz), wz1 = __fsub_rn(1.f, wz0);
+          const float wy0 = __fsub_rn(__fadd_rn((float)iy, 1.f), ly), wy1 = __fsub_rn(1.f, wy0);
+          const float wx0 = __fsub_rn(__fadd_rn((float)ix, 1.f), lx), wx1 = __fsub_rn(1.f, wx0);
+          const float* p = s_box + ((int)cz * BY + (int)cy) * BX + (int)cx;
+          float v[8];
+          v[0] = p[0];            v[1] = p[1];
+          v[2] = p[BX];           v[3] = p[BX + 1];
+          v[4] = p[BY * BX];      v[5] = p[BY * BX + 1];
+          v[6] = p[BY * BX + BX]; v[7] = p[BY * BX + BX + 1];
+          res = trilerp(v, wz0, wz1, wy0, wy1, wx0, wx1);
+          slow |= (fast ? 0u : 1u) << it;
+        } else {
+          const int iz = __float2int_rn(lz), iy = __float2int_rn(ly), ix = __float2int_rn(lx);
+          const unsigned rz = (unsigned)(iz - oz), ry = (unsigned)(iy - oy), rx = (unsigned)(ix - ox);
+          const unsigned cz = min(rz, (unsigned)(BZ - 1)), cy = min(ry, (unsigned)(BY - 1)), cx = min(rx, (unsigned)(BX - 1));
+          const bool fast = (cz == rz) & (cy == ry) & (cx == rx);
+          res = s_box[((int)cz * BY + (int)cy) * BX + (int)cx];
+          slow |= (fast ? 0u : 1u) << it;
+        }
         if (g.has_fill) res = fill_if_oob(g, res, lz, ly, lx);
         *op = res;
       }
+      while (slow) {                                   // rare: corners outside the staged box
+        const int it = __ffs(slow) - 1;
+        slow &= slow - 1;
+        const int z = zs + it * ZSTEP;
+        const float* f2 = fl0 + (size_t)it * ZSTEP * TY * TX * 3;
+        const float lz = __fadd_rn((float)(gz0 + z), f2[0]);
+        const float ly = __fadd_rn(fy, f2[1]);
+        const float lx = __fadd_rn(fx, f2[2]);
+        float res = sample_global3<METHOD>(volb, g, lz, ly, lx);
+        if (g.has_fill) res = fill_if_oob(g, res, lz, ly, lx);
+        op0[(size_t)it * ZSTEP * H * W] = res;
+      }
     } else if (gx < W && gy < H) {
-      for (int z = zs; z < TZ && z0l + z < w.out_n0; z += ZSTEP, fl += ZSTEP * TY * TX * 3, op += (size_t)ZSTEP * H * W) {
+      // border tile: the box overhangs the volume (or the resident planes); the reference's
+      // clip / min(i0+1, max) semantics are applied before indexing the valid part of the box,
+      // so edge voxels are still served from shared memory.  Same branch-free structure.
+      unsigned slow = 0;
+      const float* fl0 = fl;
+      float* op0 = op;
+      const float mz = (float)(g.S[0] - 1), my = (float)(H - 1), mx = (float)(W - 1);
+      const int nz_out = w.out_n0 - z0l;                  // planes of this tile inside the output
+#pragma unroll U
+      for (int z = zs, it = 0; z < TZ; z += ZSTEP, ++it, fl += ZSTEP * TY * TX * 3, op += (size_t)ZSTEP * H * W) {
+        if (z >= nz_out) break;
         const float lz = __fadd_rn((float)(gz0 + z), fl[0]);
         const float ly = __fadd_rn(fy, fl[1]);
         const float lx = __fadd_rn(fx, fl[2]);
-        float res = sample_box_border<BX, BY, BZ, METHOD>(s_box, oz, oy, ox, bb, volb, g, lz, ly, lx);
+        float res;
+        if (METHOD == NRT_LINEAR) {
+          const float xz = fminf(fmaxf(lz, 0.f), mz), xy = fminf(fmaxf(ly, 0.f), my), xx = fminf(fmaxf(lx, 0.f), mx);
+          const int iz0 = __float2int_rd(xz), iy0 = __float2int_rd(xy), ix0 = __float2int_rd(xx);
+          const int iz1 = min(iz0 + 1, g.S[0] - 1), iy1 = min(iy0 + 1, H - 1), ix1 = min(ix0 + 1, W - 1);
+          const bool fast = (iz0 >= bb.lo_z) & (iz1 <= bb.hi_z) & (iy0 >= bb.lo_y) & (iy1 <= bb.hi_y) &
+                            (ix0 >= bb.lo_x) & (ix1 <= bb.hi_x);
+          // weights exactly as axis_linear: wlo = f1 - x, whi = 1 - wlo
+          const float wz0 = __fsub_rn((float)iz1, xz), wz1 = __fsub_rn(1.f, wz0);
+          const float wy0 = __fsub_rn((float)iy1, xy), wy1 = __fsub_rn(1.f, wy0);
+          const float wx0 = __fsub_rn((float)ix1, xx), wx1 = __fsub_rn(1.f, wx0);
+          // clamp into the box so that the unconditional loads stay inside shared memory
+          const int cz0 = min(max(iz0 - oz, 0), BZ - 1), cz1 = min(max(iz1 - oz, 0), BZ - 1);
+          const int cy0 = min(max(iy0 - oy, 0), BY - 1), cy1 = min(max(iy1 - oy, 0), BY - 1);
+          const int cx0 = min(max(ix0 - ox, 0), BX - 1), cx1 = min(max(ix1 - ox, 0), BX - 1);
+          const float* r00 = s_box + (cz0 * BY + cy0) * BX;
+          const float* r01 = s_box + (cz0 * BY + cy1) * BX;
+          const float* r10 = s_box + (cz1 * BY + cy0) * BX;
+          const float* r11 = s_box + (cz1 * BY + cy1) * BX;
+          float v[8];
+          v[0] = r00[cx0]; v[1] = r00[cx1];
+          v[2] = r01[cx0]; v[3] = r01[cx1];
+          v[4] = r10[cx0]; v[5] = r10[cx1];
+          v[6] = r11[cx0]; v[7] = r11[cx1];
+          res = trilerp(v, wz0, wz1, wy0, wy1, wx0, wx1);
+          slow |= (fast ? 0u : 1u) << it;
+        } else {
+          const int iz = axis_nearest(lz, g.S[0] - 1), iy = axis_nearest(ly, H - 1), ix = axis_nearest(lx, W - 1);
+          const bool fast = (iz >= bb.lo_z) & (iz <= bb.hi_z) & (iy >= bb.lo_y) & (iy <= bb.hi_y) &
+                            (ix >= bb.lo_x) & (ix <= bb.hi_x);
+          const int cz = min(max(iz - oz, 0), BZ - 1), cy = min(max(iy - oy, 0), BY - 1), cx = min(max(ix - ox, 0), BX - 1);
+          res = s_box[(cz * BY + cy) * BX + cx];
+          slow |= (fast ? 0u : 1u) << it;
+        }
         if (g.has_fill) res = fill_if_oob(g, res, lz, ly, lx);
         *op = res;
+      }
+      while (slow) {                                   // corners outside the staged box
+        const int it = __ffs(slow) - 1;
+        slow &= slow - 1;
+        const int z = zs + it * ZSTEP;
+        const float* f2 = fl0 + (size_t)it * ZSTEP * TY * TX * 3;
+        const float lz = __fadd_rn((float)(gz0 + z), f2[0]);
+        const float ly = __fadd_rn(fy, f2[1]);
+        const float lx = __fadd_rn(fx, f2[2]);
+        float res = sample_global3<METHOD>(volb, g, lz, ly, lx);
+        if (g.has_fill) res = fill_if_oob(g, res, lz, ly, lx);
+        op0[(size_t)it * ZSTEP * H * W] = res;
       }
     }
   }
@@ -444,7 +627,7 @@ __device__ __forceinline__ void decode_tile(const TileGeo& w, int tile, int TXc,
 }
 
 // v1: one tile per CTA, several CTAs per SM overlap each other's load phase
-template <int TZ, int TY, int HALO, int METHOD>
+template <int TZ, int TY, int HALO, int METHOD, int U = 2>
 __global__ void __launch_bounds__(256)
 warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
                    const __grid_constant__ CUtensorMap tm_flow,
@@ -465,7 +648,7 @@ warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
   }
   __syncthreads();
   mbar_wait(bar, 0);
-  compute_tile<TZ, TY, HALO, 8, METHOD>(s_flow, s_box, vol + (size_t)b * w.src_batch_stride,
+  compute_tile<TZ, TY, HALO, 8, METHOD, U>(s_flow, s_box, vol + (size_t)b * w.src_batch_stride,
                                         out + (size_t)b * w.out_vox, w, x0, y0, z0l);
 }
 
@@ -579,7 +762,7 @@ static int env_int(const char* name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
-template <int TZ, int TY, int HALO, int METHOD>
+template <int TZ, int TY, int HALO, int METHOD, int U = 2>
 static int launch_tile(const float* vol, const float* flow, float* out, TileGeo tg, int H, int W, int src_n0,
                        int out_n0, cudaStream_t st) {
   using Cfg = TileCfg<TZ, TY, HALO>;
@@ -595,7 +778,7 @@ static int launch_tile(const float* vol, const float* flow, float* out, TileGeo 
   if (rc != NRT_OK) return rc;
   rc = encode_f32_4d(&tmf, flow, fd, fb);
   if (rc != NRT_OK) return rc;
-  auto kern = warp3d_tile_kernel<TZ, TY, HALO, METHOD>;
+  auto kern = warp3d_tile_kernel<TZ, TY, HALO, METHOD, U>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM) != cudaSuccess)
@@ -701,7 +884,7 @@ static int try_tile_path(const float* vol, const float* flow, float* out, int B,
   // tile shapes (TZ x TY x 32) and halos built: the default 8x8x32 runs 4 CTAs per SM (best
   // measured on B200, profiles/); `halo` picks the smallest built halo that covers it.
   int cfg = env_int("NRT_WARP_TILE_CFG", 2);         // 0: 8x16x32, 1: 16x16x32, 2: 8x8x32, 3: 4x8x32
-  if (cfg < 0 || cfg > 3) cfg = 2;
+  if (cfg < 0 || cfg > 6) cfg = 2;
   if (halo <= 0) halo = 3;
   const int hsel = halo <= 3 ? 3 : (halo <= 4 ? 4 : (halo <= 6 ? 6 : 8));
   TileGeo tg;
@@ -740,6 +923,12 @@ static int try_tile_path(const float* vol, const float* flow, float* out, int B,
   NRT_TILE_CASE(2, 8, 8, 3) NRT_TILE_CASE(2, 8, 8, 4) NRT_TILE_CASE(2, 8, 8, 6) NRT_TILE_CASE(2, 8, 8, 8)
   NRT_TILE_CASE(3, 4, 8, 3) NRT_TILE_CASE(3, 4, 8, 4) NRT_TILE_CASE(3, 4, 8, 6) NRT_TILE_CASE(3, 4, 8, 8)
 #undef NRT_TILE_CASE
+  // experimental unroll variants of the default tile (halo 3 only)
+  if (hsel == 3 && cfg >= 4) {
+    if (cfg == 4) rc = method == NRT_LINEAR ? launch_tile<8, 8, 3, NRT_LINEAR, 4>(vol, flow, out, tg, H, W, src_n0, out_n0, st) : launch_tile<8, 8, 3, NRT_NEAREST, 4>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
+    if (cfg == 5) rc = method == NRT_LINEAR ? launch_tile<8, 8, 3, NRT_LINEAR, 8>(vol, flow, out, tg, H, W, src_n0, out_n0, st) : launch_tile<8, 8, 3, NRT_NEAREST, 8>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
+    if (cfg == 6) rc = method == NRT_LINEAR ? launch_tile<8, 8, 3, NRT_LINEAR, 1>(vol, flow, out, tg, H, W, src_n0, out_n0, st) : launch_tile<8, 8, 3, NRT_NEAREST, 1>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
+  }
   if (rc == 1) return NRT_OK;                              // not launched: fall back
   *used = true;
   return rc;
@@ -835,6 +1024,15 @@ int nrt_resize_f32(const float* vol, float* out, int B, const int32_t* in_shape,
   rg.out_vox = out_plane * out_n0;
   if (B == 0 || rg.out_vox == 0) return NRT_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (D == 3 && in_vox * C <= 0x7fffffffLL && getenv("NRT_RESIZE_GENERIC") == nullptr) {
+    const int ntz = (out_n0 + 7) / 8, nty = (rg.M[1] + 7) / 8, ntx = (rg.M[2] + 31) / 32;
+    const int64_t grid = (int64_t)B * ntz * nty * ntx;
+    if (grid <= 0x7fffffffLL) {
+      if (method == NRT_LINEAR) resize3d_kernel<NRT_LINEAR><<<(int)grid, 256, 0, st>>>(vol, out, rg, ntz, nty, ntx);
+      else resize3d_kernel<NRT_NEAREST><<<(int)grid, 256, 0, st>>>(vol, out, rg, ntz, nty, ntx);
+      return check_launch("resize3d_kernel");
+    }
+  }
 #define CALL(DD, MM) launch_resize<DD, MM>(vol, out, rg, st)
   NRT_DISPATCH_D_METHOD(D, method, CALL);
 #undef CALL

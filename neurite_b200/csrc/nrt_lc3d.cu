@@ -113,46 +113,48 @@ lc3d_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel
   }
 
   // ===== consumer warps =====
-  // lane -> (j-slice, batch item, output-channel quad): fq = lane % CQ, b = (lane / CQ) % BB,
-  // slice = lane / (CQ*BB).  The BB batch items of a position are contracted at the same time
-  // by different lanes (weights are read once per position from shared memory, broadcast
-  // across the batch lanes); the 32/(CQ*BB) slices split the F patch features.
-  constexpr int BB_LOG2 = BB == 1 ? 0 : (BB == 2 ? 1 : (BB == 4 ? 2 : 3));
+  // One warp per position.  Lane l reads float4 l, l+32, ... of the staged weight block:
+  // patch feature j = i / CQ, output-channel quad fq = i % CQ = l % CQ (fixed per lane), so the
+  // block is read exactly once, conflict-free, and each lane keeps BB x 4 accumulators.
+  const int n4 = g.F * CQ;                      // float4s per block
   const int fq = lane & (CQ - 1);
-  const int bl = (lane >> cq_log2) & (BB - 1);
-  const int js = lane >> (cq_log2 + BB_LOG2);
-  const int JS = 32 >> (cq_log2 + BB_LOG2);
-  const int iters = (g.F + JS - 1) / JS;
-  constexpr int CH = 27;
+  // The input values a lane needs do not depend on the weights: gather a chunk of them from
+  // L1/L2 into registers first (CH*BB independent loads in flight; the first chunk is issued
+  // before waiting for the TMA), then run the LDS.128 + FFMA chain with no global latency in it.
+  constexpr int CH = (27 * BB <= 54) ? 27 : (48 / BB);
+  const int iters = (n4 + 31) >> 5;
   int k = wid;
   for (int64_t n = (int64_t)blockIdx.x + (int64_t)wid * gridDim.x; n < g.pn;
        n += (int64_t)kLcWarps * gridDim.x, k += kLcWarps) {
     const int slot = k % stages;
     const uint32_t ph = (uint32_t)((k / stages) & 1);
-    const int64_t p = g.p0 + n;
-    const float* xp = x + (int64_t)(b_base + bl) * g.x_batch + patch_origin(g, p);
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    const float* xp = x + (int64_t)b_base * g.x_batch + patch_origin(g, g.p0 + n);
+    float acc[BB][4];
+#pragma unroll
+    for (int b = 0; b < BB; ++b) { acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.f; }
     const float4* w4 = reinterpret_cast<const float4*>(smem_raw + (size_t)slot * blk_stride);
-    // The input values a lane needs do not depend on the weights: gather a chunk of them from
-    // L1/L2 into registers first (CH independent loads in flight; the first chunk is issued
-    // before waiting for the TMA), then run the LDS.128 + FFMA chain with no global latency in it.
     for (int i0 = 0; i0 < iters; i0 += CH) {
-      float xv[CH];
+      float xv[CH][BB];
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
-        const int j = js + (i0 + c) * JS;
-        xv[c] = (j < g.F) ? __ldg(xp + s_jmap[j]) : 0.f;
+        const int i = lane + ((i0 + c) << 5);
+        const int off = (i < n4) ? s_jmap[i >> cq_log2] : 0;
+#pragma unroll
+        for (int b = 0; b < BB; ++b) xv[c][b] = __ldg(xp + (int64_t)b * g.x_batch + off);
       }
       if (i0 == 0) mbar_wait(full + slot, ph);
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
-        const int j = js + (i0 + c) * JS;
-        if (j < g.F) {
-          const float4 wv = w4[(j << cq_log2) + fq];
-          acc0 = fmaf(xv[c], wv.x, acc0);
-          acc1 = fmaf(xv[c], wv.y, acc1);
-          acc2 = fmaf(xv[c], wv.z, acc2);
-          acc3 = fmaf(xv[c], wv.w, acc3);
+        const int i = lane + ((i0 + c) << 5);
+        if (i < n4) {
+          const float4 wv = w4[i];
+#pragma unroll
+          for (int b = 0; b < BB; ++b) {
+            acc[b][0] = fmaf(xv[c][b], wv.x, acc[b][0]);
+            acc[b][1] = fmaf(xv[c][b], wv.y, acc[b][1]);
+            acc[b][2] = fmaf(xv[c][b], wv.z, acc[b][2]);
+            acc[b][3] = fmaf(xv[c][b], wv.w, acc[b][3]);
+          }
         }
       }
     }
@@ -160,22 +162,24 @@ lc3d_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel
     if (lane == 0) {                             // slot free: every lane has read its share
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(empty + slot)) : "memory");
     }
-    // fold the j-slices
-    for (int o = 16; o >= (CQ << BB_LOG2); o >>= 1) {
-      acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
-      acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
-      acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
-      acc3 += __shfl_xor_sync(0xffffffffu, acc3, o);
-    }
-    if (js == 0) {
+    // fold the 32/CQ lanes that share an output quad
+#pragma unroll
+    for (int b = 0; b < BB; ++b)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        for (int o = 16; o >= CQ; o >>= 1) acc[b][q] += __shfl_xor_sync(0xffffffffu, acc[b][q], o);
+    if (lane < CQ) {
       float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
       if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + n * g.Cout) + fq);
-      float4 r;
-      r.x = activate(acc0 + bv.x, g.activation);
-      r.y = activate(acc1 + bv.y, g.activation);
-      r.z = activate(acc2 + bv.z, g.activation);
-      r.w = activate(acc3 + bv.w, g.activation);
-      reinterpret_cast<float4*>(out + ((int64_t)(b_base + bl) * g.pn + n) * g.Cout)[fq] = r;
+#pragma unroll
+      for (int b = 0; b < BB; ++b) {
+        float4 r;
+        r.x = activate(acc[b][0] + bv.x, g.activation);
+        r.y = activate(acc[b][1] + bv.y, g.activation);
+        r.z = activate(acc[b][2] + bv.z, g.activation);
+        r.w = activate(acc[b][3] + bv.w, g.activation);
+        reinterpret_cast<float4*>(out + ((int64_t)(b_base + b) * g.pn + n) * g.Cout)[fq] = r;
+      }
     }
   }
 }
@@ -321,12 +325,11 @@ extern "C" int nrt_lc3d_fwd_f32(const float* x, const float* kernel, const float
     int cq_log2 = 0;
     while ((1 << cq_log2) < cq) ++cq_log2;
     int b = 0, rc = NRT_OK;
-    const int max_bb = 32 / cq;                  // batch items that fit the lanes of one warp
     while (b < B && rc == NRT_OK) {
       const int left = B - b;
-      if (left >= 8 && max_bb >= 8) { rc = launch_stream<8>(x, kernel, bias, out, g, b, cq_log2, st); b += 8; }
-      else if (left >= 4 && max_bb >= 4) { rc = launch_stream<4>(x, kernel, bias, out, g, b, cq_log2, st); b += 4; }
-      else if (left >= 2 && max_bb >= 2) { rc = launch_stream<2>(x, kernel, bias, out, g, b, cq_log2, st); b += 2; }
+      if (left >= 8) { rc = launch_stream<8>(x, kernel, bias, out, g, b, cq_log2, st); b += 8; }
+      else if (left >= 4) { rc = launch_stream<4>(x, kernel, bias, out, g, b, cq_log2, st); b += 4; }
+      else if (left >= 2) { rc = launch_stream<2>(x, kernel, bias, out, g, b, cq_log2, st); b += 2; }
       else { rc = launch_stream<1>(x, kernel, bias, out, g, b, cq_log2, st); b += 1; }
     }
     if (rc <= 0) return rc;       // rc == 1: weight block does not fit the ring -> generic

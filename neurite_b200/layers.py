@@ -157,7 +157,7 @@ class SpatialTransformer(_Layer):
         assert len(inputs) == 2, 'inputs has to be len 2, found: %d' % len(inputs)
         vol, trf = inputs
         nd = vol.dim() - 2
-        if trf.dim() == 3:                                                     # affine [B, N, N+1]
+        if trf.dim() == 3 and tuple(trf.shape[1:]) == (nd, nd + 1):            # affine [B, N, N+1]
             trf = self._affine_to_dense(trf, tuple(vol.shape[1:-1]) if self.shape is None else tuple(self.shape))
         if self.indexing == 'xy':                                              # swap the first two shift channels
             trf = torch.cat([trf[..., 1:2], trf[..., 0:1], trf[..., 2:]], -1)

@@ -287,7 +287,7 @@ def test_lc3d_golden(ne, monkeypatch, name, generic):
         if use_bias:
             lay.bias.copy_(torch.from_numpy(g['bias']))
     lay.cuda()
-    out = lay(dev(g['x'])).cpu().numpy()
+    out = lay(dev(g['x'])).detach().cpu().numpy()
     assert out.shape == g['out'].shape
     np.testing.assert_allclose(out, g['out'], rtol=1e-5, atol=2e-5)
 

@@ -47,13 +47,18 @@ def main():
     b = torch.empty_like(a)
     ms = timeit(lambda: b.copy_(a))
     print('copy 20B/vox          : %.3f ms  %.0f GB/s' % (ms, 20.0 * B * V / ms / 1e6))
+    quick = os.environ.get('SWEEP_QUICK') == '1'
     for fname, flow in flows.items():
+        if quick and fname != 'iid3':
+            continue
         for method in ('linear', 'nearest'):
             for label, env in [('generic', {'NRT_WARP_TILE': '0'})] + \
                               [('tile cfg%d halo%d' % (c, h), {'NRT_WARP_TILE': '1', 'NRT_WARP_TILE_CFG': str(c), 'H': h})
-                               for c in range(4) for h in ((3, 4) if fname != 'smooth8' else (3, 4, 6, 8))] + \
+                               for c in range(7) for h in ((3, 4) if fname != 'smooth8' else (3, 4, 6, 8))] + \
                               [('persist %d' % pc, {'NRT_WARP_TILE': '1', 'NRT_WARP_PERSIST': str(pc), 'H': 3}) for pc in (1, 2, 3, 4, 5)]:
                 h = env.pop('H', 0)
+                if quick and not (label.startswith('tile cfg') and label.endswith('halo3') and label[8] in '23456'):
+                    continue
                 os.environ['NRT_WARP_PERSIST'] = env.get('NRT_WARP_PERSIST', '0')
                 os.environ.update(env)
                 ms = timeit(lambda: utils._warp_batched(vol, flow, method, None, halo=h))
