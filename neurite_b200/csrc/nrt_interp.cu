@@ -388,86 +388,74 @@ __device__ __forceinline__ float sample_global3(const float* __restrict__ volb, 
   }
 }
 
-// one voxel from a box that lies fully inside the resident volume: no clipping needed
-template <int BX, int BY, int BZ, int METHOD>
-__device__ __forceinline__ float sample_box_interior(const float* __restrict__ s_box, int oz, int oy, int ox,
-                                                     const float* __restrict__ volb, const Geo& g,
-                                                     float lz, float ly, float lx) {
-  if (METHOD == NRT_LINEAR) {
-    const int iz = __float2int_rd(lz), iy = __float2int_rd(ly), ix = __float2int_rd(lx);
-    const unsigned rz = (unsigned)(iz - oz), ry = (unsigned)(iy - oy), rx = (unsigned)(ix - ox);
-    if ((rz < (unsigned)(BZ - 1)) & (ry < (unsigned)(BY - 1)) & (rx < (unsigned)(BX - 1))) {
-      // inside an interior box 0 <= loc < max on every axis, so clip() is the identity and
-      // i1 = i0 + 1: same values as axis_linear, without the min/max chain
-      const float wz0 = __fsub_rn(__fadd_rn((float)iz, 1.f), lz), wz1 = __fsub_rn(1.f, wz0);
-      const float wy0 = __fsub_rn(__fadd_rn((float)iy, 1.f), ly), wy1 = __fsub_rn(1.f, wy0);
-      const float wx0 = __fsub_rn(__fadd_rn((float)ix, 1.f), lx), wx1 = __fsub_rn(1.f, wx0);
-      const float* p = s_box + ((int)rz * BY + (int)ry) * BX + (int)rx;
-      float v[8];
-      v[0] = p[0];            v[1] = p[1];
-      v[2] = p[BX];           v[3] = p[BX + 1];
-      v[4] = p[BY * BX];      v[5] = p[BY * BX + 1];
-      v[6] = p[BY * BX + BX]; v[7] = p[BY * BX + BX + 1];
-      return trilerp(v, wz0, wz1, wy0, wy1, wx0, wx1);
-    }
-    return sample_global3<METHOD>(volb, g, lz, ly, lx);
-  } else {
-    const int iz = __float2int_rn(lz), iy = __float2int_rn(ly), ix = __float2int_rn(lx);
-    const unsigned rz = (unsigned)(iz - oz), ry = (unsigned)(iy - oy), rx = (unsigned)(ix - ox);
-    if ((rz < (unsigned)BZ) & (ry < (unsigned)BY) & (rx < (unsigned)BX))
-      return s_box[((int)rz * BY + (int)ry) * BX + (int)rx];
-    return sample_global3<METHOD>(volb, g, lz, ly, lx);
-  }
-}
-
-// one voxel from a box that overhangs the volume / the resident planes (zero-filled by the
-// TMA there, never read): clip first, then test against the valid part of the box
-struct BoxBounds { int lo_z, hi_z, lo_y, hi_y, lo_x, hi_x; };
-
-template <int BX, int BY, int BZ, int METHOD>
-__device__ __forceinline__ float sample_box_border(const float* __restrict__ s_box, int oz, int oy, int ox,
-                                                   const BoxBounds& bb, const float* __restrict__ volb,
-                                                   const Geo& g, float lz, float ly, float lx) {
-  if (METHOD == NRT_LINEAR) {
-    const float mz = (float)(g.S[0] - 1), my = (float)(g.S[1] - 1), mx = (float)(g.S[2] - 1);
-    const float cz = fminf(fmaxf(lz, 0.f), mz), cy = fminf(fmaxf(ly, 0.f), my), cx = fminf(fmaxf(lx, 0.f), mx);
-    const float f0z = floorf(cz), f0y = floorf(cy), f0x = floorf(cx);
-    const int iz = __float2int_rz(f0z), iy = __float2int_rz(f0y), ix = __float2int_rz(f0x);
-    if ((iz >= bb.lo_z) & (iz < bb.hi_z) & (iy >= bb.lo_y) & (iy < bb.hi_y) & (ix >= bb.lo_x) & (ix < bb.hi_x)) {
-      const float wz0 = __fsub_rn(__fadd_rn(f0z, 1.f), cz), wz1 = __fsub_rn(1.f, wz0);
-      const float wy0 = __fsub_rn(__fadd_rn(f0y, 1.f), cy), wy1 = __fsub_rn(1.f, wy0);
-      const float wx0 = __fsub_rn(__fadd_rn(f0x, 1.f), cx), wx1 = __fsub_rn(1.f, wx0);
-      const float* p = s_box + ((iz - oz) * BY + (iy - oy)) * BX + (ix - ox);
-      float v[8];
-      v[0] = p[0];            v[1] = p[1];
-      v[2] = p[BX];           v[3] = p[BX + 1];
-      v[4] = p[BY * BX];      v[5] = p[BY * BX + 1];
-      v[6] = p[BY * BX + BX]; v[7] = p[BY * BX + BX + 1];
-      return trilerp(v, wz0, wz1, wy0, wy1, wx0, wx1);
-    }
-    return sample_global3<METHOD>(volb, g, lz, ly, lx);
-  } else {
-    const int iz = axis_nearest(lz, g.S[0] - 1), iy = axis_nearest(ly, g.S[1] - 1), ix = axis_nearest(lx, g.S[2] - 1);
-    if ((iz >= bb.lo_z) & (iz <= bb.hi_z) & (iy >= bb.lo_y) & (iy <= bb.hi_y) & (ix >= bb.lo_x) & (ix <= bb.hi_x))
-      return s_box[((iz - oz) * BY + (iy - oy)) * BX + (ix - ox)];
-    return sample_global3<METHOD>(volb, g, lz, ly, lx);
-  }
-}
-
 __device__ __forceinline__ float fill_if_oob(const Geo& g, float res, float lz, float ly, float lx) {
   const bool oob = (lz < 0.f) | (lz > (float)(g.S[0] - 1)) | (ly < 0.f) | (ly > (float)(g.S[1] - 1)) |
                    (lx < 0.f) | (lx > (float)(g.S[2] - 1));
   return apply_fill(res, oob, g.fill);
 }
 
-// Process one staged tile.  Warp w owns row y = w % TY of planes z = w / TY, + NW/TY, ...
-template <int TZ, int TY, int HALO, int NW, int METHOD, int U = 2>
-__device__ __forceinline__ void compute_tile(const float* __restrict__ s_flow, const float* __restrict__ s_box,
-                                             const float* __restrict__ volb, float* __restrict__ outb,
-                                             const TileGeo& w, int x0, int y0, int z0l) {
+// Per-axis corner setup against the staged box.
+//   EDGE = false: the box does not overhang the volume on this axis, so a sample whose two
+//     corners are in the box satisfies 0 <= loc < max: clip() is the identity, i1 = i0 + 1
+//     and the second corner sits at a compile-time stride.
+//   EDGE = true: the reference's clip / min(i0+1, max) is applied first; the second corner's
+//     offset becomes a run-time 0-or-stride.
+// `c0` is clamped into the box so the (unconditional) shared-memory loads are always legal;
+// `ok` says whether they were the right addresses.
+template <bool EDGE, int BDIM>
+struct AxisBox {
+  int c0;        // first corner, box-relative, clamped
+  int d;         // (second corner - first corner) in elements of this axis (EDGE only)
+  float wlo, whi;
+  bool ok;
+  __device__ __forceinline__ void setup(float loc, int o, int lo, int hi, int maxi) {
+    if (!EDGE) {
+      const int i0 = __float2int_rd(loc);
+      const unsigned r = (unsigned)(i0 - o);
+      const unsigned c = min(r, (unsigned)(BDIM - 2));
+      ok = (c == r);
+      c0 = (int)c;
+      d = 1;
+      wlo = __fsub_rn(__fadd_rn((float)i0, 1.f), loc);
+    } else {
+      const float x = fminf(fmaxf(loc, 0.f), (float)maxi);
+      const int i0 = __float2int_rd(x);
+      const int i1 = min(i0 + 1, maxi);
+      ok = (i0 >= lo) & (i1 <= hi);
+      d = i1 - i0;                                   // 0 at the volume's far edge, else 1
+      c0 = min(max(i0 - o, 0), BDIM - 1 - d);        // c0 + d stays inside the box
+      wlo = __fsub_rn((float)i1, x);
+    }
+    whi = __fsub_rn(1.f, wlo);
+  }
+};
+
+template <bool EDGE, int BDIM>
+__device__ __forceinline__ int nearest_box(float loc, int o, int lo, int hi, int maxi, bool& ok) {
+  const int i = EDGE ? axis_nearest(loc, maxi) : __float2int_rn(loc);
+  if (EDGE) {
+    ok = ok & (i >= lo) & (i <= hi);
+    return min(max(i - o, 0), BDIM - 1);
+  }
+  const unsigned r = (unsigned)(i - o);
+  const unsigned c = min(r, (unsigned)(BDIM - 1));
+  ok = ok & (c == r);
+  return (int)c;
+}
+
+struct BoxBounds { int lo_z, hi_z, lo_y, hi_y, lo_x, hi_x; };
+
+// The rows of one staged tile owned by this warp.  Branch-free main loop: a voxel whose
+// corners are not all inside the staged box still runs the shared-memory arithmetic on a
+// clamped (legal, meaningless) address and is recorded in `slow`; it is recomputed through
+// global memory after the loop.  Without a divergent branch in the body the compiler can
+// overlap the LDS latency of one iteration with the multiply/add chain of the previous one.
+template <int TZ, int TY, int HALO, int NW, int METHOD, int U, bool EZ, bool EY, bool EX>
+__device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, const float* __restrict__ s_box,
+                                          const float* __restrict__ volb, float* __restrict__ outb,
+                                          const TileGeo& w, int x0, int y0, int z0l, bool partial) {
   using Cfg = TileCfg<TZ, TY, HALO>;
   constexpr int TX = Cfg::TX, BX = Cfg::BX, BY = Cfg::BY, BZ = Cfg::BZ;
-  static_assert(NW % TY == 0 || TY % NW == 0, "warps must tile the rows of a plane");
   constexpr int ZSTEP = NW >= TY ? NW / TY : 1;          // planes between a warp's rows
   constexpr int YROWS = NW >= TY ? 1 : TY / NW;          // rows per plane per warp
   const Geo& g = w.g;
@@ -478,143 +466,97 @@ __device__ __forceinline__ void compute_tile(const float* __restrict__ s_flow, c
   const int ox = x0 - Cfg::HX, oy = y0 - HALO, oz = gz0 - HALO;
   const int gx = x0 + lane;
   const float fx = (float)gx;
-  // interior tile: the whole box lies inside the resident part of the volume and the whole
-  // tile inside the produced output -> no clipping, no masking, 3 unsigned compares per voxel
-  const bool interior = (oz >= g.src_z0) && (oz + BZ <= g.src_z0 + g.src_n0) && (oy >= 0) && (oy + BY <= H) &&
-                        (ox >= 0) && (ox + BX <= W) && (z0l + TZ <= w.out_n0);
   BoxBounds bb;
   bb.lo_z = max(oz, g.src_z0); bb.hi_z = min(oz + BZ - 1, g.src_z0 + g.src_n0 - 1);
   bb.lo_y = max(oy, 0); bb.hi_y = min(oy + BY - 1, H - 1);
   bb.lo_x = max(ox, 0); bb.hi_x = min(ox + BX - 1, W - 1);
+  const int nz_out = partial ? min(TZ, w.out_n0 - z0l) : TZ;
 #pragma unroll
   for (int yr = 0; yr < YROWS; ++yr) {
     const int yy = (NW >= TY ? wid % TY : wid) + yr * NW;
     const int gy = y0 + yy;
+    if (partial && (gx >= W || gy >= H)) continue;
     const float fy = (float)gy;
     const float* fl = s_flow + ((zs * TY + yy) * TX + lane) * 3;
     float* op = outb + ((size_t)(z0l + zs) * H + gy) * W + gx;
-    if (interior) {
-      // Branch-free main loop: a voxel whose corners are not all inside the staged box still
-      // runs the shared-memory arithmetic on a clamped (valid, meaningless) address and is
-      // recorded in `slow`; it is recomputed through global memory after the loop.  Without a
-      // divergent branch in the body the compiler can overlap the LDS latency of one
-      // iteration with the multiply/add chain of the previous one.
-      unsigned slow = 0;
-      const float* fl0 = fl;
-      float* op0 = op;
+    unsigned slow = 0;
+    const float* fl0 = fl;
+    float* op0 = op;
 #pragma unroll U
-      for (int z = zs, it = 0; z < TZ; z += ZSTEP, ++it, fl += ZSTEP * TY * TX * 3, op += (size_t)ZSTEP * H * W) {
-        const float lz = __fadd_rn((float)(gz0 + z), fl[0]);
-        const float ly = __fadd_rn(fy, fl[1]);
-        const float lx = __fadd_rn(fx, fl[2]);
-        float res;
-        if (METHOD == NRT_LINEAR) {
-          const int iz = __float2int_rd(lz), iy = __float2int_rd(ly), ix = __float2int_rd(lx);
-          const unsigned rz = (unsigned)(iz - oz), ry = (unsigned)(iy - oy), rx = (unsigned)(ix - ox);
-          const unsigned cz = min(rz, (unsigned)(BZ - 2)), cy = min(ry, (unsigned)(BY - 2)), cx = min(rx, (unsigned)(BX - 2));
-          const bool fast = (cz == rz) & (cy == ry) & (cx == rx);
-          // inside an interior box 0 <= loc < max on every axis, so clip() is the identity and
-          // i1 = i0 + 1: same values as axis_linear, without the min/max chain
-          const float wz0 = __fsub_rn(__fadd_rn((float)iz, 1.f), lz), wz1 = __fsub_rn(1.f, wz0);
-          const float wy0 = __fsub_rn(__fadd_rn((float)iy, 1.f), ly), wy1 = __fsub_rn(1.f, wy0);
-          const float wx0 = __fsub_rn(__fadd_rn((float)ix, 1.f), lx), wx1 = __fsub_rn(1.f, wx0);
-          const float* p = s_box + ((int)cz * BY + (int)cy) * BX + (int)cx;
-          float v[8];
-          v[0] = p[0];            v[1] = p[1];
-          v[2] = p[BX];           v[3] = p[BX + 1];
-          v[4] = p[BY * BX];      v[5] = p[BY * BX + 1];
-          v[6] = p[BY * BX + BX]; v[7] = p[BY * BX + BX + 1];
-          res = trilerp(v, wz0, wz1, wy0, wy1, wx0, wx1);
-          slow |= (fast ? 0u : 1u) << it;
-        } else {
-          const int iz = __float2int_rn(lz), iy = __float2int_rn(ly), ix = __float2int_rn(lx);
-          const unsigned rz = (unsigned)(iz - oz), ry = (unsigned)(iy - oy), rx = (unsigned)(ix - ox);
-          const unsigned cz = min(rz, (unsigned)(BZ - 1)), cy = min(ry, (unsigned)(BY - 1)), cx = min(rx, (unsigned)(BX - 1));
-          const bool fast = (cz == rz) & (cy == ry) & (cx == rx);
-          res = s_box[((int)cz * BY + (int)cy) * BX + (int)cx];
-          slow |= (fast ? 0u : 1u) << it;
-        }
-        if (g.has_fill) res = fill_if_oob(g, res, lz, ly, lx);
-        *op = res;
+    for (int z = zs, it = 0; z < TZ; z += ZSTEP, ++it, fl += ZSTEP * TY * TX * 3, op += (size_t)ZSTEP * H * W) {
+      if (partial && z >= nz_out) break;
+      const float lz = __fadd_rn((float)(gz0 + z), fl[0]);
+      const float ly = __fadd_rn(fy, fl[1]);
+      const float lx = __fadd_rn(fx, fl[2]);
+      float res;
+      if (METHOD == NRT_LINEAR) {
+        AxisBox<EZ, BZ> az; AxisBox<EY, BY> ay; AxisBox<EX, BX> ax;
+        az.setup(lz, oz, bb.lo_z, bb.hi_z, g.S[0] - 1);
+        ay.setup(ly, oy, bb.lo_y, bb.hi_y, H - 1);
+        ax.setup(lx, ox, bb.lo_x, bb.hi_x, W - 1);
+        const float* p = s_box + (az.c0 * BY + ay.c0) * BX + ax.c0;
+        const int dz = EZ ? az.d * (BY * BX) : BY * BX;
+        const int dy = EY ? ay.d * BX : BX;
+        const int dx = EX ? ax.d : 1;
+        float v[8];
+        v[0] = p[0];       v[1] = p[dx];
+        v[2] = p[dy];      v[3] = p[dy + dx];
+        v[4] = p[dz];      v[5] = p[dz + dx];
+        v[6] = p[dz + dy]; v[7] = p[dz + dy + dx];
+        res = trilerp(v, az.wlo, az.whi, ay.wlo, ay.whi, ax.wlo, ax.whi);
+        slow |= ((az.ok & ay.ok & ax.ok) ? 0u : 1u) << it;
+      } else {
+        bool ok = true;
+        const int cz = nearest_box<EZ, BZ>(lz, oz, bb.lo_z, bb.hi_z, g.S[0] - 1, ok);
+        const int cy = nearest_box<EY, BY>(ly, oy, bb.lo_y, bb.hi_y, H - 1, ok);
+        const int cx = nearest_box<EX, BX>(lx, ox, bb.lo_x, bb.hi_x, W - 1, ok);
+        res = s_box[(cz * BY + cy) * BX + cx];
+        slow |= (ok ? 0u : 1u) << it;
       }
-      while (slow) {                                   // rare: corners outside the staged box
-        const int it = __ffs(slow) - 1;
-        slow &= slow - 1;
-        const int z = zs + it * ZSTEP;
-        const float* f2 = fl0 + (size_t)it * ZSTEP * TY * TX * 3;
-        const float lz = __fadd_rn((float)(gz0 + z), f2[0]);
-        const float ly = __fadd_rn(fy, f2[1]);
-        const float lx = __fadd_rn(fx, f2[2]);
-        float res = sample_global3<METHOD>(volb, g, lz, ly, lx);
-        if (g.has_fill) res = fill_if_oob(g, res, lz, ly, lx);
-        op0[(size_t)it * ZSTEP * H * W] = res;
-      }
-    } else if (gx < W && gy < H) {
-      // border tile: the box overhangs the volume (or the resident planes); the reference's
-      // clip / min(i0+1, max) semantics are applied before indexing the valid part of the box,
-      // so edge voxels are still served from shared memory.  Same branch-free structure.
-      unsigned slow = 0;
-      const float* fl0 = fl;
-      float* op0 = op;
-      const float mz = (float)(g.S[0] - 1), my = (float)(H - 1), mx = (float)(W - 1);
-      const int nz_out = w.out_n0 - z0l;                  // planes of this tile inside the output
-#pragma unroll U
-      for (int z = zs, it = 0; z < TZ; z += ZSTEP, ++it, fl += ZSTEP * TY * TX * 3, op += (size_t)ZSTEP * H * W) {
-        if (z >= nz_out) break;
-        const float lz = __fadd_rn((float)(gz0 + z), fl[0]);
-        const float ly = __fadd_rn(fy, fl[1]);
-        const float lx = __fadd_rn(fx, fl[2]);
-        float res;
-        if (METHOD == NRT_LINEAR) {
-          const float xz = fminf(fmaxf(lz, 0.f), mz), xy = fminf(fmaxf(ly, 0.f), my), xx = fminf(fmaxf(lx, 0.f), mx);
-          const int iz0 = __float2int_rd(xz), iy0 = __float2int_rd(xy), ix0 = __float2int_rd(xx);
-          const int iz1 = min(iz0 + 1, g.S[0] - 1), iy1 = min(iy0 + 1, H - 1), ix1 = min(ix0 + 1, W - 1);
-          const bool fast = (iz0 >= bb.lo_z) & (iz1 <= bb.hi_z) & (iy0 >= bb.lo_y) & (iy1 <= bb.hi_y) &
-                            (ix0 >= bb.lo_x) & (ix1 <= bb.hi_x);
-          // weights exactly as axis_linear: wlo = f1 - x, whi = 1 - wlo
-          const float wz0 = __fsub_rn((float)iz1, xz), wz1 = __fsub_rn(1.f, wz0);
-          const float wy0 = __fsub_rn((float)iy1, xy), wy1 = __fsub_rn(1.f, wy0);
-          const float wx0 = __fsub_rn((float)ix1, xx), wx1 = __fsub_rn(1.f, wx0);
-          // clamp into the box so that the unconditional loads stay inside shared memory
-          const int cz0 = min(max(iz0 - oz, 0), BZ - 1), cz1 = min(max(iz1 - oz, 0), BZ - 1);
-          const int cy0 = min(max(iy0 - oy, 0), BY - 1), cy1 = min(max(iy1 - oy, 0), BY - 1);
-          const int cx0 = min(max(ix0 - ox, 0), BX - 1), cx1 = min(max(ix1 - ox, 0), BX - 1);
-          const float* r00 = s_box + (cz0 * BY + cy0) * BX;
-          const float* r01 = s_box + (cz0 * BY + cy1) * BX;
-          const float* r10 = s_box + (cz1 * BY + cy0) * BX;
-          const float* r11 = s_box + (cz1 * BY + cy1) * BX;
-          float v[8];
-          v[0] = r00[cx0]; v[1] = r00[cx1];
-          v[2] = r01[cx0]; v[3] = r01[cx1];
-          v[4] = r10[cx0]; v[5] = r10[cx1];
-          v[6] = r11[cx0]; v[7] = r11[cx1];
-          res = trilerp(v, wz0, wz1, wy0, wy1, wx0, wx1);
-          slow |= (fast ? 0u : 1u) << it;
-        } else {
-          const int iz = axis_nearest(lz, g.S[0] - 1), iy = axis_nearest(ly, H - 1), ix = axis_nearest(lx, W - 1);
-          const bool fast = (iz >= bb.lo_z) & (iz <= bb.hi_z) & (iy >= bb.lo_y) & (iy <= bb.hi_y) &
-                            (ix >= bb.lo_x) & (ix <= bb.hi_x);
-          const int cz = min(max(iz - oz, 0), BZ - 1), cy = min(max(iy - oy, 0), BY - 1), cx = min(max(ix - ox, 0), BX - 1);
-          res = s_box[(cz * BY + cy) * BX + cx];
-          slow |= (fast ? 0u : 1u) << it;
-        }
-        if (g.has_fill) res = fill_if_oob(g, res, lz, ly, lx);
-        *op = res;
-      }
-      while (slow) {                                   // corners outside the staged box
-        const int it = __ffs(slow) - 1;
-        slow &= slow - 1;
-        const int z = zs + it * ZSTEP;
-        const float* f2 = fl0 + (size_t)it * ZSTEP * TY * TX * 3;
-        const float lz = __fadd_rn((float)(gz0 + z), f2[0]);
-        const float ly = __fadd_rn(fy, f2[1]);
-        const float lx = __fadd_rn(fx, f2[2]);
-        float res = sample_global3<METHOD>(volb, g, lz, ly, lx);
-        if (g.has_fill) res = fill_if_oob(g, res, lz, ly, lx);
-        op0[(size_t)it * ZSTEP * H * W] = res;
-      }
+      if (g.has_fill) res = fill_if_oob(g, res, lz, ly, lx);
+      *op = res;
+    }
+    while (slow) {                                     // rare: corners outside the staged box
+      const int it = __ffs(slow) - 1;
+      slow &= slow - 1;
+      const int z = zs + it * ZSTEP;
+      const float* f2 = fl0 + (size_t)it * ZSTEP * TY * TX * 3;
+      const float lz = __fadd_rn((float)(gz0 + z), f2[0]);
+      const float ly = __fadd_rn(fy, f2[1]);
+      const float lx = __fadd_rn(fx, f2[2]);
+      float res = sample_global3<METHOD>(volb, g, lz, ly, lx);
+      if (g.has_fill) res = fill_if_oob(g, res, lz, ly, lx);
+      op0[(size_t)it * ZSTEP * H * W] = res;
     }
   }
+}
+
+// Process one staged tile.  Warp w owns row y = w % TY of planes z = w / TY, + NW/TY, ...
+// The per-axis EDGE flags are tile-uniform, so the dispatch below costs one uniform switch.
+template <int TZ, int TY, int HALO, int NW, int METHOD, int U = 2>
+__device__ __forceinline__ void compute_tile(const float* __restrict__ s_flow, const float* __restrict__ s_box,
+                                             const float* __restrict__ volb, float* __restrict__ outb,
+                                             const TileGeo& w, int x0, int y0, int z0l) {
+  using Cfg = TileCfg<TZ, TY, HALO>;
+  static_assert(NW % TY == 0 || TY % NW == 0, "warps must tile the rows of a plane");
+  const Geo& g = w.g;
+  const int ox = x0 - Cfg::HX, oy = y0 - HALO, oz = w.out_z0 + z0l - HALO;
+  const bool ez = !((oz >= g.src_z0) && (oz + Cfg::BZ <= g.src_z0 + g.src_n0));
+  const bool ey = !((oy >= 0) && (oy + Cfg::BY <= g.S[1]));
+  const bool ex = !((ox >= 0) && (ox + Cfg::BX <= g.S[2]));
+  const bool partial = (z0l + TZ > w.out_n0) || (y0 + TY > g.S[1]) || (x0 + Cfg::TX > g.S[2]);
+#define NRT_ROWS(a, b, c) tile_rows<TZ, TY, HALO, NW, METHOD, U, a, b, c>(s_flow, s_box, volb, outb, w, x0, y0, z0l, partial)
+  switch ((ez ? 4 : 0) | (ey ? 2 : 0) | (ex ? 1 : 0)) {
+    case 0: NRT_ROWS(false, false, false); break;
+    case 1: NRT_ROWS(false, false, true); break;
+    case 2: NRT_ROWS(false, true, false); break;
+    case 3: NRT_ROWS(false, true, true); break;
+    case 4: NRT_ROWS(true, false, false); break;
+    case 5: NRT_ROWS(true, false, true); break;
+    case 6: NRT_ROWS(true, true, false); break;
+    default: NRT_ROWS(true, true, true); break;
+  }
+#undef NRT_ROWS
 }
 
 __device__ __forceinline__ void decode_tile(const TileGeo& w, int tile, int TXc, int TYc, int TZc,
@@ -626,9 +568,11 @@ __device__ __forceinline__ void decode_tile(const TileGeo& w, int tile, int TXc,
   x0 = tx * TXc; y0 = ty * TYc; z0l = tz * TZc;
 }
 
-// v1: one tile per CTA, several CTAs per SM overlap each other's load phase
-template <int TZ, int TY, int HALO, int METHOD, int U = 2>
-__global__ void __launch_bounds__(256)
+// v1: one tile per CTA, several CTAs per SM overlap each other's load phase.  3-D grid
+// (x tiles, y tiles, z tiles * batch) keeps the per-CTA prologue free of div/mod chains:
+// with only 8-16 voxels per thread the prologue is a visible part of the instruction count.
+template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8>
+__global__ void __launch_bounds__(NW * 32)
 warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
                    const __grid_constant__ CUtensorMap tm_flow,
                    const float* __restrict__ vol, float* __restrict__ out, TileGeo w) {
@@ -637,8 +581,8 @@ warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
   float* s_flow = reinterpret_cast<float*>(smem_raw);                       // [TZ][TY][TX][3]
   float* s_box = s_flow + Cfg::FLOW_ELEMS;                                  // [BZ][BY][BX]
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_box + Cfg::BOX_ELEMS);
-  int b, x0, y0, z0l;
-  decode_tile(w, blockIdx.x, Cfg::TX, TY, TZ, b, x0, y0, z0l);
+  const int b = blockIdx.z / w.ntz;
+  const int x0 = blockIdx.x * Cfg::TX, y0 = blockIdx.y * TY, z0l = (blockIdx.z - b * w.ntz) * TZ;
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
@@ -648,8 +592,8 @@ warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
   }
   __syncthreads();
   mbar_wait(bar, 0);
-  compute_tile<TZ, TY, HALO, 8, METHOD, U>(s_flow, s_box, vol + (size_t)b * w.src_batch_stride,
-                                        out + (size_t)b * w.out_vox, w, x0, y0, z0l);
+  compute_tile<TZ, TY, HALO, NW, METHOD, U>(s_flow, s_box, vol + (size_t)b * w.src_batch_stride,
+                                            out + (size_t)b * w.out_vox, w, x0, y0, z0l);
 }
 
 // v2: persistent CTAs, NSTAGE-deep TMA ring.  Thread 0 prefetches tile i+NSTAGE-1 while all
@@ -762,13 +706,12 @@ static int env_int(const char* name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
-template <int TZ, int TY, int HALO, int METHOD, int U = 2>
+template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8>
 static int launch_tile(const float* vol, const float* flow, float* out, TileGeo tg, int H, int W, int src_n0,
                        int out_n0, cudaStream_t st) {
   using Cfg = TileCfg<TZ, TY, HALO>;
   tg.ntz = (out_n0 + TZ - 1) / TZ; tg.nty = (H + TY - 1) / TY; tg.ntx = (W + Cfg::TX - 1) / Cfg::TX;
-  const int64_t grid = (int64_t)tg.B * tg.ntz * tg.nty * tg.ntx;
-  if (grid > 0x7fffffffLL || Cfg::SMEM > 227 * 1024) return 1;   // caller falls back to the gather kernel
+  if ((int64_t)tg.B * tg.ntz > 65535 || tg.nty > 65535 || Cfg::SMEM > 227 * 1024) return 1;   // caller falls back
   CUtensorMap tmv, tmf;
   const uint64_t vd[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)src_n0, (uint64_t)tg.B};
   const uint32_t vb[4] = {(uint32_t)Cfg::BX, (uint32_t)Cfg::BY, (uint32_t)Cfg::BZ, 1};
@@ -778,14 +721,15 @@ static int launch_tile(const float* vol, const float* flow, float* out, TileGeo 
   if (rc != NRT_OK) return rc;
   rc = encode_f32_4d(&tmf, flow, fd, fb);
   if (rc != NRT_OK) return rc;
-  auto kern = warp3d_tile_kernel<TZ, TY, HALO, METHOD, U>;
+  auto kern = warp3d_tile_kernel<TZ, TY, HALO, METHOD, U, NW>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(warp3d_tile)");
     configured = true;
   }
-  kern<<<(int)grid, 256, Cfg::SMEM, st>>>(tmv, tmf, vol, out, tg);
+  const dim3 grid(tg.ntx, tg.nty, tg.ntz * tg.B);
+  kern<<<grid, NW * 32, Cfg::SMEM, st>>>(tmv, tmf, vol, out, tg);
   return check_launch("warp3d_tile_kernel");
 }
 
@@ -907,9 +851,6 @@ static int try_tile_path(const float* vol, const float* flow, float* out, int B,
                : launch_persist<tz, ty, 3, nw, ns, cps, NRT_NEAREST>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
     NRT_PERSIST_CASE(1, 8, 16, 32, 2, 1)
     NRT_PERSIST_CASE(2, 8, 8, 16, 2, 2)
-    NRT_PERSIST_CASE(3, 8, 8, 16, 3, 1)
-    NRT_PERSIST_CASE(4, 8, 8, 32, 3, 1)
-    NRT_PERSIST_CASE(5, 4, 8, 16, 3, 2)
 #undef NRT_PERSIST_CASE
     if (rc != 1) { *used = true; return rc; }
   }
@@ -926,8 +867,8 @@ static int try_tile_path(const float* vol, const float* flow, float* out, int B,
   // experimental unroll variants of the default tile (halo 3 only)
   if (hsel == 3 && cfg >= 4) {
     if (cfg == 4) rc = method == NRT_LINEAR ? launch_tile<8, 8, 3, NRT_LINEAR, 4>(vol, flow, out, tg, H, W, src_n0, out_n0, st) : launch_tile<8, 8, 3, NRT_NEAREST, 4>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
-    if (cfg == 5) rc = method == NRT_LINEAR ? launch_tile<8, 8, 3, NRT_LINEAR, 8>(vol, flow, out, tg, H, W, src_n0, out_n0, st) : launch_tile<8, 8, 3, NRT_NEAREST, 8>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
-    if (cfg == 6) rc = method == NRT_LINEAR ? launch_tile<8, 8, 3, NRT_LINEAR, 1>(vol, flow, out, tg, H, W, src_n0, out_n0, st) : launch_tile<8, 8, 3, NRT_NEAREST, 1>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
+    if (cfg == 5) rc = method == NRT_LINEAR ? launch_tile<8, 8, 3, NRT_LINEAR, 2, 4>(vol, flow, out, tg, H, W, src_n0, out_n0, st) : launch_tile<8, 8, 3, NRT_NEAREST, 2, 4>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
+    if (cfg == 6) rc = method == NRT_LINEAR ? launch_tile<8, 8, 3, NRT_LINEAR, 4, 4>(vol, flow, out, tg, H, W, src_n0, out_n0, st) : launch_tile<8, 8, 3, NRT_NEAREST, 4, 4>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
   }
   if (rc == 1) return NRT_OK;                              // not launched: fall back
   *used = true;

@@ -82,7 +82,8 @@ def _rand_case(shape, amp, seed, smooth=False):
 
 @pytest.mark.parametrize('cfg', [0, 1, 2, 3])
 @pytest.mark.parametrize('shape,amp,halo', [((20, 40, 64), 3.0, 3), ((17, 24, 36), 6.0, 4), ((9, 16, 32), 2.0, 5),
-                                            ((33, 18, 100), 3.0, 0), ((40, 48, 96), 9.0, 8)])
+                                            ((33, 18, 100), 3.0, 0), ((40, 48, 96), 9.0, 8), ((16, 16, 36), 5.0, 4),
+                                            ((12, 20, 32), 4.0, 4)])
 @pytest.mark.parametrize('method,fill', [('linear', None), ('linear', -2.5), ('nearest', 0.0)])
 def test_warp_tile_configs_bit_exact(ne, monkeypatch, cfg, shape, amp, halo, method, fill):
     monkeypatch.setenv('NRT_WARP_TILE_CFG', str(cfg))
