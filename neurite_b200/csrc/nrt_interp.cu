@@ -342,7 +342,7 @@ struct TileCfg {
   static constexpr int BZ = TZ + 2 * HALO, BY = TY + 2 * HALO, BX = TX + 2 * HX;
   static constexpr int ROWS = TY / NW;                  // rows of 32 voxels per warp per plane
   static constexpr int FLOW_ELEMS = TZ * TY * TX * 3, BOX_ELEMS = BZ * BY * BX;
-  static constexpr size_t SMEM = (size_t)(FLOW_ELEMS + BOX_ELEMS) * sizeof(float) + 16;
+  static constexpr size_t SMEM = (size_t)(FLOW_ELEMS + BOX_ELEMS) * sizeof(float) + 32;   // + mbarrier + box origin
   static_assert(TY % NW == 0, "TY must be a multiple of the warp count");
   static_assert(BX <= 256 && BY <= 256 && BZ <= 256, "TMA box limit");
 };
@@ -453,7 +453,8 @@ struct BoxBounds { int lo_z, hi_z, lo_y, hi_y, lo_x, hi_x; };
 template <int TZ, int TY, int HALO, int NW, int METHOD, int U, bool EZ, bool EY, bool EX>
 __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, const float* __restrict__ s_box,
                                           const float* __restrict__ volb, float* __restrict__ outb,
-                                          const TileGeo& w, int x0, int y0, int z0l, bool partial) {
+                                          const TileGeo& w, int x0, int y0, int z0l, int ox, int oy, int oz,
+                                          bool partial) {
   using Cfg = TileCfg<TZ, TY, HALO>;
   constexpr int TX = Cfg::TX, BX = Cfg::BX, BY = Cfg::BY, BZ = Cfg::BZ;
   constexpr int ZSTEP = NW >= TY ? NW / TY : 1;          // planes between a warp's rows
@@ -463,7 +464,6 @@ __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, cons
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int zs = NW >= TY ? wid / TY : 0;
   const int gz0 = w.out_z0 + z0l;
-  const int ox = x0 - Cfg::HX, oy = y0 - HALO, oz = gz0 - HALO;
   const int gx = x0 + lane;
   const float fx = (float)gx;
   BoxBounds bb;
@@ -536,16 +536,15 @@ __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, cons
 template <int TZ, int TY, int HALO, int NW, int METHOD, int U = 2>
 __device__ __forceinline__ void compute_tile(const float* __restrict__ s_flow, const float* __restrict__ s_box,
                                              const float* __restrict__ volb, float* __restrict__ outb,
-                                             const TileGeo& w, int x0, int y0, int z0l) {
+                                             const TileGeo& w, int x0, int y0, int z0l, int ox, int oy, int oz) {
   using Cfg = TileCfg<TZ, TY, HALO>;
   static_assert(NW % TY == 0 || TY % NW == 0, "warps must tile the rows of a plane");
   const Geo& g = w.g;
-  const int ox = x0 - Cfg::HX, oy = y0 - HALO, oz = w.out_z0 + z0l - HALO;
   const bool ez = !((oz >= g.src_z0) && (oz + Cfg::BZ <= g.src_z0 + g.src_n0));
   const bool ey = !((oy >= 0) && (oy + Cfg::BY <= g.S[1]));
   const bool ex = !((ox >= 0) && (ox + Cfg::BX <= g.S[2]));
   const bool partial = (z0l + TZ > w.out_n0) || (y0 + TY > g.S[1]) || (x0 + Cfg::TX > g.S[2]);
-#define NRT_ROWS(a, b, c) tile_rows<TZ, TY, HALO, NW, METHOD, U, a, b, c>(s_flow, s_box, volb, outb, w, x0, y0, z0l, partial)
+#define NRT_ROWS(a, b, c) tile_rows<TZ, TY, HALO, NW, METHOD, U, a, b, c>(s_flow, s_box, volb, outb, w, x0, y0, z0l, ox, oy, oz, partial)
   switch ((ez ? 4 : 0) | (ey ? 2 : 0) | (ex ? 1 : 0)) {
     case 0: NRT_ROWS(false, false, false); break;
     case 1: NRT_ROWS(false, false, true); break;
@@ -559,15 +558,6 @@ __device__ __forceinline__ void compute_tile(const float* __restrict__ s_flow, c
 #undef NRT_ROWS
 }
 
-__device__ __forceinline__ void decode_tile(const TileGeo& w, int tile, int TXc, int TYc, int TZc,
-                                            int& b, int& x0, int& y0, int& z0l) {
-  const int tx = tile % w.ntx; tile /= w.ntx;
-  const int ty = tile % w.nty; tile /= w.nty;
-  const int tz = tile % w.ntz;
-  b = tile / w.ntz;
-  x0 = tx * TXc; y0 = ty * TYc; z0l = tz * TZc;
-}
-
 // v1: one tile per CTA, several CTAs per SM overlap each other's load phase.  3-D grid
 // (x tiles, y tiles, z tiles * batch) keeps the per-CTA prologue free of div/mod chains:
 // with only 8-16 voxels per thread the prologue is a visible part of the instruction count.
@@ -575,91 +565,71 @@ template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8>
 __global__ void __launch_bounds__(NW * 32)
 warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
                    const __grid_constant__ CUtensorMap tm_flow,
-                   const float* __restrict__ vol, float* __restrict__ out, TileGeo w) {
+                   const float* __restrict__ vol, const float* __restrict__ flow,
+                   float* __restrict__ out, TileGeo w, int follow) {
   using Cfg = TileCfg<TZ, TY, HALO>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* s_flow = reinterpret_cast<float*>(smem_raw);                       // [TZ][TY][TX][3]
   float* s_box = s_flow + Cfg::FLOW_ELEMS;                                  // [BZ][BY][BX]
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_box + Cfg::BOX_ELEMS);
+  int* s_org = reinterpret_cast<int*>(bar + 1);                             // box origin (global coords)
   const int b = blockIdx.z / w.ntz;
   const int x0 = blockIdx.x * Cfg::TX, y0 = blockIdx.y * TY, z0l = (blockIdx.z - b * w.ntz) * TZ;
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-    mbar_expect_tx(bar, (uint32_t)((Cfg::FLOW_ELEMS + Cfg::BOX_ELEMS) * sizeof(float)));
-    tma_load_4d(s_flow, &tm_flow, bar, x0 * 3, y0, z0l, b);
-    tma_load_4d(s_box, &tm_vol, bar, x0 - Cfg::HX, y0 - HALO, w.out_z0 + z0l - HALO - w.g.src_z0, b);
-  }
-  __syncthreads();
-  mbar_wait(bar, 0);
-  compute_tile<TZ, TY, HALO, NW, METHOD, U>(s_flow, s_box, vol + (size_t)b * w.src_batch_stride,
-                                            out + (size_t)b * w.out_vox, w, x0, y0, z0l);
-}
-
-// v2: persistent CTAs, NSTAGE-deep TMA ring.  Thread 0 prefetches tile i+NSTAGE-1 while all
-// warps gather tile i; full[] barriers carry the TMA transaction bytes, empty[] barriers
-// collect one arrival per warp when a stage has been consumed (no CTA-wide __syncthreads
-// in the steady state).
-template <int TZ, int TY, int HALO, int NW, int NSTAGE, int CPS, int METHOD>
-__global__ void __launch_bounds__(NW * 32, CPS)
-warp3d_persist_kernel(const __grid_constant__ CUtensorMap tm_vol,
-                      const __grid_constant__ CUtensorMap tm_flow,
-                      const float* __restrict__ vol, float* __restrict__ out, TileGeo w, int ntiles) {
-  using Cfg = TileCfg<TZ, TY, HALO>;
-  constexpr int STAGE_ELEMS = Cfg::FLOW_ELEMS + Cfg::BOX_ELEMS;
-  static_assert((Cfg::FLOW_ELEMS * 4) % 128 == 0 && (STAGE_ELEMS * 4) % 128 == 0, "TMA destinations must stay 128-byte aligned");
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* s_base = reinterpret_cast<float*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_base + NSTAGE * STAGE_ELEMS);
-  uint64_t* empty = full + NSTAGE;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NW); }
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  auto issue = [&](int tile, int stage) {
-    int b, x0, y0, z0l;
-    decode_tile(w, tile, Cfg::TX, TY, TZ, b, x0, y0, z0l);
-    float* sf = s_base + stage * STAGE_ELEMS;
-    mbar_expect_tx(full + stage, (uint32_t)(STAGE_ELEMS * sizeof(float)));
-    tma_load_4d(sf, &tm_flow, full + stage, x0 * 3, y0, z0l, b);
-    tma_load_4d(sf + Cfg::FLOW_ELEMS, &tm_vol, full + stage, x0 - Cfg::HX, y0 - HALO,
-                w.out_z0 + z0l - HALO - w.g.src_z0, b);
-  };
-
-  // prologue: fill NSTAGE-1 stages
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE - 1; ++s) {
-      const int t = blockIdx.x + s * gridDim.x;
-      if (t < ntiles) issue(t, s);
-    }
-  }
-  int it = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int stage = it % NSTAGE;
+  if (threadIdx.x < 32) {
     if (threadIdx.x == 0) {
-      // prefetch the tile NSTAGE-1 iterations ahead into the stage consumed last iteration
-      const int pf_it = it + NSTAGE - 1;
-      const int pf_tile = tile + (NSTAGE - 1) * gridDim.x;
-      if (pf_tile < ntiles) {
-        const int ps = pf_it % NSTAGE;
-        const int round = pf_it / NSTAGE;               // how many times stage ps has been filled before
-        if (round >= 1) mbar_wait(empty + ps, (uint32_t)((round - 1) & 1));
-        issue(pf_tile, ps);
+      // speculative load: flow tile + the box centred on the tile itself (right for small or
+      // incoherent displacements), issued before anything is known about the flow
+      mbar_init(bar, 1);
+      fence_mbar_init();
+      mbar_expect_tx(bar, (uint32_t)((Cfg::FLOW_ELEMS + Cfg::BOX_ELEMS) * sizeof(float)));
+      tma_load_4d(s_flow, &tm_flow, bar, x0 * 3, y0, z0l, b);
+      tma_load_4d(s_box, &tm_vol, bar, x0 - Cfg::HX, y0 - HALO, w.out_z0 + z0l - HALO - w.g.src_z0, b);
+    }
+    // Meanwhile warp 0 looks at where the tile lands ON AVERAGE (mean shift over a 3x3x3
+    // lattice of its voxels, one lane each).  A large coherent displacement means the
+    // speculative box is useless; the box is then re-staged around the displaced position,
+    // so that the halo only has to cover the variation of the flow inside the tile.  An
+    // incoherent flow averages out and keeps the speculative box at no extra latency.
+    int sz = 0, sy = 0, sx = 0;
+    if (follow) {
+      float mz = 0.f, my = 0.f, mx = 0.f;
+      const int l = threadIdx.x;
+      if (l < 27) {
+        const int jz = l / 9, jy = (l / 3) % 3, jx = l % 3;
+        const int cz = min(z0l + (jz * (TZ - 1)) / 2, w.out_n0 - 1);
+        const int cy = min(y0 + (jy * (TY - 1)) / 2, w.g.S[1] - 1);
+        const int cx = min(x0 + (jx * (Cfg::TX - 1)) / 2, w.g.S[2] - 1);
+        const float* f = flow + ((((size_t)b * w.out_n0 + cz) * w.g.S[1] + cy) * w.g.S[2] + cx) * 3;
+        const float lim = 1048576.f;
+        mz = fminf(fmaxf(__ldg(f + 0), -lim), lim);
+        my = fminf(fmaxf(__ldg(f + 1), -lim), lim);
+        mx = fminf(fmaxf(__ldg(f + 2), -lim), lim);
+      }
+      mz = warp_sum(mz) * (1.f / 27.f); my = warp_sum(my) * (1.f / 27.f); mx = warp_sum(mx) * (1.f / 27.f);
+      // dead band: 2 voxels in z/y, 4 in x (the TMA needs the x start 16-byte aligned and
+      // the x halo is already rounded up to 4)
+      if (fabsf(mz) >= 2.f || fabsf(my) >= 2.f || fabsf(mx) >= 4.f) {
+        sz = __float2int_rn(mz); sy = __float2int_rn(my); sx = __float2int_rn(mx * 0.25f) * 4;
       }
     }
-    mbar_wait(full + stage, (uint32_t)((it / NSTAGE) & 1));
-    int b, x0, y0, z0l;
-    decode_tile(w, tile, Cfg::TX, TY, TZ, b, x0, y0, z0l);
-    const float* sf = s_base + stage * STAGE_ELEMS;
-    compute_tile<TZ, TY, HALO, NW, METHOD>(sf, sf + Cfg::FLOW_ELEMS, vol + (size_t)b * w.src_batch_stride,
-                                           out + (size_t)b * w.out_vox, w, x0, y0, z0l);
-    __syncwarp();
-    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(empty + stage)) : "memory");
+    if (threadIdx.x == 0) {
+      s_org[0] = w.out_z0 + z0l - HALO + sz; s_org[1] = y0 - HALO + sy; s_org[2] = x0 - Cfg::HX + sx;
+      s_org[3] = (sz | sy | sx) != 0;
+    }
   }
+  __syncthreads();
+  const int oz = s_org[0], oy = s_org[1], ox = s_org[2];
+  const bool restage = s_org[3] != 0;
+  mbar_wait(bar, 0);
+  if (restage) {                                   // block-uniform
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, (uint32_t)(Cfg::BOX_ELEMS * sizeof(float)));
+      tma_load_4d(s_box, &tm_vol, bar, ox, oy, oz - w.g.src_z0, b);
+    }
+    mbar_wait(bar, 1);
+  }
+  compute_tile<TZ, TY, HALO, NW, METHOD, U>(s_flow, s_box, vol + (size_t)b * w.src_batch_stride,
+                                            out + (size_t)b * w.out_vox, w, x0, y0, z0l, ox, oy, oz);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -729,39 +699,8 @@ static int launch_tile(const float* vol, const float* flow, float* out, TileGeo 
     configured = true;
   }
   const dim3 grid(tg.ntx, tg.nty, tg.ntz * tg.B);
-  kern<<<grid, NW * 32, Cfg::SMEM, st>>>(tmv, tmf, vol, out, tg);
+  kern<<<grid, NW * 32, Cfg::SMEM, st>>>(tmv, tmf, vol, flow, out, tg, env_int("NRT_WARP_FOLLOW", 1));
   return check_launch("warp3d_tile_kernel");
-}
-
-template <int TZ, int TY, int HALO, int NW, int NSTAGE, int CPS, int METHOD>
-static int launch_persist(const float* vol, const float* flow, float* out, TileGeo tg, int H, int W, int src_n0,
-                          int out_n0, cudaStream_t st) {
-  constexpr int ctas_per_sm = CPS;
-  using Cfg = TileCfg<TZ, TY, HALO>;
-  constexpr size_t SMEM = (size_t)NSTAGE * (Cfg::FLOW_ELEMS + Cfg::BOX_ELEMS) * sizeof(float) + 2 * NSTAGE * 8 + 16;
-  tg.ntz = (out_n0 + TZ - 1) / TZ; tg.nty = (H + TY - 1) / TY; tg.ntx = (W + Cfg::TX - 1) / Cfg::TX;
-  const int64_t ntiles = (int64_t)tg.B * tg.ntz * tg.nty * tg.ntx;
-  if (ntiles > 0x7fffffffLL || SMEM > 227 * 1024) return 1;
-  CUtensorMap tmv, tmf;
-  const uint64_t vd[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)src_n0, (uint64_t)tg.B};
-  const uint32_t vb[4] = {(uint32_t)Cfg::BX, (uint32_t)Cfg::BY, (uint32_t)Cfg::BZ, 1};
-  const uint64_t fd[4] = {(uint64_t)W * 3, (uint64_t)H, (uint64_t)out_n0, (uint64_t)tg.B};
-  const uint32_t fb[4] = {(uint32_t)Cfg::TX * 3, (uint32_t)TY, (uint32_t)TZ, 1};
-  int rc = encode_f32_4d(&tmv, vol, vd, vb);
-  if (rc != NRT_OK) return rc;
-  rc = encode_f32_4d(&tmf, flow, fd, fb);
-  if (rc != NRT_OK) return rc;
-  auto kern = warp3d_persist_kernel<TZ, TY, HALO, NW, NSTAGE, CPS, METHOD>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM) != cudaSuccess)
-      return check_launch("cudaFuncSetAttribute(warp3d_persist)");
-    configured = true;
-  }
-  int grid = sm_count() * ctas_per_sm;
-  if (ntiles < grid) grid = (int)ntiles;
-  kern<<<grid, NW * 32, SMEM, st>>>(tmv, tmf, vol, out, tg, (int)ntiles);
-  return check_launch("warp3d_persist_kernel");
 }
 
 template <int D, int METHOD>
@@ -827,8 +766,8 @@ static int try_tile_path(const float* vol, const float* flow, float* out, int B,
   if (W % 4 != 0 || !aligned16(vol) || !aligned16(flow) || W < 32) return NRT_OK;
   // tile shapes (TZ x TY x 32) and halos built: the default 8x8x32 runs 4 CTAs per SM (best
   // measured on B200, profiles/); `halo` picks the smallest built halo that covers it.
-  int cfg = env_int("NRT_WARP_TILE_CFG", 2);         // 0: 8x16x32, 1: 16x16x32, 2: 8x8x32, 3: 4x8x32
-  if (cfg < 0 || cfg > 6) cfg = 2;
+  int cfg = env_int("NRT_WARP_TILE_CFG", 2);         // 0: 8x16x32, 2: 8x8x32 (default), 3: 4x8x32
+  if (cfg != 0 && cfg != 2 && cfg != 3) cfg = 2;
   if (halo <= 0) halo = 3;
   const int hsel = halo <= 3 ? 3 : (halo <= 4 ? 4 : (halo <= 6 ? 6 : 8));
   TileGeo tg;
@@ -840,36 +779,15 @@ static int try_tile_path(const float* vol, const float* flow, float* out, int B,
   tg.src_batch_stride = (int64_t)src_n0 * H * W;
   tg.out_vox = (int64_t)out_n0 * H * W;
   int rc = 1;
-  // persistent TMA-ring kernels (v2).  pcfg: 1 = 8x16x32 tile, 32 warps, 2 stages, 1 CTA/SM;
-  // 2 = 8x8x32 tile, 16 warps, 2 stages, 2 CTAs/SM; 3 = 8x8x32, 16 warps, 3 stages, 1 CTA/SM
-  const int pcfg = env_int("NRT_WARP_PERSIST", 0);
-  if (pcfg > 0 && hsel == 3) {
-#define NRT_PERSIST_CASE(i, tz, ty, nw, ns, cps)                                                          \
-    if (pcfg == (i))                                                                                     \
-      rc = method == NRT_LINEAR                                                                          \
-               ? launch_persist<tz, ty, 3, nw, ns, cps, NRT_LINEAR>(vol, flow, out, tg, H, W, src_n0, out_n0, st)   \
-               : launch_persist<tz, ty, 3, nw, ns, cps, NRT_NEAREST>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
-    NRT_PERSIST_CASE(1, 8, 16, 32, 2, 1)
-    NRT_PERSIST_CASE(2, 8, 8, 16, 2, 2)
-#undef NRT_PERSIST_CASE
-    if (rc != 1) { *used = true; return rc; }
-  }
 #define NRT_TILE_CASE(i, tz, ty, hh)                                                                     \
   if (cfg == (i) && hsel == (hh))                                                                        \
     rc = method == NRT_LINEAR                                                                            \
              ? launch_tile<tz, ty, hh, NRT_LINEAR>(vol, flow, out, tg, H, W, src_n0, out_n0, st)         \
              : launch_tile<tz, ty, hh, NRT_NEAREST>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
   NRT_TILE_CASE(0, 8, 16, 3) NRT_TILE_CASE(0, 8, 16, 4) NRT_TILE_CASE(0, 8, 16, 6) NRT_TILE_CASE(0, 8, 16, 8)
-  NRT_TILE_CASE(1, 16, 16, 3) NRT_TILE_CASE(1, 16, 16, 4) NRT_TILE_CASE(1, 16, 16, 6) NRT_TILE_CASE(1, 16, 16, 8)
   NRT_TILE_CASE(2, 8, 8, 3) NRT_TILE_CASE(2, 8, 8, 4) NRT_TILE_CASE(2, 8, 8, 6) NRT_TILE_CASE(2, 8, 8, 8)
   NRT_TILE_CASE(3, 4, 8, 3) NRT_TILE_CASE(3, 4, 8, 4) NRT_TILE_CASE(3, 4, 8, 6) NRT_TILE_CASE(3, 4, 8, 8)
 #undef NRT_TILE_CASE
-  // experimental unroll variants of the default tile (halo 3 only)
-  if (hsel == 3 && cfg >= 4) {
-    if (cfg == 4) rc = method == NRT_LINEAR ? launch_tile<8, 8, 3, NRT_LINEAR, 4>(vol, flow, out, tg, H, W, src_n0, out_n0, st) : launch_tile<8, 8, 3, NRT_NEAREST, 4>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
-    if (cfg == 5) rc = method == NRT_LINEAR ? launch_tile<8, 8, 3, NRT_LINEAR, 2, 4>(vol, flow, out, tg, H, W, src_n0, out_n0, st) : launch_tile<8, 8, 3, NRT_NEAREST, 2, 4>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
-    if (cfg == 6) rc = method == NRT_LINEAR ? launch_tile<8, 8, 3, NRT_LINEAR, 4, 4>(vol, flow, out, tg, H, W, src_n0, out_n0, st) : launch_tile<8, 8, 3, NRT_NEAREST, 4, 4>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
-  }
   if (rc == 1) return NRT_OK;                              // not launched: fall back
   *used = true;
   return rc;

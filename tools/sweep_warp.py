@@ -54,10 +54,9 @@ def main():
         for method in ('linear', 'nearest'):
             for label, env in [('generic', {'NRT_WARP_TILE': '0'})] + \
                               [('tile cfg%d halo%d' % (c, h), {'NRT_WARP_TILE': '1', 'NRT_WARP_TILE_CFG': str(c), 'H': h})
-                               for c in range(7) for h in ((3, 4) if fname != 'smooth8' else (3, 4, 6, 8))] + \
-                              [('persist %d' % pc, {'NRT_WARP_TILE': '1', 'NRT_WARP_PERSIST': str(pc), 'H': 3}) for pc in (1, 2, 3, 4, 5)]:
+                               for c in (0, 2, 3) for h in ((3, 4) if fname != 'smooth8' else (3, 4, 6, 8))]:
                 h = env.pop('H', 0)
-                if quick and not (label.startswith('tile cfg') and label.endswith('halo3') and label[8] in '23456'):
+                if quick and not (label.startswith('tile cfg') and label.endswith('halo3') and label[8] in '023'):
                     continue
                 os.environ['NRT_WARP_PERSIST'] = env.get('NRT_WARP_PERSIST', '0')
                 os.environ.update(env)
