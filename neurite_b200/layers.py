@@ -138,6 +138,15 @@ class SpatialTransformer(_Layer):
         self.ndims = len(input_shape[0]) - 2
         self.built = True
 
+    def call_host(self, inputs, out=None, chunk=1):
+        """[vol, dense shift] as CPU (pinned) tensors -> warped volume on the CPU, with the
+        PCIe copies pipelined against the kernel (utils.warp_host)."""
+        assert len(inputs) == 2, 'inputs has to be len 2, found: %d' % len(inputs)
+        vol, trf = inputs
+        if self.indexing == 'xy':
+            trf = torch.cat([trf[..., 1:2], trf[..., 0:1], trf[..., 2:]], -1)
+        return utils.warp_host(vol, trf, out, self.interp_method, self.fill_value, self.halo, chunk=chunk)
+
     def _affine_to_dense(self, mat, volshape):
         """[B, N, N+1] affine -> dense shift [B, *volshape, N] (vxm.utils.affine_to_dense_shift)."""
         nd = len(volshape)

@@ -249,6 +249,49 @@ class _WarpFn(torch.autograd.Function):
         return gvol, gflow, None, None, None, None
 
 
+_HOST_STREAMS = {}
+
+
+def warp_host(vol, flow, out=None, interp_method='linear', fill_value=None, halo=0, device=None, chunk=1):
+    """Dense warp for HOST tensors: vol [B,*S,C], flow [B,*S,D] on the CPU (pinned memory
+    for full PCIe speed) -> out [B,*S,C] on the CPU (written in place if given).
+
+    The batch is cut into chunks of `chunk` volumes that travel over three CUDA streams in
+    a ring: the host->device copy of chunk i+1 overlaps the kernel and the device->host copy
+    of chunk i (the two PCIe directions are independent), so a batch costs about
+    max(H2D, D2H) instead of H2D + kernel + D2H.  Returns after the result is in `out`."""
+    method = method_id(interp_method)
+    if vol.is_cuda or flow.is_cuda:
+        raise ValueError('warp_host takes CPU tensors; use SpatialTransformer / transform for device tensors')
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    vol = vol.to(torch.float32).contiguous()
+    flow = flow.to(torch.float32).contiguous()
+    B = vol.shape[0]
+    if out is None:
+        out = torch.empty(tuple(flow.shape[:-1]) + (vol.shape[-1],), dtype=torch.float32, pin_memory=True)
+    key = (dev.type, dev.index)
+    if key not in _HOST_STREAMS:
+        _HOST_STREAMS[key] = [torch.cuda.Stream(device=dev) for _ in range(3)]
+    streams = _HOST_STREAMS[key]
+    cur = torch.cuda.current_stream(dev)
+    shape = [int(s) for s in vol.shape[1:-1]]
+    done = []
+    for i, b0 in enumerate(range(0, B, chunk)):
+        st = streams[i % len(streams)]
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            dv = vol[b0:b0 + chunk].to(dev, non_blocking=True)
+            df = flow[b0:b0 + chunk].to(dev, non_blocking=True)
+            o = _warp_raw(dv, df, shape, method, fill_value, (0, shape[0], 0, shape[0]), int(halo), None)
+            out[b0:b0 + chunk].copy_(o, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+            done.append(ev)
+    for ev in done:
+        ev.synchronize()
+    return out
+
+
 def transform(vol, loc_shift, interp_method='linear', indexing='ij', fill_value=None):
     """voxelmorph.utils.transform: interpn(vol, ndgrid + loc_shift).  vol [*S, C], shift [*S, D]."""
     if indexing not in ('ij', 'xy'):

@@ -47,12 +47,28 @@ def num_threads():
     return int(lib().oracle_num_threads())
 
 
-def warp(vol, flow, interp_method='linear', fill_value=None):
-    """vol [B,*S,C], flow [B,*S,D] -> [B,*S,C]"""
+def set_num_threads(n):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is asked to use every host core."""
+    lib().oracle_set_num_threads(ctypes.c_int(int(n)))
+    return num_threads()
+
+
+def use_all_cores():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return set_num_threads(n)
+
+
+def warp(vol, flow, interp_method='linear', fill_value=None, out=None):
+    """vol [B,*S,C], flow [B,*S,D] -> [B,*S,C] (written into `out` if given)"""
     vol = np.ascontiguousarray(vol, dtype=F32)
     flow = np.ascontiguousarray(flow, dtype=F32)
     D = flow.shape[-1]
-    out = np.empty(flow.shape[:-1] + (vol.shape[-1],), dtype=F32)
+    if out is None:
+        out = np.empty(flow.shape[:-1] + (vol.shape[-1],), dtype=F32)
+    assert out.dtype == F32 and out.flags.c_contiguous and out.shape == flow.shape[:-1] + (vol.shape[-1],)
     lib().oracle_warp_f32(_p(vol), _p(flow), _p(out), ctypes.c_int(vol.shape[0]), _ints(vol.shape[1:-1]),
                           ctypes.c_int(D), ctypes.c_int(vol.shape[-1]),
                           ctypes.c_int(0 if interp_method == 'linear' else 1),

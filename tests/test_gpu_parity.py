@@ -340,3 +340,16 @@ def test_lc3d_shared_weights_equal_conv3d_cfg4_shape(ne):
     torch.backends.cudnn.allow_tf32 = False
     ref = torch.nn.functional.conv3d(x.permute(0, 4, 1, 2, 3), w.permute(4, 3, 0, 1, 2)).permute(0, 2, 3, 4, 1)
     np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_warp_host_pipeline_matches_device_path(ne):
+    rng = np.random.default_rng(31)
+    vol = torch.from_numpy(rng.standard_normal((5, 12, 16, 32, 1)).astype(F32)).pin_memory()
+    flow = torch.from_numpy(rng.uniform(-3, 3, (5, 12, 16, 32, 3)).astype(F32)).pin_memory()
+    lay = ne.layers.SpatialTransformer()
+    ref = lay([vol.cuda(), flow.cuda()]).cpu()
+    for chunk in (1, 2, 5):
+        out = lay.call_host([vol, flow], chunk=chunk)
+        assert not out.is_cuda and torch.equal(out, ref)
+    buf = torch.empty_like(ref).pin_memory()
+    assert lay.call_host([vol, flow], out=buf) is buf and torch.equal(buf, ref)
