@@ -249,13 +249,14 @@ resize_kernel(const float* __restrict__ vol, float* __restrict__ out, ResizeGeo 
 // ---------------------------------------------------------------------------------------
 struct AxisEntry { int o0, o1; float wlo, whi; };
 
-template <int METHOD>
+// CT = compile-time channel count (1..4: unrolled, immediate load offsets) or 0 = run-time C
+template <int METHOD, int CT>
 __global__ void __launch_bounds__(256)
 resize3d_kernel(const float* __restrict__ vol, float* __restrict__ out, ResizeGeo w, int ntz, int nty, int ntx) {
   constexpr int TZ = 8, TY = 8, TX = 32;
   __shared__ AxisEntry s_ax[TZ + TY + TX];
   const Geo& g = w.g;
-  const int C = g.C;
+  const int C = CT > 0 ? CT : g.C;
   int tile = blockIdx.x;
   const int tx = tile % ntx; tile /= ntx;
   const int ty = tile % nty; tile /= nty;
@@ -304,6 +305,7 @@ resize3d_kernel(const float* __restrict__ vol, float* __restrict__ out, ResizeGe
       const float* p2 = volb + b01 + ex.o0; const float* p3 = volb + b01 + ex.o1;
       const float* p4 = volb + b10 + ex.o0; const float* p5 = volb + b10 + ex.o1;
       const float* p6 = volb + b11 + ex.o0; const float* p7 = volb + b11 + ex.o1;
+#pragma unroll
       for (int c = 0; c < C; ++c) {
         float r = __fadd_rn(0.f, __fmul_rn(k0, __ldg(p0 + c)));
         r = __fadd_rn(r, __fmul_rn(k1, __ldg(p1 + c)));
@@ -317,6 +319,7 @@ resize3d_kernel(const float* __restrict__ vol, float* __restrict__ out, ResizeGe
       }
     } else {
       const float* p0 = volb + ez.o0 + ey.o0 + ex.o0;
+#pragma unroll
       for (int c = 0; c < C; ++c) outb[c] = __ldg(p0 + c);
     }
   }
@@ -887,8 +890,19 @@ int nrt_resize_f32(const float* vol, float* out, int B, const int32_t* in_shape,
     const int ntz = (out_n0 + 7) / 8, nty = (rg.M[1] + 7) / 8, ntx = (rg.M[2] + 31) / 32;
     const int64_t grid = (int64_t)B * ntz * nty * ntx;
     if (grid <= 0x7fffffffLL) {
-      if (method == NRT_LINEAR) resize3d_kernel<NRT_LINEAR><<<(int)grid, 256, 0, st>>>(vol, out, rg, ntz, nty, ntx);
-      else resize3d_kernel<NRT_NEAREST><<<(int)grid, 256, 0, st>>>(vol, out, rg, ntz, nty, ntx);
+#define NRT_RESIZE3D(CT)                                                                              \
+      do {                                                                                            \
+        if (method == NRT_LINEAR) resize3d_kernel<NRT_LINEAR, CT><<<(int)grid, 256, 0, st>>>(vol, out, rg, ntz, nty, ntx); \
+        else resize3d_kernel<NRT_NEAREST, CT><<<(int)grid, 256, 0, st>>>(vol, out, rg, ntz, nty, ntx);  \
+      } while (0)
+      switch (C) {
+        case 1: NRT_RESIZE3D(1); break;
+        case 2: NRT_RESIZE3D(2); break;
+        case 3: NRT_RESIZE3D(3); break;
+        case 4: NRT_RESIZE3D(4); break;
+        default: NRT_RESIZE3D(0); break;
+      }
+#undef NRT_RESIZE3D
       return check_launch("resize3d_kernel");
     }
   }

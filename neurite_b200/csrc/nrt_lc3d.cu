@@ -67,11 +67,11 @@ __device__ __forceinline__ int64_t patch_origin(const LcGeo& g, int64_t p) {
 // ---------------------------------------------------------------------------------------
 // streaming kernel.  CQ = Cout/4 (power of two <= 32), BB = batch items per pass.
 // ---------------------------------------------------------------------------------------
-constexpr int kLcMaxWarps = 8;              // consumer warps (one position each at a time) + 1 producer warp
+constexpr int kLcMaxWarps = 7;              // consumer groups (<= ring slots - 1) + 1 producer warp
 constexpr int kLcMaxStages = 8;
 
-template <int BB>
-__global__ void __launch_bounds__((kLcMaxWarps + 1) * 32, 1)
+template <int BB, int WPP>
+__global__ void __launch_bounds__((kLcMaxWarps * WPP + 1) * 32, 1)
 lc3d_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
                    const float* __restrict__ bias, float* __restrict__ out, LcGeo g, int b_base,
                    int stages, int cq_log2) {
@@ -84,10 +84,10 @@ lc3d_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel
   int* s_jmap = reinterpret_cast<int*>(empty + stages);                          // [F]
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-  const int kLcWarps = (int)(blockDim.x >> 5) - 1;
+  const int kLcWarps = ((int)(blockDim.x >> 5) - 1) / WPP;     // consumer groups; each group = WPP warps sharing a position
   for (int j = tid; j < g.F; j += (int)blockDim.x) s_jmap[j] = feature_offset(g, j);
   if (tid == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, WPP); }
     fence_mbar_init();
   }
   __syncthreads();
@@ -96,7 +96,7 @@ lc3d_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel
   // CTAs work on neighbouring patches at the same time, so the input stays hot in L2 while
   // the weight stream as a whole advances contiguously.  Step k uses ring slot k % stages
   // and is consumed by warp k % kLcWarps.
-  if (wid == kLcWarps) {
+  if (wid == kLcWarps * WPP) {
     // ===== producer: one thread streams weight blocks into the ring =====
     if (lane == 0) {
       int k = 0;
@@ -123,12 +123,16 @@ lc3d_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel
   // before waiting for the TMA), then run the LDS.128 + FFMA chain with no global latency in it.
   constexpr int CH = (27 * BB <= 54) ? 27 : (48 / BB);
   const int iters = (n4 + 31) >> 5;
-  int k = wid;
-  for (int64_t n = (int64_t)blockIdx.x + (int64_t)wid * gridDim.x; n < g.pn;
+  // WPP warps share a position: warp `sub` of the group contracts batch items
+  // [b_base + sub*BB, b_base + (sub+1)*BB) against the same staged weight block.
+  const int grp = wid / WPP, sub = wid - grp * WPP;
+  const int b0 = b_base + sub * BB;
+  int k = grp;
+  for (int64_t n = (int64_t)blockIdx.x + (int64_t)grp * gridDim.x; n < g.pn;
        n += (int64_t)kLcWarps * gridDim.x, k += kLcWarps) {
     const int slot = k % stages;
     const uint32_t ph = (uint32_t)((k / stages) & 1);
-    const float* xp = x + (int64_t)b_base * g.x_batch + patch_origin(g, g.p0 + n);
+    const float* xp = x + (int64_t)b0 * g.x_batch + patch_origin(g, g.p0 + n);
     float acc[BB][4];
 #pragma unroll
     for (int b = 0; b < BB; ++b) { acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.f; }
@@ -178,7 +182,7 @@ lc3d_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel
         r.y = activate(acc[b][1] + bv.y, g.activation);
         r.z = activate(acc[b][2] + bv.z, g.activation);
         r.w = activate(acc[b][3] + bv.w, g.activation);
-        reinterpret_cast<float4*>(out + ((int64_t)(b_base + b) * g.pn + n) * g.Cout)[fq] = r;
+        reinterpret_cast<float4*>(out + ((int64_t)(b0 + b) * g.pn + n) * g.Cout)[fq] = r;
       }
     }
   }
@@ -262,7 +266,7 @@ lc3d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel, c
   }
 }
 
-template <int BB>
+template <int BB, int WPP>
 static int launch_stream(const float* x, const float* kernel, const float* bias, float* out, const LcGeo& g,
                          int b_base, int cq_log2, cudaStream_t st) {
   const uint32_t blk_bytes = (uint32_t)g.F * g.Cout * sizeof(float);
@@ -272,17 +276,17 @@ static int launch_stream(const float* x, const float* kernel, const float* bias,
   if (stages < 2) return 1;                      // caller falls back to the generic kernel
   if (stages > kLcMaxStages) stages = kLcMaxStages;
   const size_t smem = (size_t)stages * blk_stride + (size_t)stages * 16 + (size_t)g.F * sizeof(int) + 16;
-  auto kern = lc3d_stream_kernel<BB>;
+  auto kern = lc3d_stream_kernel<BB, WPP>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("cudaFuncSetAttribute(lc3d_stream)");
   int grid = sm_count();
   if (g.pn < grid) grid = (int)g.pn;
-  int nw = kLcMaxWarps;                          // as many consumers as the ring allows (measured best)
+  int nw = kLcMaxWarps;                          // as many consumer groups as the ring allows (measured best)
   if (const char* e = getenv("NRT_LC3D_WARPS")) nw = atoi(e);
   if (nw < 1) nw = 1;
   if (nw > kLcMaxWarps) nw = kLcMaxWarps;
   if (nw > stages - 1) nw = stages - 1;
-  kern<<<grid, (nw + 1) * 32, smem, st>>>(x, kernel, bias, out, g, b_base, stages, cq_log2);
+  kern<<<grid, (nw * WPP + 1) * 32, smem, st>>>(x, kernel, bias, out, g, b_base, stages, cq_log2);
   return check_launch("lc3d_stream_kernel");
 }
 
@@ -325,12 +329,12 @@ extern "C" int nrt_lc3d_fwd_f32(const float* x, const float* kernel, const float
     int cq_log2 = 0;
     while ((1 << cq_log2) < cq) ++cq_log2;
     int b = 0, rc = NRT_OK;
-    while (b < B && rc == NRT_OK) {
+    while (b < B && rc == NRT_OK) {              // batch items per pass = BB * WPP (weights streamed once per pass)
       const int left = B - b;
-      if (left >= 8) { rc = launch_stream<8>(x, kernel, bias, out, g, b, cq_log2, st); b += 8; }
-      else if (left >= 4) { rc = launch_stream<4>(x, kernel, bias, out, g, b, cq_log2, st); b += 4; }
-      else if (left >= 2) { rc = launch_stream<2>(x, kernel, bias, out, g, b, cq_log2, st); b += 2; }
-      else { rc = launch_stream<1>(x, kernel, bias, out, g, b, cq_log2, st); b += 1; }
+      if (left >= 8) { rc = launch_stream<4, 2>(x, kernel, bias, out, g, b, cq_log2, st); b += 8; }
+      else if (left >= 4) { rc = launch_stream<2, 2>(x, kernel, bias, out, g, b, cq_log2, st); b += 4; }
+      else if (left >= 2) { rc = launch_stream<2, 1>(x, kernel, bias, out, g, b, cq_log2, st); b += 2; }
+      else { rc = launch_stream<1, 1>(x, kernel, bias, out, g, b, cq_log2, st); b += 1; }
     }
     if (rc <= 0) return rc;       // rc == 1: weight block does not fit the ring -> generic
   }

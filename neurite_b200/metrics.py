@@ -51,9 +51,12 @@ def dice_sums(y_true, y_pred, normalize=False, check_input_limits=True, group=No
         check(lib.nrt_dice_sums_f32(ptr(t), ptr(p), B, V, L, 0, V, int(bool(normalize)), int(bool(check_input_limits)),
                                     ptr(sums), ptr(flag), ptr(ws), ws_bytes, stream_ptr(t.device)))
     if group is not None:
+        # one collective: the [B,L,3] partial sums and the range flag travel together
         import torch.distributed as dist
-        dist.all_reduce(sums, group=group)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        packed = torch.cat([sums.reshape(-1), flag.to(torch.float32)])
+        dist.all_reduce(packed, group=group)
+        sums = packed[:-1].reshape(B, L, 3).contiguous()
+        flag = (packed[-1:] > 0).to(torch.int32)
     return sums, flag
 
 
