@@ -290,6 +290,11 @@ int nrt_warp_bwd_f32(const float* vol, const float* flow, const float* grad_out,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (method == NRT_NEAREST && grad_flow) cudaMemsetAsync(grad_flow, 0, (size_t)B * nvox * D * sizeof(float), st);
   float* gf = method == NRT_NEAREST ? nullptr : grad_flow;
+  if (D == 3 && C == 1 && (grad_vol || gf)) {
+    bool used = false;
+    rc = warp3d_bwd_tile(vol, flow, grad_out, grad_vol, gf, B, shape, method, has_fill, st, &used);
+    if (rc != NRT_OK || used) return rc;
+  }
   if (!grad_vol && !gf) return check_launch("warp_bwd memset");
 #define CALL(DD, MM) warp_bwd_kernel<DD, MM><<<grid_for((int64_t)B * nvox), 256, 0, st>>>(vol, flow, grad_out, grad_vol, gf, g, B, nvox)
   NRT_BWD_DISPATCH(D, method, CALL);

@@ -23,6 +23,10 @@ int sm_count();
 #define NRT_REQUIRE(cond, status, ...) \
   do { if (!(cond)) return ::nrt::set_error((status), __VA_ARGS__); } while (0)
 
+// tiled backward of the D=3, C=1 warp (defined in nrt_interp.cu next to the forward tile kernel)
+int warp3d_bwd_tile(const float* vol, const float* flow, const float* gout, float* gvol, float* gflow, int B,
+                    const int32_t* shape, int method, int has_fill, cudaStream_t st, bool* used);
+
 inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -636,6 +636,169 @@ warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
 }
 
 // ---------------------------------------------------------------------------------------
+// warp3d_bwd_tile_kernel: gradient of the D=3, C=1 warp.  Same staging as the forward
+// (flow tile + source box by TMA, plus the upstream-gradient tile); d/dvol is accumulated
+// into a shared-memory box with shared atomics and flushed once per tile with 128-bit
+// vector reductions (red.global.add.v4.f32), i.e. ~1 global atomic per output voxel
+// instead of 8; d/dflow is written directly.  Voxels whose corners fall outside the
+// staged box go straight to global memory.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// d out / d loc for one sample, given corner values v (order 000..111) and the per-axis weights
+__device__ __forceinline__ void trilerp_grad(const float (&v)[8], float wz0, float wz1, float wy0, float wy1,
+                                             float wx0, float wx1, float& gz, float& gy, float& gx) {
+  // corner bit 0 carries weight w0 = f1 - x (d/dx = -1), bit 1 carries w1 = 1 - w0 (d/dx = +1)
+  gx = wz0 * (wy0 * (v[1] - v[0]) + wy1 * (v[3] - v[2])) + wz1 * (wy0 * (v[5] - v[4]) + wy1 * (v[7] - v[6]));
+  gy = wz0 * (wx0 * (v[2] - v[0]) + wx1 * (v[3] - v[1])) + wz1 * (wx0 * (v[6] - v[4]) + wx1 * (v[7] - v[5]));
+  gz = wy0 * (wx0 * (v[4] - v[0]) + wx1 * (v[5] - v[1])) + wy1 * (wx0 * (v[6] - v[2]) + wx1 * (v[7] - v[3]));
+}
+
+template <int METHOD>
+__device__ __forceinline__ void bwd_global3(const float* __restrict__ volb, float* __restrict__ gvolb, const Geo& g,
+                                            float lz, float ly, float lx, float go, bool want_flow,
+                                            float& gz, float& gy, float& gx) {
+  gz = gy = gx = 0.f;
+  if (METHOD == NRT_LINEAR) {
+    const Axis az = axis_linear(lz, (float)(g.S[0] - 1), g.S[0] - 1);
+    const Axis ay = axis_linear(ly, (float)(g.S[1] - 1), g.S[1] - 1);
+    const Axis ax = axis_linear(lx, (float)(g.S[2] - 1), g.S[2] - 1);
+    const int r00 = (az.i0 * g.S[1] + ay.i0) * g.S[2], r01 = (az.i0 * g.S[1] + ay.i1) * g.S[2];
+    const int r10 = (az.i1 * g.S[1] + ay.i0) * g.S[2], r11 = (az.i1 * g.S[1] + ay.i1) * g.S[2];
+    const int idx[8] = {r00 + ax.i0, r00 + ax.i1, r01 + ax.i0, r01 + ax.i1, r10 + ax.i0, r10 + ax.i1, r11 + ax.i0, r11 + ax.i1};
+    const float w[8] = {az.wlo * ay.wlo * ax.wlo, az.wlo * ay.wlo * ax.whi, az.wlo * ay.whi * ax.wlo, az.wlo * ay.whi * ax.whi,
+                        az.whi * ay.wlo * ax.wlo, az.whi * ay.wlo * ax.whi, az.whi * ay.whi * ax.wlo, az.whi * ay.whi * ax.whi};
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (gvolb) atomicAdd(gvolb + idx[c], w[c] * go);
+      v[c] = want_flow ? __ldg(volb + idx[c]) : 0.f;
+    }
+    if (want_flow) {
+      trilerp_grad(v, az.wlo, az.whi, ay.wlo, ay.whi, ax.wlo, ax.whi, gz, gy, gx);
+      gz = (lz >= 0.f && lz <= (float)(g.S[0] - 1)) ? gz * go : 0.f;
+      gy = (ly >= 0.f && ly <= (float)(g.S[1] - 1)) ? gy * go : 0.f;
+      gx = (lx >= 0.f && lx <= (float)(g.S[2] - 1)) ? gx * go : 0.f;
+    }
+  } else if (gvolb) {
+    const int iz = axis_nearest(lz, g.S[0] - 1), iy = axis_nearest(ly, g.S[1] - 1), ix = axis_nearest(lx, g.S[2] - 1);
+    atomicAdd(gvolb + (iz * g.S[1] + iy) * g.S[2] + ix, go);
+  }
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(256)
+warp3d_bwd_tile_kernel(const __grid_constant__ CUtensorMap tm_vol, const __grid_constant__ CUtensorMap tm_flow,
+                       const __grid_constant__ CUtensorMap tm_gout, const float* __restrict__ vol,
+                       float* __restrict__ gvol, float* __restrict__ gflow, TileGeo w) {
+  constexpr int TZ = 8, TY = 8, HALO = 3, NW = 8;
+  using Cfg = TileCfg<TZ, TY, HALO>;
+  constexpr int TX = Cfg::TX, BX = Cfg::BX, BY = Cfg::BY, BZ = Cfg::BZ;
+  constexpr int GOUT_ELEMS = TZ * TY * TX;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* s_flow = reinterpret_cast<float*>(smem_raw);                       // [TZ][TY][TX][3]
+  float* s_box = s_flow + Cfg::FLOW_ELEMS;                                  // [BZ][BY][BX] source values
+  float* s_gout = s_box + Cfg::BOX_ELEMS;                                   // [TZ][TY][TX]
+  float* s_acc = s_gout + GOUT_ELEMS;                                       // [BZ][BY][BX] d/dvol accumulator
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_acc + Cfg::BOX_ELEMS);
+  const Geo& g = w.g;
+  const int H = g.S[1], W = g.S[2];
+  const int b = blockIdx.z / w.ntz;
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = (blockIdx.z - b * w.ntz) * TZ;
+  const int ox = x0 - Cfg::HX, oy = y0 - HALO, oz = z0 - HALO;
+  const bool want_flow = gflow != nullptr && METHOD == NRT_LINEAR;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(bar, (uint32_t)((Cfg::FLOW_ELEMS + Cfg::BOX_ELEMS + GOUT_ELEMS) * sizeof(float)));
+    tma_load_4d(s_flow, &tm_flow, bar, x0 * 3, y0, z0, b);
+    tma_load_4d(s_box, &tm_vol, bar, ox, oy, oz, b);
+    tma_load_4d(s_gout, &tm_gout, bar, x0, y0, z0, b);
+  }
+  for (int i = threadIdx.x; i < Cfg::BOX_ELEMS; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  mbar_wait(bar, 0);
+
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int gx_ = x0 + lane, gy_ = y0 + wid;
+  const float* volb = vol + (size_t)b * w.src_batch_stride;
+  float* gvolb = gvol ? gvol + (size_t)b * w.src_batch_stride : nullptr;
+  BoxBounds bb;
+  bb.lo_z = max(oz, 0); bb.hi_z = min(oz + BZ - 1, g.S[0] - 1);
+  bb.lo_y = max(oy, 0); bb.hi_y = min(oy + BY - 1, H - 1);
+  bb.lo_x = max(ox, 0); bb.hi_x = min(ox + BX - 1, W - 1);
+  if (gx_ < W && gy_ < H) {
+    for (int z = 0; z < TZ && z0 + z < g.S[0]; ++z) {
+      const int t = (z * TY + wid) * TX + lane;
+      const float go = s_gout[t];
+      const float lz = __fadd_rn((float)(z0 + z), s_flow[t * 3 + 0]);
+      const float ly = __fadd_rn((float)gy_, s_flow[t * 3 + 1]);
+      const float lx = __fadd_rn((float)gx_, s_flow[t * 3 + 2]);
+      float gz = 0.f, gy = 0.f, gx = 0.f;
+      const bool oob = g.has_fill && ((lz < 0.f) | (lz > (float)(g.S[0] - 1)) | (ly < 0.f) | (ly > (float)(H - 1)) |
+                                      (lx < 0.f) | (lx > (float)(W - 1)));
+      if (!oob) {
+        if (METHOD == NRT_LINEAR) {
+          AxisBox<true, BZ> az; AxisBox<true, BY> ay; AxisBox<true, BX> ax;
+          az.setup(lz, oz, bb.lo_z, bb.hi_z, g.S[0] - 1);
+          ay.setup(ly, oy, bb.lo_y, bb.hi_y, H - 1);
+          ax.setup(lx, ox, bb.lo_x, bb.hi_x, W - 1);
+          if (az.ok & ay.ok & ax.ok) {
+            const int base = (az.c0 * BY + ay.c0) * BX + ax.c0;
+            const int dz = az.d * (BY * BX), dy = ay.d * BX, dx = ax.d;
+            const int off[8] = {0, dx, dy, dy + dx, dz, dz + dx, dz + dy, dz + dy + dx};
+            const float w00 = az.wlo * ay.wlo, w01 = az.wlo * ay.whi, w10 = az.whi * ay.wlo, w11 = az.whi * ay.whi;
+            const float wc[8] = {w00 * ax.wlo, w00 * ax.whi, w01 * ax.wlo, w01 * ax.whi,
+                                 w10 * ax.wlo, w10 * ax.whi, w11 * ax.wlo, w11 * ax.whi};
+            float v[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              if (gvolb) atomicAdd(s_acc + base + off[c], wc[c] * go);
+              v[c] = s_box[base + off[c]];
+            }
+            if (want_flow) {
+              trilerp_grad(v, az.wlo, az.whi, ay.wlo, ay.whi, ax.wlo, ax.whi, gz, gy, gx);
+              gz = (lz >= 0.f && lz <= (float)(g.S[0] - 1)) ? gz * go : 0.f;
+              gy = (ly >= 0.f && ly <= (float)(H - 1)) ? gy * go : 0.f;
+              gx = (lx >= 0.f && lx <= (float)(W - 1)) ? gx * go : 0.f;
+            }
+          } else {
+            bwd_global3<METHOD>(volb, gvolb, g, lz, ly, lx, go, want_flow, gz, gy, gx);
+          }
+        } else {
+          const int iz = axis_nearest(lz, g.S[0] - 1), iy = axis_nearest(ly, H - 1), ix = axis_nearest(lx, W - 1);
+          if ((iz >= bb.lo_z) & (iz <= bb.hi_z) & (iy >= bb.lo_y) & (iy <= bb.hi_y) & (ix >= bb.lo_x) & (ix <= bb.hi_x)) {
+            if (gvolb) atomicAdd(s_acc + ((iz - oz) * BY + (iy - oy)) * BX + (ix - ox), go);
+          } else {
+            bwd_global3<METHOD>(volb, gvolb, g, lz, ly, lx, go, false, gz, gy, gx);
+          }
+        }
+      }
+      if (want_flow) {
+        float* gf = gflow + ((((size_t)b * g.S[0] + (z0 + z)) * H + gy_) * W + gx_) * 3;
+        gf[0] = gz; gf[1] = gy; gf[2] = gx;
+      }
+    }
+  }
+  if (!gvolb) return;
+  __syncthreads();
+  // flush the accumulator box: rows of BX floats, 4 at a time (ox and W are multiples of 4,
+  // so every in-volume quad is 16-byte aligned and entirely inside or outside the volume)
+  constexpr int QX = BX / 4;
+  for (int q = threadIdx.x; q < BZ * BY * QX; q += blockDim.x) {
+    const int qx = q % QX, r = q / QX;
+    const int by_ = r % BY, bz_ = r / BY;
+    const int gz_ = oz + bz_, gyy = oy + by_, gxx = ox + qx * 4;
+    if (gz_ < 0 || gz_ >= g.S[0] || gyy < 0 || gyy >= H || gxx < 0 || gxx >= W) continue;
+    const float4 a = *reinterpret_cast<const float4*>(s_acc + (bz_ * BY + by_) * BX + qx * 4);
+    if (a.x == 0.f && a.y == 0.f && a.z == 0.f && a.w == 0.f) continue;
+    red_add_v4(gvolb + ((size_t)gz_ * H + gyy) * W + gxx, a.x, a.y, a.z, a.w);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // host: tensor-map encoding through the runtime's driver entry point (no -lcuda needed)
 // ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -677,6 +840,47 @@ static int encode_f32_4d(CUtensorMap* tm, const void* base, const uint64_t dims[
 static int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return (s && *s) ? atoi(s) : dflt;
+}
+
+int warp3d_bwd_tile(const float* vol, const float* flow, const float* gout, float* gvol, float* gflow, int B,
+                    const int32_t* shape, int method, int has_fill, cudaStream_t st, bool* used) {
+  *used = false;
+  constexpr int TZ = 8, TY = 8, HALO = 3;
+  using Cfg = TileCfg<TZ, TY, HALO>;
+  const int D0 = shape[0], H = shape[1], W = shape[2];
+  if (env_int("NRT_WARP_BWD_TILE", 1) == 0) return NRT_OK;
+  if (W % 4 != 0 || W < 32 || !aligned16(vol) || !aligned16(flow) || !aligned16(gout) || (gvol && !aligned16(gvol)))
+    return NRT_OK;
+  TileGeo tg;
+  tg.g.S[0] = D0; tg.g.S[1] = H; tg.g.S[2] = W;
+  tg.g.src_z0 = 0; tg.g.src_n0 = D0; tg.g.C = 1; tg.g.has_fill = has_fill; tg.g.fill = 0.f; tg.g.err = nullptr;
+  tg.out_z0 = 0; tg.out_n0 = D0; tg.B = B;
+  tg.ntz = (D0 + TZ - 1) / TZ; tg.nty = (H + TY - 1) / TY; tg.ntx = (W + Cfg::TX - 1) / Cfg::TX;
+  tg.src_batch_stride = (int64_t)D0 * H * W; tg.out_vox = tg.src_batch_stride;
+  if ((int64_t)B * tg.ntz > 65535 || tg.nty > 65535) return NRT_OK;
+  constexpr size_t SMEM = (size_t)(Cfg::FLOW_ELEMS + 2 * Cfg::BOX_ELEMS + TZ * TY * Cfg::TX) * sizeof(float) + 16;
+  CUtensorMap tmv, tmf, tmg;
+  const uint64_t vd[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)D0, (uint64_t)B};
+  const uint32_t vb[4] = {(uint32_t)Cfg::BX, (uint32_t)Cfg::BY, (uint32_t)Cfg::BZ, 1};
+  const uint64_t fd[4] = {(uint64_t)W * 3, (uint64_t)H, (uint64_t)D0, (uint64_t)B};
+  const uint32_t fb[4] = {(uint32_t)Cfg::TX * 3, (uint32_t)TY, (uint32_t)TZ, 1};
+  const uint32_t gb[4] = {(uint32_t)Cfg::TX, (uint32_t)TY, (uint32_t)TZ, 1};
+  int rc = encode_f32_4d(&tmv, vol, vd, vb);
+  if (rc == NRT_OK) rc = encode_f32_4d(&tmf, flow, fd, fb);
+  if (rc == NRT_OK) rc = encode_f32_4d(&tmg, gout, vd, gb);
+  if (rc != NRT_OK) return rc;
+  const dim3 grid(tg.ntx, tg.nty, tg.ntz * B);
+  *used = true;
+  if (method == NRT_LINEAR) {
+    static bool cfgd = false;
+    if (!cfgd) { if (cudaFuncSetAttribute(warp3d_bwd_tile_kernel<NRT_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM) != cudaSuccess) return check_launch("cudaFuncSetAttribute(warp3d_bwd_tile)"); cfgd = true; }
+    warp3d_bwd_tile_kernel<NRT_LINEAR><<<grid, 256, SMEM, st>>>(tmv, tmf, tmg, vol, gvol, gflow, tg);
+  } else {
+    static bool cfgd = false;
+    if (!cfgd) { if (cudaFuncSetAttribute(warp3d_bwd_tile_kernel<NRT_NEAREST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM) != cudaSuccess) return check_launch("cudaFuncSetAttribute(warp3d_bwd_tile)"); cfgd = true; }
+    warp3d_bwd_tile_kernel<NRT_NEAREST><<<grid, 256, SMEM, st>>>(tmv, tmf, tmg, vol, gvol, gflow, tg);
+  }
+  return check_launch("warp3d_bwd_tile_kernel");
 }
 
 template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8>

@@ -52,7 +52,8 @@ def interpn_torch(vol, loc, method='linear', fill=None):
     return out
 
 
-@pytest.mark.parametrize('shape,C', [((6, 7, 8), 1), ((5, 6, 9), 3), ((9, 10), 2), ((17,), 1)])
+@pytest.mark.parametrize('shape,C', [((6, 7, 8), 1), ((5, 6, 9), 3), ((9, 10), 2), ((17,), 1), ((10, 12, 36), 1),
+                                     ((19, 9, 64), 1)])
 @pytest.mark.parametrize('method,fill', [('linear', None), ('linear', 0.5), ('nearest', None)])
 def test_warp_and_interpn_gradients(ne, shape, C, method, fill):
     g = torch.Generator().manual_seed(len(shape) * 10 + C)
