@@ -191,6 +191,23 @@ dice_bwd_kernel(const float* __restrict__ t, const float* __restrict__ p, const 
   const int64_t n = V * L;
   const float* tb = t + (int64_t)b * n;
   const float* pb = p + (int64_t)b * n;
+  if ((L & 3) == 0 && (((uintptr_t)t | (uintptr_t)p | (uintptr_t)gt | (uintptr_t)gp) & 15) == 0) {
+    // float4 path: a quad never straddles a voxel because L % 4 == 0
+    const float4* t4 = reinterpret_cast<const float4*>(tb);
+    const float4* p4 = reinterpret_cast<const float4*>(pb);
+    const int L4 = L >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n >> 2); i += (int64_t)gridDim.x * blockDim.x) {
+      const int l = (int)(i % L4) * 4;
+      const float4 tv = ld_stream_f4(t4 + i), pv = ld_stream_f4(p4 + i);
+      const float a0 = s_coef[l], a1 = s_coef[l + 1], a2 = s_coef[l + 2], a3 = s_coef[l + 3];
+      const float c0 = s_coef[L + l], c1 = s_coef[L + l + 1], c2 = s_coef[L + l + 2], c3 = s_coef[L + l + 3];
+      if (gp) st_stream_f4(reinterpret_cast<float4*>(gp + (int64_t)b * n) + i,
+                           make_float4(a0 * tv.x - c0 * pv.x, a1 * tv.y - c1 * pv.y, a2 * tv.z - c2 * pv.z, a3 * tv.w - c3 * pv.w));
+      if (gt) st_stream_f4(reinterpret_cast<float4*>(gt + (int64_t)b * n) + i,
+                           make_float4(a0 * pv.x - c0 * tv.x, a1 * pv.y - c1 * tv.y, a2 * pv.z - c2 * tv.z, a3 * pv.w - c3 * tv.w));
+    }
+    return;
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int l = (int)(i % L);
     const float tv = ld_stream_f(tb + i), pv = ld_stream_f(pb + i);
@@ -244,6 +261,45 @@ cce_bwd_kernel(const float* __restrict__ t, const float* __restrict__ p, const f
         tv = tv * keep + add;
         gp[r * C + c] = up * (tsum * expf(pr[c] - mx) / s - tv);     // softmax * sum t - t
       }
+    }
+  }
+}
+
+// vector path (from_logits = False): C/4 lanes per row, coalesced float4 streams
+__global__ void __launch_bounds__(256)
+cce_bwd_vec4_kernel(const float4* __restrict__ t4, const float4* __restrict__ p4, const float* __restrict__ label_w,
+                    const float* __restrict__ sample_w, int64_t n, int C, int q, float smoothing,
+                    const float* __restrict__ gscale_ptr, float gscale, const float* __restrict__ gper,
+                    float4* __restrict__ gp4) {
+  const float eps = 1e-7f, one_m_eps = __fsub_rn(1.0f, 1e-7f);
+  const float keep = 1.f - smoothing, add = smoothing / (float)C;
+  const float gs = gscale_ptr ? gscale * __ldg(gscale_ptr) : gscale;
+  const int tid = threadIdx.x, sub = tid & (q - 1);
+  const int rows_per_pass = 256 / q;
+  float4 lw = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (label_w) lw = __ldg(reinterpret_cast<const float4*>(label_w) + sub);
+  for (int64_t r0 = (int64_t)blockIdx.x * rows_per_pass; r0 < n; r0 += (int64_t)gridDim.x * rows_per_pass) {
+    const int64_t r = r0 + tid / q;                       // block-uniform trip count (group shuffles below)
+    const bool valid = r < n;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f), p = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (valid) { t = ld_stream_f4(t4 + r * q + sub); p = ld_stream_f4(p4 + r * q + sub); }
+    t.x = t.x * lw.x * keep + add; t.y = t.y * lw.y * keep + add; t.z = t.z * lw.z * keep + add; t.w = t.w * lw.w * keep + add;
+    float s = (p.x + p.y) + (p.z + p.w);
+    for (int o = q >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float rs = 1.f / s;
+    const float q0 = p.x * rs, q1 = p.y * rs, q2 = p.z * rs, q3 = p.w * rs;
+    const bool m0 = q0 >= eps && q0 <= one_m_eps, m1 = q1 >= eps && q1 <= one_m_eps;
+    const bool m2 = q2 >= eps && q2 <= one_m_eps, m3 = q3 >= eps && q3 <= one_m_eps;
+    float ts = ((m0 ? t.x : 0.f) + (m1 ? t.y : 0.f)) + ((m2 ? t.z : 0.f) + (m3 ? t.w : 0.f));
+    for (int o = q >> 1; o > 0; o >>= 1) ts += __shfl_xor_sync(0xffffffffu, ts, o);
+    if (valid) {
+      const float up = -gs * (sample_w ? __ldg(sample_w + r) : 1.f) * (gper ? __ldg(gper + r) : 1.f) * rs;
+      float4 g;
+      g.x = up * ((m0 ? t.x / q0 : 0.f) - ts);
+      g.y = up * ((m1 ? t.y / q1 : 0.f) - ts);
+      g.z = up * ((m2 ? t.z / q2 : 0.f) - ts);
+      g.w = up * ((m3 ? t.w / q3 : 0.f) - ts);
+      gp4[r * q + sub] = g;
     }
   }
 }
@@ -367,6 +423,16 @@ int nrt_cce_bwd_f32(const float* y_true, const float* y_pred, const float* label
   NRT_REQUIRE(y_true && y_pred && grad_pred, NRT_E_ARG, "null pointer");
   NRT_REQUIRE(n >= 0 && C >= 1, NRT_E_ARG, "bad n/C");
   if (n == 0) return NRT_OK;
+  const int q = C / 4;
+  if (!from_logits && C % 4 == 0 && q <= 32 && (q & (q - 1)) == 0 && aligned16(y_true) && aligned16(y_pred) &&
+      aligned16(grad_pred) && (!label_w || aligned16(label_w))) {
+    const int rows_per_pass = 256 / q;
+    const int grid = (int)imin64((n + rows_per_pass - 1) / rows_per_pass, (int64_t)sm_count() * 16);
+    cce_bwd_vec4_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(y_true), reinterpret_cast<const float4*>(y_pred), label_w, sample_w, n, C, q,
+        label_smoothing, grad_scalar, scale, grad_per_elem, reinterpret_cast<float4*>(grad_pred));
+    return check_launch("cce_bwd_vec4_kernel");
+  }
   cce_bwd_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       y_true, y_pred, label_w, sample_w, n, C, from_logits, label_smoothing, grad_scalar, scale, grad_per_elem, grad_pred);
   return check_launch("cce_bwd_kernel");

@@ -353,3 +353,20 @@ def test_warp_host_pipeline_matches_device_path(ne):
         assert not out.is_cuda and torch.equal(out, ref)
     buf = torch.empty_like(ref).pin_memory()
     assert lay.call_host([vol, flow], out=buf) is buf and torch.equal(buf, ref)
+
+
+def test_empty_and_degenerate_inputs(ne):
+    """empty / size-1 inputs behave like the reference's gather (no launch, right shapes)."""
+    vol = torch.randn(4, 5, 6, 2, device='cuda')
+    out = ne.utils.interpn(vol, torch.zeros((0, 3), device='cuda'))
+    assert tuple(out.shape) == (0, 2)
+    st = ne.layers.SpatialTransformer()
+    out = st([torch.zeros((0, 4, 5, 6, 1), device='cuda'), torch.zeros((0, 4, 5, 6, 3), device='cuda')])
+    assert tuple(out.shape) == (0, 4, 5, 6, 1)
+    one = torch.randn(1, 1, 1, 1, 1, device='cuda')                     # a single voxel: every sample clamps to it
+    out = st([one, torch.full((1, 1, 1, 1, 3), 2.5, device='cuda')])
+    assert torch.equal(out, one)
+    tiny = ne.utils.resize(torch.randn(4, 4, 4, 1, device='cuda'), 0.2)  # int(4*0.2) = 0 voxels per axis
+    assert tuple(tiny.shape) == (0, 0, 0, 1)
+    same = torch.randn(2, 3, 4, 5, 1, device='cuda')
+    assert ne.layers.Resize(1)(same) is not None and torch.equal(ne.layers.Resize(1)(same), same)   # utils.py:250-251
