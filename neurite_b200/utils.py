@@ -72,6 +72,8 @@ def _interpn_raw(vol32, loc32, method, fill_value):
     out_shape = tuple(loc32.shape[:-1])
     n_out = int(np.prod(out_shape)) if len(out_shape) else 1
     out = torch.empty(out_shape + (C,), dtype=torch.float32, device=vol32.device)
+    if out.numel() == 0:
+        return out
     with torch.cuda.device(vol32.device):
         check(lib.nrt_interpn_f32(ptr(vol32), i32_array(vol32.shape[:-1]), nb_dims, C, ptr(loc32), n_out, method,
                                   0 if fill_value is None else 1, 0.0 if fill_value is None else float(fill_value),
