@@ -338,13 +338,16 @@ struct TileGeo {
 
 // Compile-time tile / box geometry.  HZ = HY = HALO; the x halo is rounded up to 4 voxels
 // because the TMA needs the innermost start coordinate 16-byte aligned.
-template <int TZ, int TY, int HALO>
+// CC = channels staged per voxel (1..4): the box keeps the volume's channels-last layout, so
+// (x, c) is one contiguous TMA dimension of BX*CC floats.
+template <int TZ, int TY, int HALO, int CC = 1>
 struct TileCfg {
   static constexpr int TX = 32, NW = 8;
   static constexpr int HX = (HALO + 3) & ~3;
   static constexpr int BZ = TZ + 2 * HALO, BY = TY + 2 * HALO, BX = TX + 2 * HX;
   static constexpr int ROWS = TY / NW;                  // rows of 32 voxels per warp per plane
-  static constexpr int FLOW_ELEMS = TZ * TY * TX * 3, BOX_ELEMS = BZ * BY * BX;
+  static constexpr int FLOW_ELEMS = TZ * TY * TX * 3, BOX_ELEMS = BZ * BY * BX * CC;
+  static_assert(BX * CC <= 256, "TMA box limit on the merged (x, channel) dimension");
   static constexpr size_t SMEM = (size_t)(FLOW_ELEMS + BOX_ELEMS) * sizeof(float) + 32;   // + mbarrier + box origin
   static_assert(TY % NW == 0, "TY must be a multiple of the warp count");
   static_assert(BX <= 256 && BY <= 256 && BZ <= 256, "TMA box limit");
@@ -366,10 +369,25 @@ __device__ __forceinline__ float trilerp(const float (&v)[8], float wz0, float w
   return r;
 }
 
+// the same, split: corner weights once per voxel, accumulation once per channel
+__device__ __forceinline__ void corner_weights(float wz0, float wz1, float wy0, float wy1, float wx0, float wx1,
+                                               float (&k)[8]) {
+  const float w00 = __fmul_rn(wz0, wy0), w01 = __fmul_rn(wz0, wy1);
+  const float w10 = __fmul_rn(wz1, wy0), w11 = __fmul_rn(wz1, wy1);
+  k[0] = __fmul_rn(w00, wx0); k[1] = __fmul_rn(w00, wx1); k[2] = __fmul_rn(w01, wx0); k[3] = __fmul_rn(w01, wx1);
+  k[4] = __fmul_rn(w10, wx0); k[5] = __fmul_rn(w10, wx1); k[6] = __fmul_rn(w11, wx0); k[7] = __fmul_rn(w11, wx1);
+}
+__device__ __forceinline__ float acc8(const float (&k)[8], const float (&v)[8]) {
+  float r = __fadd_rn(0.f, __fmul_rn(k[0], v[0]));
+#pragma unroll
+  for (int c = 1; c < 8; ++c) r = __fadd_rn(r, __fmul_rn(k[c], v[c]));
+  return r;
+}
+
 // general (any position, any flow) sample through global memory -- the semantics baseline
-template <int METHOD>
-__device__ __forceinline__ float sample_global3(const float* __restrict__ volb, const Geo& g,
-                                                float lz, float ly, float lx) {
+template <int METHOD, int CC = 1>
+__device__ __forceinline__ void sample_global3(const float* __restrict__ volb, const Geo& g,
+                                               float lz, float ly, float lx, float (&res)[CC]) {
   if (METHOD == NRT_LINEAR) {
     Axis az = axis_linear(lz, (float)(g.S[0] - 1), g.S[0] - 1);
     const Axis ay = axis_linear(ly, (float)(g.S[1] - 1), g.S[1] - 1);
@@ -378,16 +396,21 @@ __device__ __forceinline__ float sample_global3(const float* __restrict__ volb, 
     az.i1 = to_resident(g, az.i1);
     const int r00 = (az.i0 * g.S[1] + ay.i0) * g.S[2], r01 = (az.i0 * g.S[1] + ay.i1) * g.S[2];
     const int r10 = (az.i1 * g.S[1] + ay.i0) * g.S[2], r11 = (az.i1 * g.S[1] + ay.i1) * g.S[2];
-    float v[8];
-    v[0] = __ldg(volb + r00 + ax.i0); v[1] = __ldg(volb + r00 + ax.i1);
-    v[2] = __ldg(volb + r01 + ax.i0); v[3] = __ldg(volb + r01 + ax.i1);
-    v[4] = __ldg(volb + r10 + ax.i0); v[5] = __ldg(volb + r10 + ax.i1);
-    v[6] = __ldg(volb + r11 + ax.i0); v[7] = __ldg(volb + r11 + ax.i1);
-    return trilerp(v, az.wlo, az.whi, ay.wlo, ay.whi, ax.wlo, ax.whi);
+    const int idx[8] = {r00 + ax.i0, r00 + ax.i1, r01 + ax.i0, r01 + ax.i1, r10 + ax.i0, r10 + ax.i1, r11 + ax.i0, r11 + ax.i1};
+    float k[8];
+    corner_weights(az.wlo, az.whi, ay.wlo, ay.whi, ax.wlo, ax.whi, k);
+#pragma unroll
+    for (int c = 0; c < CC; ++c) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = __ldg(volb + (size_t)idx[q] * CC + c);
+      res[c] = acc8(k, v);
+    }
   } else {
     const int iz = to_resident(g, axis_nearest(lz, g.S[0] - 1));
     const int iy = axis_nearest(ly, g.S[1] - 1), ix = axis_nearest(lx, g.S[2] - 1);
-    return __ldg(volb + (iz * g.S[1] + iy) * g.S[2] + ix);
+#pragma unroll
+    for (int c = 0; c < CC; ++c) res[c] = __ldg(volb + (size_t)((iz * g.S[1] + iy) * g.S[2] + ix) * CC + c);
   }
 }
 
@@ -453,12 +476,12 @@ struct BoxBounds { int lo_z, hi_z, lo_y, hi_y, lo_x, hi_x; };
 // clamped (legal, meaningless) address and is recorded in `slow`; it is recomputed through
 // global memory after the loop.  Without a divergent branch in the body the compiler can
 // overlap the LDS latency of one iteration with the multiply/add chain of the previous one.
-template <int TZ, int TY, int HALO, int NW, int METHOD, int U, bool EZ, bool EY, bool EX>
+template <int TZ, int TY, int HALO, int NW, int METHOD, int U, bool EZ, bool EY, bool EX, int CC>
 __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, const float* __restrict__ s_box,
                                           const float* __restrict__ volb, float* __restrict__ outb,
                                           const TileGeo& w, int x0, int y0, int z0l, int ox, int oy, int oz,
                                           bool partial) {
-  using Cfg = TileCfg<TZ, TY, HALO>;
+  using Cfg = TileCfg<TZ, TY, HALO, CC>;
   constexpr int TX = Cfg::TX, BX = Cfg::BX, BY = Cfg::BY, BZ = Cfg::BZ;
   constexpr int ZSTEP = NW >= TY ? NW / TY : 1;          // planes between a warp's rows
   constexpr int YROWS = NW >= TY ? 1 : TY / NW;          // rows per plane per warp
@@ -481,43 +504,60 @@ __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, cons
     if (partial && (gx >= W || gy >= H)) continue;
     const float fy = (float)gy;
     const float* fl = s_flow + ((zs * TY + yy) * TX + lane) * 3;
-    float* op = outb + ((size_t)(z0l + zs) * H + gy) * W + gx;
+    float* op = outb + (((size_t)(z0l + zs) * H + gy) * W + gx) * CC;
     unsigned slow = 0;
     const float* fl0 = fl;
     float* op0 = op;
 #pragma unroll U
-    for (int z = zs, it = 0; z < TZ; z += ZSTEP, ++it, fl += ZSTEP * TY * TX * 3, op += (size_t)ZSTEP * H * W) {
+    for (int z = zs, it = 0; z < TZ; z += ZSTEP, ++it, fl += ZSTEP * TY * TX * 3, op += (size_t)ZSTEP * H * W * CC) {
       if (partial && z >= nz_out) break;
       const float lz = __fadd_rn((float)(gz0 + z), fl[0]);
       const float ly = __fadd_rn(fy, fl[1]);
       const float lx = __fadd_rn(fx, fl[2]);
-      float res;
+      float res[CC];
       if (METHOD == NRT_LINEAR) {
         AxisBox<EZ, BZ> az; AxisBox<EY, BY> ay; AxisBox<EX, BX> ax;
         az.setup(lz, oz, bb.lo_z, bb.hi_z, g.S[0] - 1);
         ay.setup(ly, oy, bb.lo_y, bb.hi_y, H - 1);
         ax.setup(lx, ox, bb.lo_x, bb.hi_x, W - 1);
-        const float* p = s_box + (az.c0 * BY + ay.c0) * BX + ax.c0;
-        const int dz = EZ ? az.d * (BY * BX) : BY * BX;
-        const int dy = EY ? ay.d * BX : BX;
-        const int dx = EX ? ax.d : 1;
-        float v[8];
-        v[0] = p[0];       v[1] = p[dx];
-        v[2] = p[dy];      v[3] = p[dy + dx];
-        v[4] = p[dz];      v[5] = p[dz + dx];
-        v[6] = p[dz + dy]; v[7] = p[dz + dy + dx];
-        res = trilerp(v, az.wlo, az.whi, ay.wlo, ay.whi, ax.wlo, ax.whi);
+        const float* p = s_box + ((az.c0 * BY + ay.c0) * BX + ax.c0) * CC;
+        const int dz = (EZ ? az.d * (BY * BX) : BY * BX) * CC;
+        const int dy = (EY ? ay.d * BX : BX) * CC;
+        const int dx = (EX ? ax.d : 1) * CC;
+        if (CC == 1) {
+          float v[8];
+          v[0] = p[0];       v[1] = p[dx];
+          v[2] = p[dy];      v[3] = p[dy + dx];
+          v[4] = p[dz];      v[5] = p[dz + dx];
+          v[6] = p[dz + dy]; v[7] = p[dz + dy + dx];
+          res[0] = trilerp(v, az.wlo, az.whi, ay.wlo, ay.whi, ax.wlo, ax.whi);
+        } else {
+          float k[8];
+          corner_weights(az.wlo, az.whi, ay.wlo, ay.whi, ax.wlo, ax.whi, k);
+          const int off[8] = {0, dx, dy, dy + dx, dz, dz + dx, dz + dy, dz + dy + dx};
+#pragma unroll
+          for (int c = 0; c < CC; ++c) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = p[off[q] + c];
+            res[c] = acc8(k, v);
+          }
+        }
         slow |= ((az.ok & ay.ok & ax.ok) ? 0u : 1u) << it;
       } else {
         bool ok = true;
         const int cz = nearest_box<EZ, BZ>(lz, oz, bb.lo_z, bb.hi_z, g.S[0] - 1, ok);
         const int cy = nearest_box<EY, BY>(ly, oy, bb.lo_y, bb.hi_y, H - 1, ok);
         const int cx = nearest_box<EX, BX>(lx, ox, bb.lo_x, bb.hi_x, W - 1, ok);
-        res = s_box[(cz * BY + cy) * BX + cx];
+#pragma unroll
+        for (int c = 0; c < CC; ++c) res[c] = s_box[((cz * BY + cy) * BX + cx) * CC + c];
         slow |= (ok ? 0u : 1u) << it;
       }
-      if (g.has_fill) res = fill_if_oob(g, res, lz, ly, lx);
-      *op = res;
+#pragma unroll
+      for (int c = 0; c < CC; ++c) {
+        if (g.has_fill) res[c] = fill_if_oob(g, res[c], lz, ly, lx);
+        op[c] = res[c];
+      }
     }
     while (slow) {                                     // rare: corners outside the staged box
       const int it = __ffs(slow) - 1;
@@ -527,27 +567,31 @@ __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, cons
       const float lz = __fadd_rn((float)(gz0 + z), f2[0]);
       const float ly = __fadd_rn(fy, f2[1]);
       const float lx = __fadd_rn(fx, f2[2]);
-      float res = sample_global3<METHOD>(volb, g, lz, ly, lx);
-      if (g.has_fill) res = fill_if_oob(g, res, lz, ly, lx);
-      op0[(size_t)it * ZSTEP * H * W] = res;
+      float res[CC];
+      sample_global3<METHOD, CC>(volb, g, lz, ly, lx, res);
+#pragma unroll
+      for (int c = 0; c < CC; ++c) {
+        if (g.has_fill) res[c] = fill_if_oob(g, res[c], lz, ly, lx);
+        op0[(size_t)it * ZSTEP * H * W * CC + c] = res[c];
+      }
     }
   }
 }
 
 // Process one staged tile.  Warp w owns row y = w % TY of planes z = w / TY, + NW/TY, ...
 // The per-axis EDGE flags are tile-uniform, so the dispatch below costs one uniform switch.
-template <int TZ, int TY, int HALO, int NW, int METHOD, int U = 2>
+template <int TZ, int TY, int HALO, int NW, int METHOD, int U = 2, int CC = 1>
 __device__ __forceinline__ void compute_tile(const float* __restrict__ s_flow, const float* __restrict__ s_box,
                                              const float* __restrict__ volb, float* __restrict__ outb,
                                              const TileGeo& w, int x0, int y0, int z0l, int ox, int oy, int oz) {
-  using Cfg = TileCfg<TZ, TY, HALO>;
+  using Cfg = TileCfg<TZ, TY, HALO, CC>;
   static_assert(NW % TY == 0 || TY % NW == 0, "warps must tile the rows of a plane");
   const Geo& g = w.g;
   const bool ez = !((oz >= g.src_z0) && (oz + Cfg::BZ <= g.src_z0 + g.src_n0));
   const bool ey = !((oy >= 0) && (oy + Cfg::BY <= g.S[1]));
   const bool ex = !((ox >= 0) && (ox + Cfg::BX <= g.S[2]));
   const bool partial = (z0l + TZ > w.out_n0) || (y0 + TY > g.S[1]) || (x0 + Cfg::TX > g.S[2]);
-#define NRT_ROWS(a, b, c) tile_rows<TZ, TY, HALO, NW, METHOD, U, a, b, c>(s_flow, s_box, volb, outb, w, x0, y0, z0l, ox, oy, oz, partial)
+#define NRT_ROWS(a, b, c) tile_rows<TZ, TY, HALO, NW, METHOD, U, a, b, c, CC>(s_flow, s_box, volb, outb, w, x0, y0, z0l, ox, oy, oz, partial)
   switch ((ez ? 4 : 0) | (ey ? 2 : 0) | (ex ? 1 : 0)) {
     case 0: NRT_ROWS(false, false, false); break;
     case 1: NRT_ROWS(false, false, true); break;
@@ -564,13 +608,13 @@ __device__ __forceinline__ void compute_tile(const float* __restrict__ s_flow, c
 // v1: one tile per CTA, several CTAs per SM overlap each other's load phase.  3-D grid
 // (x tiles, y tiles, z tiles * batch) keeps the per-CTA prologue free of div/mod chains:
 // with only 8-16 voxels per thread the prologue is a visible part of the instruction count.
-template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8>
+template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8, int CC = 1>
 __global__ void __launch_bounds__(NW * 32)
 warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
                    const __grid_constant__ CUtensorMap tm_flow,
                    const float* __restrict__ vol, const float* __restrict__ flow,
                    float* __restrict__ out, TileGeo w, int follow) {
-  using Cfg = TileCfg<TZ, TY, HALO>;
+  using Cfg = TileCfg<TZ, TY, HALO, CC>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* s_flow = reinterpret_cast<float*>(smem_raw);                       // [TZ][TY][TX][3]
   float* s_box = s_flow + Cfg::FLOW_ELEMS;                                  // [BZ][BY][BX]
@@ -586,7 +630,7 @@ warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
       fence_mbar_init();
       mbar_expect_tx(bar, (uint32_t)((Cfg::FLOW_ELEMS + Cfg::BOX_ELEMS) * sizeof(float)));
       tma_load_4d(s_flow, &tm_flow, bar, x0 * 3, y0, z0l, b);
-      tma_load_4d(s_box, &tm_vol, bar, x0 - Cfg::HX, y0 - HALO, w.out_z0 + z0l - HALO - w.g.src_z0, b);
+      tma_load_4d(s_box, &tm_vol, bar, (x0 - Cfg::HX) * CC, y0 - HALO, w.out_z0 + z0l - HALO - w.g.src_z0, b);
     }
     // Meanwhile warp 0 looks at where the tile lands ON AVERAGE (mean shift over a 3x3x3
     // lattice of its voxels, one lane each).  A large coherent displacement means the
@@ -627,12 +671,12 @@ warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
   if (restage) {                                   // block-uniform
     if (threadIdx.x == 0) {
       mbar_expect_tx(bar, (uint32_t)(Cfg::BOX_ELEMS * sizeof(float)));
-      tma_load_4d(s_box, &tm_vol, bar, ox, oy, oz - w.g.src_z0, b);
+      tma_load_4d(s_box, &tm_vol, bar, ox * CC, oy, oz - w.g.src_z0, b);
     }
     mbar_wait(bar, 1);
   }
-  compute_tile<TZ, TY, HALO, NW, METHOD, U>(s_flow, s_box, vol + (size_t)b * w.src_batch_stride,
-                                            out + (size_t)b * w.out_vox, w, x0, y0, z0l, ox, oy, oz);
+  compute_tile<TZ, TY, HALO, NW, METHOD, U, CC>(s_flow, s_box, vol + (size_t)b * w.src_batch_stride,
+                                                out + (size_t)b * w.out_vox * CC, w, x0, y0, z0l, ox, oy, oz);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -883,22 +927,24 @@ int warp3d_bwd_tile(const float* vol, const float* flow, const float* gout, floa
   return check_launch("warp3d_bwd_tile_kernel");
 }
 
-template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8>
+template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8, int CC = 1>
 static int launch_tile(const float* vol, const float* flow, float* out, TileGeo tg, int H, int W, int src_n0,
                        int out_n0, cudaStream_t st) {
-  using Cfg = TileCfg<TZ, TY, HALO>;
+  using Cfg = TileCfg<TZ, TY, HALO, CC>;
   tg.ntz = (out_n0 + TZ - 1) / TZ; tg.nty = (H + TY - 1) / TY; tg.ntx = (W + Cfg::TX - 1) / Cfg::TX;
   if ((int64_t)tg.B * tg.ntz > 65535 || tg.nty > 65535 || Cfg::SMEM > 227 * 1024) return 1;   // caller falls back
+  tg.g.C = CC;
+  tg.src_batch_stride = (int64_t)src_n0 * H * W * CC;
   CUtensorMap tmv, tmf;
-  const uint64_t vd[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)src_n0, (uint64_t)tg.B};
-  const uint32_t vb[4] = {(uint32_t)Cfg::BX, (uint32_t)Cfg::BY, (uint32_t)Cfg::BZ, 1};
+  const uint64_t vd[4] = {(uint64_t)W * CC, (uint64_t)H, (uint64_t)src_n0, (uint64_t)tg.B};
+  const uint32_t vb[4] = {(uint32_t)(Cfg::BX * CC), (uint32_t)Cfg::BY, (uint32_t)Cfg::BZ, 1};
   const uint64_t fd[4] = {(uint64_t)W * 3, (uint64_t)H, (uint64_t)out_n0, (uint64_t)tg.B};
   const uint32_t fb[4] = {(uint32_t)Cfg::TX * 3, (uint32_t)TY, (uint32_t)TZ, 1};
   int rc = encode_f32_4d(&tmv, vol, vd, vb);
   if (rc != NRT_OK) return rc;
   rc = encode_f32_4d(&tmf, flow, fd, fb);
   if (rc != NRT_OK) return rc;
-  auto kern = warp3d_tile_kernel<TZ, TY, HALO, METHOD, U, NW>;
+  auto kern = warp3d_tile_kernel<TZ, TY, HALO, METHOD, U, NW, CC>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM) != cudaSuccess)
@@ -964,7 +1010,7 @@ static int check_common(int D, int C, int method) {
   return NRT_OK;
 }
 
-static int try_tile_path(const float* vol, const float* flow, float* out, int B, const int32_t* shape,
+static int try_tile_path(const float* vol, const float* flow, float* out, int B, const int32_t* shape, int C,
                          int method, int has_fill, float fill, int src_z0, int src_n0, int out_z0,
                          int out_n0, int halo, int32_t* err_flag, cudaStream_t st, bool* used) {
   *used = false;
@@ -986,6 +1032,20 @@ static int try_tile_path(const float* vol, const float* flow, float* out, int B,
   tg.src_batch_stride = (int64_t)src_n0 * H * W;
   tg.out_vox = (int64_t)out_n0 * H * W;
   int rc = 1;
+  if (C > 1) {
+    // 2-4 channels: (x, channel) is one contiguous TMA dimension; 4x8x32 tiles keep the
+    // staged box (22 KB per channel) small enough for two CTAs per SM
+#define NRT_TILE_C(cc)                                                                                   \
+    if (C == (cc))                                                                                       \
+      rc = method == NRT_LINEAR                                                                          \
+               ? launch_tile<4, 8, 3, NRT_LINEAR, 2, 8, cc>(vol, flow, out, tg, H, W, src_n0, out_n0, st)  \
+               : launch_tile<4, 8, 3, NRT_NEAREST, 2, 8, cc>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
+    NRT_TILE_C(2) NRT_TILE_C(3) NRT_TILE_C(4)
+#undef NRT_TILE_C
+    if (rc == 1) return NRT_OK;
+    *used = true;
+    return rc;
+  }
 #define NRT_TILE_CASE(i, tz, ty, hh)                                                                     \
   if (cfg == (i) && hsel == (hh))                                                                        \
     rc = method == NRT_LINEAR                                                                            \
@@ -1049,9 +1109,9 @@ int nrt_warp_f32(const float* vol, const float* flow, float* out, int B, const i
               "slab too large for int32 indexing");
   if (B == 0 || out_n0 == 0) return NRT_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (D == 3 && C == 1) {
+  if (D == 3 && C <= 4) {
     bool used = false;
-    rc = try_tile_path(vol, flow, out, B, shape, method, has_fill, fill, src_z0, src_n0, out_z0, out_n0,
+    rc = try_tile_path(vol, flow, out, B, shape, C, method, has_fill, fill, src_z0, src_n0, out_z0, out_n0,
                        halo, err_flag, st, &used);
     if (rc != NRT_OK || used) return rc;
   }

@@ -4,6 +4,7 @@ neurite_b200.layers -- drop-ins for the hot-path layers of neurite.layers
 
     Resize / Zoom           layers.py:91-185
     SpatialTransformer      voxelmorph.layers.SpatialTransformer (call sites models.py:806, 1157)
+    VecInt, ComposeTransform, RescaleTransform   voxelmorph layers composed from the warp / resize
     LocallyConnected3D      layers.py:811-1197  (implementation 1)
 
 Constructor arguments, defaults, `get_config()` keys, `compute_output_shape`, weight names
@@ -181,6 +182,85 @@ class SpatialTransformer(_Layer):
                 outs.append(utils.interpn(vol[b], loc, self.interp_method, self.fill_value))
             return torch.stack(outs, 0)
         return utils._warp_batched(vol, trf, self.interp_method, self.fill_value, halo=self.halo)
+
+
+# ---------------------------------------------------------------------------------------
+# voxelmorph-adjacent transforms that feed the warp.  Thin compositions
+# of the kernels above; call sites in the reference: neurite/tf/models.py:802-804, 1149.
+# ---------------------------------------------------------------------------------------
+class VecInt(_Layer):
+    """vxm.layers.VecInt: integrate a stationary velocity field by scaling and squaring
+    (method 'ss'): v /= 2^int_steps; repeat int_steps times: v += warp(v, v)."""
+
+    def __init__(self, indexing='ij', method='ss', int_steps=7, out_time_pt=1, **kwargs):
+        assert indexing in ['ij', 'xy'], "indexing has to be 'ij' (matrix) or 'xy' (cartesian)"
+        if method != 'ss':
+            raise NotImplementedError("VecInt: only method='ss' (scaling and squaring) is built")
+        self.indexing, self.method, self.int_steps, self.out_time_pt = indexing, method, int_steps, out_time_pt
+        super().__init__(**kwargs)
+
+    def get_config(self):
+        config = super().get_config().copy()
+        config.update({'indexing': self.indexing, 'method': self.method, 'int_steps': self.int_steps,
+                       'out_time_pt': self.out_time_pt})
+        return config
+
+    def call(self, inputs):
+        v = inputs[0] if isinstance(inputs, (list, tuple)) else inputs
+        if self.indexing == 'xy':
+            v = torch.cat([v[..., 1:2], v[..., 0:1], v[..., 2:]], -1)
+        v = v * self.out_time_pt if self.out_time_pt != 1 else v
+        v = v / (2 ** self.int_steps)
+        for _ in range(self.int_steps):
+            v = v + utils._warp_batched(v, v, 'linear', None)
+        return v
+
+
+class ComposeTransform(_Layer):
+    """vxm.layers.ComposeTransform for dense shifts: T = t_0 o t_1 o ... (the right-most
+    transform is applied first): curr = t_last; curr = curr + warp(t_next, curr)."""
+
+    def __init__(self, interp_method='linear', shift_center=True, indexing='ij', **kwargs):
+        self.interp_method, self.shift_center, self.indexing = interp_method, shift_center, indexing
+        super().__init__(**kwargs)
+
+    def get_config(self):
+        config = super().get_config().copy()
+        config.update({'interp_method': self.interp_method, 'shift_center': self.shift_center,
+                       'indexing': self.indexing})
+        return config
+
+    def call(self, transforms):
+        if not isinstance(transforms, (list, tuple)) or len(transforms) < 2:
+            raise ValueError('ComposeTransform must be called on a list of at least two transforms')
+        for t in transforms:
+            if t.dim() == 3:
+                raise NotImplementedError('ComposeTransform: affine inputs are not built; expand them with '
+                                          'SpatialTransformer._affine_to_dense first')
+        curr = transforms[-1]
+        for nxt in reversed(transforms[:-1]):
+            curr = curr + utils._warp_batched(nxt, curr, self.interp_method, None)
+        return curr
+
+
+class RescaleTransform(_Layer):
+    """vxm.layers.RescaleTransform for dense shifts: resize the field by zoom_factor and scale
+    its values by the same factor (values first when up-sampling, resize first when down-sampling)."""
+
+    def __init__(self, zoom_factor, interp_method='linear', **kwargs):
+        self.zoom_factor, self.interp_method = zoom_factor, interp_method
+        super().__init__(**kwargs)
+
+    def get_config(self):
+        config = super().get_config().copy()
+        config.update({'zoom_factor': self.zoom_factor, 'interp_method': self.interp_method})
+        return config
+
+    def call(self, trf):
+        ndims = trf.dim() - 2
+        if self.zoom_factor < 1:
+            return utils._resize_batched(trf, [self.zoom_factor] * ndims, self.interp_method) * self.zoom_factor
+        return utils._resize_batched(trf * self.zoom_factor, [self.zoom_factor] * ndims, self.interp_method)
 
 
 # ---------------------------------------------------------------------------------------

@@ -234,3 +234,35 @@ def spatial_transformer(vol, trf, interp_method='linear', indexing='ij', fill_va
         trf = np.concatenate([trf[..., 1:2], trf[..., 0:1], trf[..., 2:]], -1)
     return np.stack([transform(vol[b], trf[b], interp_method, 'ij', fill_value)
                      for b in range(vol.shape[0])], 0)
+
+
+# ---------------------------------------------------------------------------------------
+# voxelmorph-adjacent compositions of the warp (third party, UNPINNED)
+# call sites in the reference: VecInt neurite/tf/models.py:802, 1149; RescaleTransform /
+# Resize of the half-resolution field :803-804
+# ---------------------------------------------------------------------------------------
+def vec_int(vel, int_steps=7, indexing='ij'):
+    """vxm.layers.VecInt(method='ss'): scaling and squaring.  vel [B,*S,D] -> displacement."""
+    out = []
+    for b in range(vel.shape[0]):
+        v = (np.asarray(vel[b], dtype=F32) / F32(2 ** int_steps)).astype(F32)
+        for _ in range(int_steps):
+            v = (v + transform(v, v, 'linear', indexing)).astype(F32)
+        out.append(v)
+    return np.stack(out, 0)
+
+
+def compose(transforms, interp_method='linear', indexing='ij'):
+    """vxm.utils.compose for dense shifts [*S,D]: T = t_0 o t_1 o ... (right-most applied first)."""
+    curr = np.asarray(transforms[-1], dtype=F32)
+    for nxt in reversed(transforms[:-1]):
+        curr = (curr + transform(np.asarray(nxt, dtype=F32), curr, interp_method, indexing)).astype(F32)
+    return curr
+
+
+def rescale_transform(trf, zoom_factor, interp_method='linear'):
+    """vxm.layers.RescaleTransform on dense shifts [B,*S,D]: resize the field and scale its values."""
+    z = F32(zoom_factor)
+    if zoom_factor < 1:
+        return (resize_layer(trf, zoom_factor, interp_method) * z).astype(F32)
+    return resize_layer((np.asarray(trf, dtype=F32) * z).astype(F32), zoom_factor, interp_method)

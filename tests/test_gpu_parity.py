@@ -114,12 +114,15 @@ def test_warp_box_follows_smooth_flow(ne, monkeypatch):
 
 def test_warp_batch_and_channels(ne):
     rng = np.random.default_rng(5)
-    for C in (1, 2, 4, 16):
-        vol = rng.standard_normal((3, 12, 16, 32, C)).astype(F32)
-        flow = rng.uniform(-3, 3, (3, 12, 16, 32, 3)).astype(F32)
-        ref = ointerp.spatial_transformer(vol, flow)
-        out = ne.layers.SpatialTransformer()([dev(vol), dev(flow)]).cpu().numpy()
-        np.testing.assert_array_equal(out, ref)
+    for C in (1, 2, 3, 4, 16):
+        for S, amp in (((12, 16, 32), 3.0), ((9, 13, 68), 5.0)):
+            vol = rng.standard_normal((3,) + S + (C,)).astype(F32)
+            flow = rng.uniform(-amp, amp, (3,) + S + (3,)).astype(F32)
+            flow[1] += np.array([6.2, -5.1, 9.7], dtype=F32)              # coherent shift: box re-staging
+            for method, fill in (('linear', None), ('linear', 1.5), ('nearest', 0.0)):
+                ref = ointerp.spatial_transformer(vol, flow, method, 'ij', fill)
+                out = ne.layers.SpatialTransformer(interp_method=method, fill_value=fill)([dev(vol), dev(flow)]).cpu().numpy()
+                np.testing.assert_array_equal(out, ref)
     # xy indexing swaps the first two shift channels
     vol = rng.standard_normal((1, 8, 9, 12, 1)).astype(F32)
     flow = rng.uniform(-2, 2, (1, 8, 9, 12, 3)).astype(F32)
@@ -370,3 +373,21 @@ def test_empty_and_degenerate_inputs(ne):
     assert tuple(tiny.shape) == (0, 0, 0, 1)
     same = torch.randn(2, 3, 4, 5, 1, device='cuda')
     assert ne.layers.Resize(1)(same) is not None and torch.equal(ne.layers.Resize(1)(same), same)   # utils.py:250-251
+
+
+def test_vxm_adjacent_transforms_vs_oracle(ne):
+    """VecInt / ComposeTransform / RescaleTransform == the same
+    compositions of the oracle's warp and resize, bit for bit."""
+    rng = np.random.default_rng(41)
+    vel = rng.uniform(-4, 4, (2, 12, 16, 32, 3)).astype(F32)
+    out = ne.layers.VecInt(int_steps=5)(dev(vel)).cpu().numpy()
+    np.testing.assert_array_equal(out, ointerp.vec_int(vel, 5))
+    a = rng.uniform(-3, 3, (1, 10, 12, 32, 3)).astype(F32)
+    b = rng.uniform(-3, 3, (1, 10, 12, 32, 3)).astype(F32)
+    c = rng.uniform(-3, 3, (1, 10, 12, 32, 3)).astype(F32)
+    out = ne.layers.ComposeTransform()([dev(a), dev(b), dev(c)]).cpu().numpy()
+    np.testing.assert_array_equal(out[0], ointerp.compose([a[0], b[0], c[0]]))
+    half = rng.uniform(-2, 2, (2, 6, 8, 10, 3)).astype(F32)
+    for z in (2, 0.5):
+        out = ne.layers.RescaleTransform(z)(dev(half)).cpu().numpy()
+        np.testing.assert_array_equal(out, ointerp.rescale_transform(half, z))

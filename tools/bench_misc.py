@@ -34,7 +34,7 @@ def report(name, ms, nbytes):
 
 dev = torch.device('cuda')
 g = torch.Generator(device=dev).manual_seed(0)
-for C, B in ((1, 8), (4, 4), (16, 2)):
+for C, B in ((1, 8), (2, 4), (3, 4), (4, 4), (16, 2)):
     vol = torch.randn((B,) + S + (C,), device=dev, generator=g)
     flow = torch.rand((B,) + S + (3,), device=dev, generator=g) * 6 - 3
     st = ne.layers.SpatialTransformer()
