@@ -669,6 +669,9 @@ warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
   const bool restage = s_org[3] != 0;
   mbar_wait(bar, 0);
   if (restage) {                                   // block-uniform
+    // every thread must have observed phase 0 before phase 1 is armed: an mbarrier waiter
+    // can be at most one phase behind (parity aliasing), found with compute-sanitizer
+    __syncthreads();
     if (threadIdx.x == 0) {
       mbar_expect_tx(bar, (uint32_t)(Cfg::BOX_ELEMS * sizeof(float)));
       tma_load_4d(s_box, &tm_vol, bar, ox * CC, oy, oz - w.g.src_z0, b);
