@@ -155,10 +155,22 @@ def test_warp_slabs_equal_whole(ne):
     from neurite_b200 import dist as nd, utils
     rng = np.random.default_rng(7)
     S = (24, 20, 32)
+    for C, world_list in ((1, (2, 3, 8)), (2, (3,)), (16, (2,))):
+        _check_slabs(nd, utils, rng, S, C, world_list)
     vol = dev(rng.standard_normal((2,) + S + (1,)).astype(F32))
     flow = dev(rng.uniform(-3, 3, (2,) + S + (3,)).astype(F32))
+    # a window that is too small is reported, not silently wrong
+    err = torch.zeros(1, dtype=torch.int32, device='cuda')
+    utils._warp_batched(vol[:, 8:12].contiguous(), flow[:, 8:12].contiguous() * 4, src_z0=8, full_s0=S[0], out_z0=8,
+                        err_flag=err)
+    assert int(err.item()) == 1
+
+
+def _check_slabs(nd, utils, rng, S, C, world_list):
+    vol = dev(rng.standard_normal((2,) + S + (C,)).astype(F32))
+    flow = dev(rng.uniform(-3, 3, (2,) + S + (3,)).astype(F32))
     whole = utils._warp_batched(vol, flow)
-    for world in (2, 3, 8):
+    for world in world_list:
         parts = []
         for r in range(world):
             z0, nz = nd.slab_bounds(S[0], world, r)
@@ -169,11 +181,6 @@ def test_warp_slabs_equal_whole(ne):
                                              src_z0=lo, full_s0=S[0], out_z0=z0, err_flag=err))
             assert int(err.item()) == 0
         assert torch.equal(torch.cat(parts, 1), whole)
-    # a window that is too small is reported, not silently wrong
-    err = torch.zeros(1, dtype=torch.int32, device='cuda')
-    utils._warp_batched(vol[:, 8:12].contiguous(), flow[:, 8:12].contiguous() * 4, src_z0=8, full_s0=S[0], out_z0=8,
-                        err_flag=err)
-    assert int(err.item()) == 1
 
 
 def test_resize_full_size_and_slabs(ne):
