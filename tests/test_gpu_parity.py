@@ -398,3 +398,16 @@ def test_vxm_adjacent_transforms_vs_oracle(ne):
     for z in (2, 0.5):
         out = ne.layers.RescaleTransform(z)(dev(half)).cpu().numpy()
         np.testing.assert_array_equal(out, ointerp.rescale_transform(half, z))
+
+
+@pytest.mark.parametrize('shape,C,zoom', [((7, 9, 33), 1, 2), ((6, 5, 40), 2, 3), ((5, 6, 35), 3, 2.5), ((4, 7, 34), 4, 4),
+                                          ((9, 8, 32), 3, [1.5, 2, 3.7]), ((3, 2, 2), 1, 2), ((10, 12, 70), 3, 1.6)])
+def test_resize_upsampling_vs_oracle(ne, monkeypatch, shape, C, zoom):
+    """up-sampling shapes through the separable-table kernel and the generic kernel"""
+    rng = np.random.default_rng(51)
+    x = rng.standard_normal((2,) + shape + (C,)).astype(F32)
+    ref = ointerp.resize_layer(x, zoom)
+    out = ne.layers.Resize(zoom)(dev(x))
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    monkeypatch.setenv('NRT_RESIZE_GENERIC', '1')
+    np.testing.assert_array_equal(ne.layers.Resize(zoom)(dev(x)).cpu().numpy(), ref)
