@@ -919,12 +919,13 @@ int warp3d_bwd_tile(const float* vol, const float* flow, const float* gout, floa
   const dim3 grid(tg.ntx, tg.nty, tg.ntz * B);
   *used = true;
   if (method == NRT_LINEAR) {
-    static bool cfgd = false;
-    if (!cfgd) { if (cudaFuncSetAttribute(warp3d_bwd_tile_kernel<NRT_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM) != cudaSuccess) return check_launch("cudaFuncSetAttribute(warp3d_bwd_tile)"); cfgd = true; }
+    // (set on every launch: the attribute is per device, and the call costs ~1 us)
+    if (cudaFuncSetAttribute(warp3d_bwd_tile_kernel<NRT_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM) != cudaSuccess)
+      return check_launch("cudaFuncSetAttribute(warp3d_bwd_tile)");
     warp3d_bwd_tile_kernel<NRT_LINEAR><<<grid, 256, SMEM, st>>>(tmv, tmf, tmg, vol, gvol, gflow, tg);
   } else {
-    static bool cfgd = false;
-    if (!cfgd) { if (cudaFuncSetAttribute(warp3d_bwd_tile_kernel<NRT_NEAREST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM) != cudaSuccess) return check_launch("cudaFuncSetAttribute(warp3d_bwd_tile)"); cfgd = true; }
+    if (cudaFuncSetAttribute(warp3d_bwd_tile_kernel<NRT_NEAREST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM) != cudaSuccess)
+      return check_launch("cudaFuncSetAttribute(warp3d_bwd_tile)");
     warp3d_bwd_tile_kernel<NRT_NEAREST><<<grid, 256, SMEM, st>>>(tmv, tmf, tmg, vol, gvol, gflow, tg);
   }
   return check_launch("warp3d_bwd_tile_kernel");
@@ -948,12 +949,9 @@ static int launch_tile(const float* vol, const float* flow, float* out, TileGeo 
   rc = encode_f32_4d(&tmf, flow, fd, fb);
   if (rc != NRT_OK) return rc;
   auto kern = warp3d_tile_kernel<TZ, TY, HALO, METHOD, U, NW, CC>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM) != cudaSuccess)
-      return check_launch("cudaFuncSetAttribute(warp3d_tile)");
-    configured = true;
-  }
+  // set on every launch: the attribute is per device and the call costs ~1 us of host time
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM) != cudaSuccess)
+    return check_launch("cudaFuncSetAttribute(warp3d_tile)");
   const dim3 grid(tg.ntx, tg.nty, tg.ntz * tg.B);
   kern<<<grid, NW * 32, Cfg::SMEM, st>>>(tmv, tmf, vol, flow, out, tg, env_int("NRT_WARP_FOLLOW", 1));
   return check_launch("warp3d_tile_kernel");
