@@ -63,6 +63,14 @@ NRT_API int nrt_interpn_f32(const float* vol, const int32_t* vol_shape, int D, i
                     const float* loc, int64_t n_out, int method, int has_fill, float fill,
                     float* out, void* stream);
 
+/* interpn whose sample grid has the volume's own spatial shape (D = 3): loc [S0,S1,S2,3]
+ * -> out [S0,S1,S2,C].  Same results as nrt_interpn_f32; samples that stay within `halo`
+ * voxels (plus a coherent shift) of their own grid position are served from the TMA-staged
+ * shared-memory tiles of the warp kernel.  This is the shape voxelmorph's transform() hands
+ * to neurite.utils.interpn (utils.py:73-220). */
+NRT_API int nrt_interpn_grid_f32(const float* vol, const float* loc, float* out, const int32_t* shape,
+                         int C, int method, int has_fill, float fill, int halo, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * warp -- replaces voxelmorph.layers.SpatialTransformer on a dense shift (call sites
  * neurite/tf/models.py:806-807, 1157-1159): out[b] = interpn(vol[b], ndgrid + flow[b]).

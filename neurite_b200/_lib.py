@@ -23,6 +23,8 @@ SIGNATURES = {
     'nrt_status_string': (ctypes.c_char_p, [ctypes.c_int]),
     'nrt_interpn_f32': (ctypes.c_int, [c_vp, P_I32, ctypes.c_int, ctypes.c_int, c_vp, c_i64, ctypes.c_int,
                                         ctypes.c_int, c_f32, c_vp, c_vp]),
+    'nrt_interpn_grid_f32': (ctypes.c_int, [c_vp, c_vp, c_vp, P_I32, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f32,
+                                             ctypes.c_int, c_vp]),
     'nrt_warp_f32': (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, P_I32, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_int, ctypes.c_int, c_f32, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),

@@ -334,6 +334,7 @@ struct TileGeo {
   int B;
   int ntz, nty, ntx;     // tiles per axis
   int64_t src_batch_stride, out_vox;
+  int abs_loc;           // 1: the 'flow' tensor holds absolute sample locations (interpn on the volume's own grid)
 };
 
 // Compile-time tile / box geometry.  HZ = HY = HALO; the x halo is rounded up to 4 voxels
@@ -491,7 +492,8 @@ __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, cons
   const int zs = NW >= TY ? wid / TY : 0;
   const int gz0 = w.out_z0 + z0l;
   const int gx = x0 + lane;
-  const float fx = (float)gx;
+  // with absolute locations the grid term is 0 (0 + x == x exactly): same instruction count
+  const float fx = w.abs_loc ? 0.f : (float)gx;
   BoxBounds bb;
   bb.lo_z = max(oz, g.src_z0); bb.hi_z = min(oz + BZ - 1, g.src_z0 + g.src_n0 - 1);
   bb.lo_y = max(oy, 0); bb.hi_y = min(oy + BY - 1, H - 1);
@@ -502,16 +504,18 @@ __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, cons
     const int yy = (NW >= TY ? wid % TY : wid) + yr * NW;
     const int gy = y0 + yy;
     if (partial && (gx >= W || gy >= H)) continue;
-    const float fy = (float)gy;
+    const float fy = w.abs_loc ? 0.f : (float)gy;
+    float zf = w.abs_loc ? 0.f : (float)(gz0 + zs);                 // running z coordinate (exact small integers)
+    const float zstep = w.abs_loc ? 0.f : (float)ZSTEP;
     const float* fl = s_flow + ((zs * TY + yy) * TX + lane) * 3;
     float* op = outb + (((size_t)(z0l + zs) * H + gy) * W + gx) * CC;
     unsigned slow = 0;
     const float* fl0 = fl;
     float* op0 = op;
 #pragma unroll U
-    for (int z = zs, it = 0; z < TZ; z += ZSTEP, ++it, fl += ZSTEP * TY * TX * 3, op += (size_t)ZSTEP * H * W * CC) {
+    for (int z = zs, it = 0; z < TZ; z += ZSTEP, ++it, fl += ZSTEP * TY * TX * 3, op += (size_t)ZSTEP * H * W * CC, zf += zstep) {
       if (partial && z >= nz_out) break;
-      const float lz = __fadd_rn((float)(gz0 + z), fl[0]);
+      const float lz = __fadd_rn(zf, fl[0]);
       const float ly = __fadd_rn(fy, fl[1]);
       const float lx = __fadd_rn(fx, fl[2]);
       float res[CC];
@@ -564,7 +568,7 @@ __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, cons
       slow &= slow - 1;
       const int z = zs + it * ZSTEP;
       const float* f2 = fl0 + (size_t)it * ZSTEP * TY * TX * 3;
-      const float lz = __fadd_rn((float)(gz0 + z), f2[0]);
+      const float lz = __fadd_rn(w.abs_loc ? 0.f : (float)(gz0 + z), f2[0]);
       const float ly = __fadd_rn(fy, f2[1]);
       const float lx = __fadd_rn(fx, f2[2]);
       float res[CC];
@@ -648,9 +652,10 @@ warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
         const int cx = min(x0 + (jx * (Cfg::TX - 1)) / 2, w.g.S[2] - 1);
         const float* f = flow + ((((size_t)b * w.out_n0 + cz) * w.g.S[1] + cy) * w.g.S[2] + cx) * 3;
         const float lim = 1048576.f;
-        mz = fminf(fmaxf(__ldg(f + 0), -lim), lim);
-        my = fminf(fmaxf(__ldg(f + 1), -lim), lim);
-        mx = fminf(fmaxf(__ldg(f + 2), -lim), lim);
+        const float gz_ = w.abs_loc ? (float)(w.out_z0 + cz) : 0.f, gy_ = w.abs_loc ? (float)cy : 0.f, gx_ = w.abs_loc ? (float)cx : 0.f;
+        mz = fminf(fmaxf(__ldg(f + 0) - gz_, -lim), lim);
+        my = fminf(fmaxf(__ldg(f + 1) - gy_, -lim), lim);
+        mx = fminf(fmaxf(__ldg(f + 2) - gx_, -lim), lim);
       }
       mz = warp_sum(mz) * (1.f / 27.f); my = warp_sum(my) * (1.f / 27.f); mx = warp_sum(mx) * (1.f / 27.f);
       // dead band: 2 voxels in z/y, 4 in x (the TMA needs the x start 16-byte aligned and
@@ -901,7 +906,7 @@ int warp3d_bwd_tile(const float* vol, const float* flow, const float* gout, floa
   TileGeo tg;
   tg.g.S[0] = D0; tg.g.S[1] = H; tg.g.S[2] = W;
   tg.g.src_z0 = 0; tg.g.src_n0 = D0; tg.g.C = 1; tg.g.has_fill = has_fill; tg.g.fill = 0.f; tg.g.err = nullptr;
-  tg.out_z0 = 0; tg.out_n0 = D0; tg.B = B;
+  tg.out_z0 = 0; tg.out_n0 = D0; tg.B = B; tg.abs_loc = 0;
   tg.ntz = (D0 + TZ - 1) / TZ; tg.nty = (H + TY - 1) / TY; tg.ntx = (W + Cfg::TX - 1) / Cfg::TX;
   tg.src_batch_stride = (int64_t)D0 * H * W; tg.out_vox = tg.src_batch_stride;
   if ((int64_t)B * tg.ntz > 65535 || tg.nty > 65535) return NRT_OK;
@@ -1013,7 +1018,7 @@ static int check_common(int D, int C, int method) {
 
 static int try_tile_path(const float* vol, const float* flow, float* out, int B, const int32_t* shape, int C,
                          int method, int has_fill, float fill, int src_z0, int src_n0, int out_z0,
-                         int out_n0, int halo, int32_t* err_flag, cudaStream_t st, bool* used) {
+                         int out_n0, int halo, int32_t* err_flag, cudaStream_t st, bool* used, int abs_loc = 0) {
   *used = false;
   const int H = shape[1], W = shape[2];
   if (env_int("NRT_WARP_TILE", 1) == 0) return NRT_OK;
@@ -1030,6 +1035,7 @@ static int try_tile_path(const float* vol, const float* flow, float* out, int B,
   tg.g.has_fill = has_fill; tg.g.fill = fill; tg.g.err = err_flag;
   tg.out_z0 = out_z0; tg.out_n0 = out_n0; tg.B = B;
   tg.ntz = tg.nty = tg.ntx = 0;
+  tg.abs_loc = abs_loc;
   tg.src_batch_stride = (int64_t)src_n0 * H * W;
   tg.out_vox = (int64_t)out_n0 * H * W;
   int rc = 1;
@@ -1086,6 +1092,27 @@ int nrt_interpn_f32(const float* vol, const int32_t* vol_shape, int D, int C, co
 #define CALL(DD, MM) launch_interpn<DD, MM>(vol, g, loc, n_out, out, st)
   NRT_DISPATCH_D_METHOD(D, method, CALL);
 #undef CALL
+}
+
+int nrt_interpn_grid_f32(const float* vol, const float* loc, float* out, const int32_t* shape, int C, int method,
+                         int has_fill, float fill, int halo, void* stream) {
+  int rc = check_common(3, C, method);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(vol && loc && out && shape, NRT_E_ARG, "null pointer");
+  int64_t nvox = 1;
+  for (int d = 0; d < 3; ++d) {
+    NRT_REQUIRE(shape[d] >= 1, NRT_E_ARG, "shape[%d] = %d", d, shape[d]);
+    nvox *= shape[d];
+  }
+  NRT_REQUIRE(nvox <= 0x7fffffffLL, NRT_E_SIZE, "volume has %lld voxels (> int32)", (long long)nvox);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (C <= 4) {
+    bool used = false;
+    rc = try_tile_path(vol, loc, out, 1, shape, C, method, has_fill, fill, 0, shape[0], 0, shape[0], halo, nullptr,
+                       st, &used, /*abs_loc=*/1);
+    if (rc != NRT_OK || used) return rc;
+  }
+  return nrt_interpn_f32(vol, shape, 3, C, loc, nvox, method, has_fill, fill, out, stream);
 }
 
 int nrt_warp_f32(const float* vol, const float* flow, float* out, int B, const int32_t* shape, int D,

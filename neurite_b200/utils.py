@@ -74,6 +74,14 @@ def _interpn_raw(vol32, loc32, method, fill_value):
     out = torch.empty(out_shape + (C,), dtype=torch.float32, device=vol32.device)
     if out.numel() == 0:
         return out
+    if nb_dims == 3 and out_shape == tuple(vol32.shape[:-1]):
+        # the sample grid has the volume's own shape (what transform() passes): tiled fast path
+        with torch.cuda.device(vol32.device):
+            check(lib.nrt_interpn_grid_f32(ptr(vol32), ptr(loc32), ptr(out), i32_array(vol32.shape[:-1]), C, method,
+                                           0 if fill_value is None else 1,
+                                           0.0 if fill_value is None else float(fill_value), 0,
+                                           stream_ptr(vol32.device)))
+        return out
     with torch.cuda.device(vol32.device):
         check(lib.nrt_interpn_f32(ptr(vol32), i32_array(vol32.shape[:-1]), nb_dims, C, ptr(loc32), n_out, method,
                                   0 if fill_value is None else 1, 0.0 if fill_value is None else float(fill_value),

@@ -411,3 +411,23 @@ def test_resize_upsampling_vs_oracle(ne, monkeypatch, shape, C, zoom):
     np.testing.assert_array_equal(out.cpu().numpy(), ref)
     monkeypatch.setenv('NRT_RESIZE_GENERIC', '1')
     np.testing.assert_array_equal(ne.layers.Resize(zoom)(dev(x)).cpu().numpy(), ref)
+
+
+def test_interpn_on_the_volume_grid_uses_tiles_and_stays_exact(ne, monkeypatch):
+    """interpn(vol, grid + shift) -- the call voxelmorph's transform() makes -- goes through
+    the TMA tile kernel with absolute locations; bit-exact vs the oracle and vs the gather kernel,
+    also for locations that have nothing to do with the grid."""
+    rng = np.random.default_rng(61)
+    S = (20, 24, 64)
+    grid = np.stack(np.meshgrid(*[np.arange(s, dtype=F32) for s in S], indexing='ij'), -1)
+    for C in (1, 3):
+        vol = rng.standard_normal(S + (C,)).astype(F32)
+        for loc in ((grid + rng.uniform(-3, 3, grid.shape)).astype(F32),
+                    (grid + np.array([7.5, -6.25, 10.0], F32) + rng.uniform(-1, 1, grid.shape)).astype(F32),
+                    rng.uniform(-5, 70, grid.shape).astype(F32)):
+            for method, fill in (('linear', None), ('nearest', 0.0)):
+                ref = ointerp.interpn(vol, loc, method, fill)
+                out = ne.utils.interpn(dev(vol), dev(loc), method, fill).cpu().numpy()
+                np.testing.assert_array_equal(out, ref)
+    monkeypatch.setenv('NRT_WARP_TILE', '0')
+    np.testing.assert_array_equal(ne.utils.interpn(dev(vol), dev(loc)).cpu().numpy(), ointerp.interpn(vol, loc))
