@@ -400,6 +400,81 @@ def bench_resize(args):
     finish(world)
 
 
+def bench_mi(args, segs=False):
+    """MutualInformation: `mi` = volumes() on B pairs of 160x192x224 volumes (soft quantisation
+    fused, 8 B/voxel); `mi_segs` = segs() on two [2,160,192,224,16] probability maps (128 B/voxel)."""
+    import torch
+    import neurite_b200 as ne
+    world, rank, local = dist_setup(args.gpus)
+    dev = torch.device('cuda', local)
+    m = ne.metrics.MutualInformation(nb_bins=16)
+    if segs:
+        B = 2
+        x = torch.softmax(torch.randn((B,) + SHAPE + (16,), device=dev), -1)
+        y = torch.softmax(torch.randn((B,) + SHAPE + (16,), device=dev), -1)
+        fn, per_voxel, kern = (lambda: m.segs(x, y)), 128.0, 'mi_hist_mma_kernel<1,2,maps,maps>'
+    else:
+        B = args.batch
+        x = torch.rand((B,) + SHAPE + (1,), device=dev)
+        y = (0.7 * x * x + 0.1 + 0.1 * torch.rand_like(x)).clamp_(0, 1)
+        fn, per_voxel, kern = (lambda: m.volumes(x, y)), 8.0, 'mi_hist_mma_kernel<1,2,quant,quant>'
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed_region(fn, args.steps, args.warmup, world)
+    clocks = sampler.stop()
+    peak, peak_src = measured_peak()
+    achieved = per_voxel * B * V * args.steps / (ms * 1e-3) / 1e9
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'voxels/s, MutualInformation.%s (16 bins), 160x192x224 fp32' % ('segs' if segs else 'volumes'),
+            'value': world * B * V * args.steps / (ms * 1e-3), 'unit': 'voxels/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32 (3xTF32 tensor-core contraction)', 'data': 'synthetic',
+            'config': {'workload': 'MutualInformation(nb_bins=16).%s on %d x 160x192x224 (reference metrics.py:41-336); '
+                                   'min/max + histogram + combine + finalise kernels per step'
+                                   % ('segs, 16 labels' if segs else 'volumes', B)},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': None, 'peak_source': peak_src,
+                         'bytes_model': '%d B/voxel (two fp32 %s read once; the quantised [V,16] maps never exist)'
+                                        % (per_voxel, 'maps' if segs else 'volumes'),
+                         'kernel': kern, 'per': 'GPU',
+                         'note': '' if segs else 'volumes(): bound by issue slots / MUFU (32 exp per voxel pair), not HBM'},
+            'gpu_launches': args.steps * (4 if segs else 10), 'clocks': clocks}), flush=True)
+    finish(world)
+
+
+def bench_blur(args):
+    """GaussianBlur(sigma=1) (7 taps per axis) of B single-channel 160x192x224 volumes."""
+    import torch
+    import neurite_b200 as ne
+    world, rank, local = dist_setup(args.gpus)
+    dev = torch.device('cuda', local)
+    B = args.batch
+    x = torch.randn((B,) + SHAPE + (1,), device=dev)
+    lay = ne.layers.GaussianBlur(sigma=args.sigma)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed_region(lambda: lay(x), args.steps, args.warmup, world)
+    clocks = sampler.stop()
+    peak, peak_src = measured_peak()
+    achieved = 8.0 * B * V * args.steps / (ms * 1e-3) / 1e9
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'voxels/s, GaussianBlur(sigma=%g), 160x192x224 fp32' % args.sigma,
+            'value': world * B * V * args.steps / (ms * 1e-3), 'unit': 'voxels/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'GaussianBlur(sigma=%g) on [%d,160,192,224,1] (reference layers.py:251-364): '
+                                   'three separable passes' % (args.sigma, B)},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': None, 'peak_source': peak_src,
+                         'bytes_model': '8 B/voxel for the whole blur (read once, write once); the three-pass '
+                                        'implementation moves 24 B/voxel, so 0.33 is its ceiling',
+                         'kernel': 'sepconv_col_kernel x2 + sepconv_row_kernel', 'per': 'GPU'},
+            'gpu_launches': args.steps * 3, 'clocks': clocks}), flush=True)
+    finish(world)
+
+
 def finish(world):
     if world > 1:
         import torch.distributed as dist
@@ -413,7 +488,8 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--op', default='warp', choices=['warp', 'dice', 'cce', 'lc3d', 'resize'])
+    ap.add_argument('--op', default='warp', choices=['warp', 'dice', 'cce', 'lc3d', 'resize', 'mi', 'mi_segs', 'blur'])
+    ap.add_argument('--sigma', type=float, default=1.0)
     ap.add_argument('--batch', type=int, default=8)
     ap.add_argument('--lc-batch', type=int, default=1)
     ap.add_argument('--method', default='linear', choices=['linear', 'nearest'])
@@ -430,7 +506,8 @@ def main():
         raise SystemExit('bench.py: no CUDA device -- the product path has no CPU fallback '
                          '(use --impl reference for the CPU port of the reference)')
     {'warp': bench_warp, 'dice': bench_dice, 'cce': lambda a: bench_dice(a, cce=True), 'lc3d': bench_lc3d,
-     'resize': bench_resize}[args.op](args)
+     'resize': bench_resize, 'mi': bench_mi, 'mi_segs': lambda a: bench_mi(a, segs=True),
+     'blur': bench_blur}[args.op](args)
 
 
 if __name__ == '__main__':

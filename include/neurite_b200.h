@@ -201,6 +201,50 @@ NRT_API int nrt_lc3d_bwd_f32(const float* x, const float* kernel, const float* g
                      const int32_t* ksize, const int32_t* strides, int feature_order,
                      int64_t p0, int64_t p_count, void* stream);
 
+/* ---- mutual information (neurite/tf/metrics.py:41-336, utils.py:1099-1172) ----
+ * Two operands over nv voxels of each of B items.  An operand is either
+ *   quant = 1: an intensity image, element (b, v, c) at p[b*batch_stride + v*vox_stride + c],
+ *              soft-quantised in registers: w[bin] = exp(-alpha * (clip(x, min_clip, max_clip) - centers[bin])^2)
+ *              (soft_quantize, utils.py:1157-1171); C channels are processed independently
+ *              (MutualInformation.channelwise, metrics.py:185-225);
+ *   quant = 0: a probability / similarity map, element (b, v, bin) at p[b*batch_stride + v*vox_stride + bin]
+ *              (MutualInformation.maps, metrics.py:227-292); requires C == 1.
+ * stats[(b*C + c)][nbx*nby + nbx + nby] = joint sums  sum_v wx[i]*wy[j]  (row-major i, j), then
+ * sum_v wx[i], then sum_v wy[j]  -- the three reductions metrics.py:272-283 need.  Voxel-range
+ * sharding across GPUs: every rank passes its own voxel slab (pointer offset, nv) and the stats
+ * are summed (one all-reduce) before nrt_mi_finalize_f32.  *flag is set to 1 if a map value is
+ * negative (tf.debugging.assert_non_negative, metrics.py:262-263).  bins <= 64; bins <= 32 run on
+ * the tensor cores (3xTF32 mma).  workspace: nrt_mi_workspace_bytes(B*C, nbx, nby). */
+NRT_API int64_t nrt_mi_workspace_bytes(int items, int nbx, int nby);
+NRT_API int nrt_mi_hist_f32(const float* x, int64_t x_batch_stride, int64_t x_vox_stride, int x_quant, int nbx,
+                    const float* x_centers, const float* y, int64_t y_batch_stride, int64_t y_vox_stride,
+                    int y_quant, int nby, const float* y_centers, int B, int C, int64_t nv, float alpha,
+                    float min_clip, float max_clip, float* stats, int32_t* flag, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+/* metrics.py:265-292 on the sums:  pxy = h/(sum h + eps), px = sx/(sum sx + eps), py likewise,
+ * mi[item] = sum_ij pxy * log(pxy / (px*py + eps) + eps);  eps = K.epsilon() = 1e-7. */
+NRT_API int nrt_mi_finalize_f32(const float* stats, int items, int nbx, int nby, float eps, float* mi, void* stream);
+/* out2 = {min(x), max(x)} over n elements (K.min / K.max, utils.py:1151-1152). */
+NRT_API int64_t nrt_minmax_workspace_bytes(void);
+NRT_API int nrt_minmax_f32(const float* x, int64_t n, float* out2, void* workspace, int64_t workspace_bytes, void* stream);
+/* centers = tf.linspace(minmax[0], minmax[1], nb) in fp32 (utils.py:1153), all on the device. */
+NRT_API int nrt_mi_bin_centers_f32(const float* minmax, int nb, float* centers, void* stream);
+/* soft_quantize as a tensor op (utils.py:1099-1172): out[e*nb + b], e < n. */
+NRT_API int nrt_soft_quantize_f32(const float* x, int64_t n, const float* centers, int nb, float alpha, float min_clip,
+                          float max_clip, int return_log, float* out, void* stream);
+
+/* ---- separable convolution pass / GaussianBlur / Subsample -------------------
+ * One 1-D cross-correlation pass of separable_conv (utils.py:665-751): x viewed as
+ * [outer, L, inner] -> out [outer, L_out, inner],
+ *   out[o, l, i] = sum_j kernel[j] * x[o, l*stride - pad_before + j*dilation, i]   (zero outside [0, L)).
+ * The caller derives pad_before / L_out from TF's 'SAME' / 'VALID' rules.  kernel is a device
+ * pointer ([K]).  x and out must not alias. */
+NRT_API int nrt_sepconv_axis_f32(const float* x, float* out, int64_t outer, int64_t L, int64_t inner, const float* kernel,
+                         int K, int stride, int dilation, int pad_before, int64_t L_out, void* stream);
+/* out[o, l, i] = x[o, index[l], i]: tf.gather along an axis (subsample_axis, utils.py:818-823). */
+NRT_API int nrt_gather_axis_f32(const float* x, const int32_t* index, float* out, int64_t outer, int64_t L, int64_t inner,
+                        int64_t L_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,20 @@ SIGNATURES = {
                                          c_i64, c_i64, c_vp]),
     'nrt_lc3d_bwd_f32': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, P_I32, ctypes.c_int,
                                          ctypes.c_int, P_I32, P_I32, ctypes.c_int, c_i64, c_i64, c_vp]),
+    'nrt_mi_workspace_bytes': (c_i64, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    'nrt_mi_hist_f32': (ctypes.c_int, [c_vp, c_i64, c_i64, ctypes.c_int, ctypes.c_int, c_vp,
+                                        c_vp, c_i64, c_i64, ctypes.c_int, ctypes.c_int, c_vp,
+                                        ctypes.c_int, ctypes.c_int, c_i64, c_f32, c_f32, c_f32,
+                                        c_vp, c_vp, c_vp, c_i64, c_vp]),
+    'nrt_mi_finalize_f32': (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f32, c_vp, c_vp]),
+    'nrt_minmax_workspace_bytes': (c_i64, []),
+    'nrt_minmax_f32': (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    'nrt_mi_bin_centers_f32': (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp]),
+    'nrt_soft_quantize_f32': (ctypes.c_int, [c_vp, c_i64, c_vp, ctypes.c_int, c_f32, c_f32, c_f32,
+                                              ctypes.c_int, c_vp, c_vp]),
+    'nrt_sepconv_axis_f32': (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_int, c_i64, c_vp]),
+    'nrt_gather_axis_f32': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp]),
 }
 
 

@@ -478,3 +478,115 @@ def local_conv3d(inputs, kernel, bias, kernel_size, strides, output_shape, data_
     if post is not None:
         out = post(out)
     return out
+
+
+# ---------------------------------------------------------------------------------------
+class GaussianBlur(_Layer):
+    """Blur a tensor [B, *space, C] with a separable Gaussian, reference layers.py:251-364.
+    Isotropic or anisotropic, optionally with SDs drawn per call (`random=True`)."""
+
+    def __init__(self, sigma=None, level=None, random=False, min_sigma=0, isotropic=False, seed=None, **kwargs):
+        import warnings
+        assert sigma is not None or level is not None, 'sigma or level must be provided'
+        assert not (sigma is not None and level is not None), 'only sigma or level must be provided'
+        if level is not None:
+            warnings.warn('The `level` argument to ne.layers.GaussianBlur is deprecated and will '
+                          'be removed in a future version. Please use `sigma` instead.')
+            if level < 1:
+                raise ValueError('Gaussian blur level must not be less than 1')
+            if random:
+                raise ValueError('level argument incompatible with random blurring')
+        if isotropic and not random:
+            raise ValueError('For non-random blurring, isotropy is implicitly controlled by the '
+                             'number of sigmas provided. Set `isotropic` only for random blur.')
+        # (the reference overwrites the level-derived sigma with `sigma` -- None -- at :305; a layer
+        #  built from `level` then fails in build().  Here `level` keeps its documented meaning.)
+        self.sigma = sigma if sigma is not None else (level - 1) ** 2
+        self.random = random
+        self.min_sigma = min_sigma
+        self.isotropic = isotropic
+        self.seed = seed
+        self._calls = 0
+        super().__init__(**kwargs)
+
+    def get_config(self):
+        config = super().get_config().copy()
+        config.update({'sigma': self.sigma, 'random': self.random, 'min_sigma': self.min_sigma,
+                       'isotropic': self.isotropic, 'seed': self.seed})
+        return config
+
+    def _normalize_sigma(self, sigma, ndims):
+        sigma = np.ravel(sigma).tolist()
+        if len(sigma) not in (1, ndims):
+            raise ValueError(f'1 or {ndims} sigmas expected in {ndims}D space, got {len(sigma)}')
+        if any(s < 0 for s in sigma):
+            raise ValueError('Gaussian blur sigma must not be less than 0')
+        if len(sigma) > 1 and self.isotropic:
+            raise ValueError(f'random isotropic blur requires a single sigma, got {len(sigma)}')
+        if len(sigma) == 1:
+            sigma = sigma * ndims
+        return sigma
+
+    def build(self, input_shape):
+        ndims = len(input_shape) - 2
+        self.sigma = self._normalize_sigma(self.sigma, ndims)
+        self.min_sigma = self._normalize_sigma(self.min_sigma, ndims)
+        if self.isotropic and self.random:
+            self.sigma = self.sigma[:1]
+            self.min_sigma = self.min_sigma[:1]
+        super().build(input_shape)
+
+    def call(self, x):
+        if not any(s > 0 for s in self.sigma):
+            return x
+        seed = None if self.seed is None else self.seed + self._calls       # a fresh draw per call
+        self._calls += 1
+        kernel = utils.gaussian_kernel(sigma=self.sigma, random=self.random, min_sigma=self.min_sigma,
+                                       separate=True, seed=seed)
+        kernel = kernel if isinstance(kernel, list) else [kernel]
+        return utils.separable_conv(x, kernel, batched=True)
+
+    def compute_output_shape(self, input_shape):
+        return tuple(input_shape)
+
+
+class Subsample(_Layer):
+    """Subsample along one randomly drawn spatial axis with nearest neighbours and optionally
+    upsample again, reference layers.py:367-443."""
+
+    def __init__(self, stride_min=1, stride_max=8, axes=None, prob=1, upsample=True, seed=None, **kwargs):
+        self.stride_min = stride_min
+        self.stride_max = stride_max
+        self.axes = axes
+        self.prob = prob
+        self.upsample = upsample
+        self.seed = seed
+        self._calls = 0
+        super().__init__(**kwargs)
+
+    def get_config(self):
+        config = super().get_config().copy()
+        config.update({'stride_min': self.stride_min, 'stride_max': self.stride_max, 'axes': self.axes,
+                       'prob': self.prob, 'upsample': self.upsample, 'seed': self.seed})
+        return config
+
+    def build(self, input_shape):
+        ndims = len(input_shape) - 2
+        assert ndims in (1, 2, 3), 'only 1D, 2D, or 3D supported'
+        allowed = list(range(1, ndims + 1))
+        if self.axes is None:
+            axes = allowed
+        else:
+            axes = [int(a) % len(input_shape) for a in np.ravel(self.axes)]
+            if any(a not in allowed for a in axes):
+                raise ValueError(f'axes {self.axes} not in allowed spatial axes {allowed}')
+        self.axes = axes
+        super().build(input_shape)
+
+    def call(self, x):
+        if self.prob == 0 or self.stride_max == 1:
+            return x
+        seed = None if self.seed is None else self.seed + self._calls
+        self._calls += 1
+        return utils.subsample_axis(x, stride_min=self.stride_min, stride_max=self.stride_max, axes=self.axes,
+                                    prob=self.prob, upsample=self.upsample, seed=seed)

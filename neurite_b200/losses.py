@@ -5,6 +5,7 @@ CategoricalCrossentropy.loss = cce.  Bound methods are `(y_true, y_pred) -> Tens
 the protocol the reference hands to model.compile(loss=...) and callbacks.PredictMetrics.
 """
 from . import metrics
+from .metrics import MutualInformation  # noqa: F401  (reference losses.py:40-43 re-exports it)
 
 
 class _DiceLossMixin:

@@ -390,3 +390,251 @@ def batch_channel_flatten(x):
 
 
 flatten_batch_channel = batch_channel_flatten
+
+
+# ---------------------------------------------------------------------------------------
+# soft quantisation (utils.py:1095-1172) -- the tensor op; MutualInformation fuses it (metrics.py)
+# ---------------------------------------------------------------------------------------
+_SCRATCH = {}
+
+
+def _scratch(device, nbytes):
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _SCRATCH.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _SCRATCH[key] = buf
+    return buf
+
+
+def minmax(x, group=None):
+    """device tensor [min(x), max(x)] (K.min / K.max, utils.py:1151-1152), no host sync.
+    With `group`, the extrema over every rank's shard (one MIN all-reduce of [min, -max])."""
+    require_cuda(x)
+    x32 = _as_f32(x).contiguous()
+    out = torch.empty(2, dtype=torch.float32, device=x.device)
+    nb = lib.nrt_minmax_workspace_bytes()
+    ws = _scratch(x.device, nb)
+    with torch.cuda.device(x.device):
+        check(lib.nrt_minmax_f32(ptr(x32), x32.numel(), ptr(out), ptr(ws), nb, stream_ptr(x.device)))
+    if group is not None:
+        import torch.distributed as dist
+        packed = torch.stack([out[0], -out[1]])
+        dist.all_reduce(packed, op=dist.ReduceOp.MIN, group=group)
+        out = torch.stack([packed[0], -packed[1]])
+    return out
+
+
+def bin_centers_from_range(mm, nb_bins):
+    """tf.linspace(min, max, nb_bins) in fp32 on the device (utils.py:1153)."""
+    centers = torch.empty(int(nb_bins), dtype=torch.float32, device=mm.device)
+    with torch.cuda.device(mm.device):
+        check(lib.nrt_mi_bin_centers_f32(ptr(mm), int(nb_bins), ptr(centers), stream_ptr(mm.device)))
+    return centers
+
+
+def soft_quantize(x, bin_centers=None, nb_bins=16, alpha=1, min_clip=-np.inf, max_clip=np.inf,
+                  return_log=False):
+    """(Softly) quantize intensities with RBFs, utils.py:1099-1172: [...] -> [..., B]."""
+    require_cuda(x)
+    x32 = _as_f32(x).contiguous()
+    if bin_centers is not None:
+        centers = torch.as_tensor(bin_centers, dtype=torch.float32, device=x.device).contiguous()
+        assert nb_bins is None, 'cannot provide both bin_centers and nb_bins'
+        nb_bins = centers.shape[0]
+    else:
+        if nb_bins is None:
+            nb_bins = 16
+        centers = bin_centers_from_range(minmax(x32), nb_bins)
+    out = torch.empty(tuple(x32.shape) + (int(nb_bins),), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.nrt_soft_quantize_f32(ptr(x32), x32.numel(), ptr(centers), int(nb_bins), float(alpha),
+                                        float(min_clip), float(max_clip), int(bool(return_log)), ptr(out),
+                                        stream_ptr(x.device)))
+    return out
+
+
+soft_digitize = soft_quantize
+
+
+# ---------------------------------------------------------------------------------------
+# gaussian_kernel / separable_conv / subsample_axis (utils.py:581-826)
+# ---------------------------------------------------------------------------------------
+def gaussian_kernel(sigma, windowsize=None, indexing='ij', separate=False, random=False, min_sigma=0,
+                    dtype=torch.float32, seed=None, device=None):
+    """N-D Gaussian kernel, utils.py:581-662.  Returns torch tensors (on `device`, default CPU);
+    built on the host in fp32 with the reference's operation order.  `random=True` draws each
+    SD uniformly from [min_sigma, sigma) with a torch generator (TF's stream is not reproducible
+    elsewhere)."""
+    assert dtype.is_floating_point, f'{dtype} is not a real floating-point type'
+    npdt = {torch.float32: np.float32, torch.float64: np.float64, torch.float16: np.float16}[dtype]
+    if not isinstance(sigma, (list, tuple)):
+        sigma = [sigma]
+    if not isinstance(min_sigma, (list, tuple)):
+        min_sigma = [min_sigma] * len(sigma)
+    eps = np.finfo(npdt).eps
+    sigma = [max(f, eps) for f in sigma]
+    min_sigma = [max(f, eps) for f in min_sigma]
+    if windowsize is None:
+        windowsize = [np.round(f * 3) * 2 + 1 for f in sigma]
+    if not isinstance(windowsize, (list, tuple)):
+        windowsize = [windowsize]
+    if len(sigma) != len(windowsize):
+        raise ValueError(f'sigma {sigma} and width {windowsize} differ in length')
+    center = [(w - 1) / 2 for w in windowsize]
+    mesh = [np.arange(w) - c for w, c in zip(windowsize, center)]
+    mesh = [-0.5 * x**2 for x in mesh]
+    if not separate:
+        mesh = np.meshgrid(*mesh, indexing=indexing)
+    mesh = [m.astype(npdt) for m in mesh]
+    if random:
+        gen = torch.Generator().manual_seed(int(np.random.default_rng(seed).integers(2**31)))
+        sigma = [float(a + (b - a) * torch.rand(1, generator=gen).item()) for a, b in zip(min_sigma, sigma)]
+    exponent = [m / npdt(s**2) for m, s in zip(mesh, sigma)]
+    if not separate:
+        exponent = [np.sum(np.stack(exponent), axis=0, dtype=np.float64).astype(npdt)]
+    kernel = [np.exp(x) for x in exponent]
+    kernel = [x / np.sum(x, dtype=np.float64).astype(npdt) for x in kernel]
+    kernel = [torch.as_tensor(k, dtype=dtype, device=device) for k in kernel]
+    return kernel if len(kernel) > 1 else kernel[0]
+
+
+def _same_padding(n, k, stride, dilation):
+    n_out = -(-n // stride)
+    total = max((n_out - 1) * stride + (k - 1) * dilation + 1 - n, 0)
+    return n_out, total // 2
+
+
+def _conv_axis_raw(x32, kdev, axis, stride, dilation, pad_before, n_out):
+    """one nrt_sepconv_axis_f32 pass along dim `axis` of a contiguous fp32 tensor."""
+    shp = list(x32.shape)
+    outer = int(np.prod(shp[:axis], dtype=np.int64))
+    L = shp[axis]
+    inner = int(np.prod(shp[axis + 1:], dtype=np.int64))
+    out = torch.empty(shp[:axis] + [int(n_out)] + shp[axis + 1:], dtype=torch.float32, device=x32.device)
+    with torch.cuda.device(x32.device):
+        check(lib.nrt_sepconv_axis_f32(ptr(x32), ptr(out), outer, L, inner, ptr(kdev), int(kdev.numel()), int(stride),
+                                       int(dilation), int(pad_before), int(n_out), stream_ptr(x32.device)))
+    return out
+
+
+class _ConvAxisFn(torch.autograd.Function):
+    """autograd shell of one pass: d/dx of a stride-1 cross-correlation is the correlation of the
+    upstream gradient with the flipped kernel and the complementary padding."""
+
+    @staticmethod
+    def forward(ctx, x, kdev, axis, stride, dilation, pad_before, n_out):
+        x32 = _as_f32(x.detach()).contiguous()
+        ctx.save_for_backward(kdev)
+        ctx.cfg = (axis, stride, dilation, pad_before, x32.shape[axis])
+        return _conv_axis_raw(x32, kdev, axis, stride, dilation, pad_before, n_out)
+
+    @staticmethod
+    def backward(ctx, g):
+        (kdev,) = ctx.saved_tensors
+        axis, stride, dilation, pad_before, L = ctx.cfg
+        if stride != 1:
+            raise NotImplementedError('gradient of a strided separable_conv pass')
+        K = kdev.numel()
+        gx = _conv_axis_raw(_as_f32(g).contiguous(), kdev.flip(0).contiguous(), axis, 1, dilation,
+                            (K - 1) * dilation - pad_before, L)
+        return gx, None, None, None, None, None, None
+
+
+def separable_conv(x, kernels, axis=None, batched=False, padding='SAME', strides=None, dilations=None):
+    """Apply 1-D kernels along axes of a tensor with a trailing feature dimension; the same
+    filters across features (utils.py:665-751).  tf.nn.convolution semantics: cross-correlation,
+    zero 'SAME' padding (extra element at the end) or 'VALID'."""
+    require_cuda(x)
+    if not batched:
+        x = x[None]
+    num_dim = x.dim() - 2
+    if np.isscalar(axis):
+        axis = [axis]
+    axes_space = range(num_dim)
+    if axis is None:
+        axis = axes_space
+    assert all(ax in axes_space for ax in axis), 'non-spatial axis passed'
+
+    def conform(v):
+        v = np.ravel(1 if v is None else v).tolist()
+        return v * len(axis) if len(v) == 1 else v
+    strides, dilations = conform(strides), conform(dilations)
+    assert len(strides) == len(axis), 'number of strides and axes differ'
+    assert len(dilations) == len(axis), 'number of dilations and axes differ'
+    if not isinstance(kernels, (tuple, list)):
+        kernels = [kernels]
+    if len(kernels) == 1:
+        kernels = list(kernels) * len(axis)
+    assert len(kernels) == len(axis), 'number of kernels and axes differ'
+    if padding.upper() not in ('SAME', 'VALID'):
+        raise ValueError(f'unknown padding {padding}')
+
+    y = x
+    for ax, k, s, d in zip(axis, kernels, strides, dilations):
+        s, d = int(s), int(d)
+        if s > 1 and d > 1:
+            raise ValueError('strides > 1 not supported in conjunction with dilation_rate > 1')
+        kdev = torch.as_tensor(k, dtype=torch.float32).reshape(-1).to(x.device).contiguous()
+        K, n = kdev.numel(), y.shape[ax + 1]
+        if padding.upper() == 'SAME':
+            n_out, pb = _same_padding(n, K, s, d)
+        else:
+            n_out, pb = max(-(-(n - (K - 1) * d) // s), 0), 0
+        y = _ConvAxisFn.apply(y, kdev, ax + 1, s, d, pb, n_out)
+    return y if batched else y[0]
+
+
+def subsample_indices(width, thick, upsample=True):
+    """gather indices of subsample_axis for a drawn thickness (utils.py:812-823), fp32 like TF."""
+    f32 = np.float32
+    num_slice = int(f32(width) / f32(thick) + f32(0.5))
+
+    def lin(stop, num):
+        if num == 1:
+            return np.array([0], f32)
+        delta = f32(stop) / f32(num - 1)
+        out = delta * np.arange(num, dtype=f32)
+        out[-1] = f32(stop)
+        return out
+    ind = (lin(width - 1, num_slice) + f32(0.5)).astype(np.int32)
+    if not upsample:
+        return ind
+    return ind[(lin(num_slice - 1, width) + f32(0.5)).astype(np.int32)]
+
+
+def gather_axis(x, index, axis):
+    """tf.gather(x, index, axis=axis) on the device (nrt_gather_axis_f32)."""
+    require_cuda(x)
+    x32 = _as_f32(x).contiguous()
+    idx = torch.as_tensor(np.asarray(index, dtype=np.int32), device=x.device)
+    shp = list(x32.shape)
+    outer = int(np.prod(shp[:axis], dtype=np.int64))
+    inner = int(np.prod(shp[axis + 1:], dtype=np.int64))
+    out = torch.empty(shp[:axis] + [idx.numel()] + shp[axis + 1:], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.nrt_gather_axis_f32(ptr(x32), ptr(idx), ptr(out), outer, shp[axis], inner, idx.numel(),
+                                      stream_ptr(x.device)))
+    return out.to(x.dtype) if x.dtype != torch.float32 else out
+
+
+def subsample_axis(x, stride_min=1, stride_max=8, axes=None, prob=1, upsample=True, seed=None):
+    """Symmetrically subsample along one (randomly drawn) axis with nearest neighbours and
+    optionally upsample again (utils.py:754-826).  The axis, the thickness and the Bernoulli
+    draw come from a numpy generator seeded with `seed` (TF's random stream cannot be
+    reproduced outside TF); everything downstream of the draws follows the reference."""
+    require_cuda(x)
+    rand = np.random.default_rng(seed)
+    num_dim = x.dim()
+    if axes is None:
+        axes = range(num_dim)
+    if np.isscalar(axes):
+        axes = [axes]
+    assert all(i in range(num_dim) for i in axes), 'invalid axis passed'
+    assert 0 < stride_min and stride_min <= stride_max, 'invalid strides'
+    ax = list(axes)[int(rand.integers(0, len(axes)))]
+    thick = np.float32(rand.uniform(stride_min, stride_max))
+    assert 0 <= prob <= 1, f'{prob} not a probability'
+    if prob < 1 and not (rand.uniform() < prob):
+        thick = np.float32(1)
+    return gather_axis(x, subsample_indices(x.shape[ax], thick, upsample), ax)

@@ -261,11 +261,128 @@ def gen_lc3d():
              data_format=np.array(fmt), filters=np.array(filters))
 
 
+# ---------------------------------------------------------------------------------------
+# MutualInformation / soft_quantize  
+# ---------------------------------------------------------------------------------------
+def gen_mi():
+    import contextlib
+    import io
+    ref = 'reference neurite/tf/metrics.py:41-336 MutualInformation + utils.py:1099-1172 soft_quantize on tfshim'
+    rng = np.random.default_rng(70)
+    S = (9, 10, 11)
+
+    def make_mi(**kw):
+        with contextlib.redirect_stdout(io.StringIO()):          # the ctor prints alpha (metrics.py:114)
+            return ne.metrics.MutualInformation(**kw)
+
+    # soft_quantize as a tensor op
+    x = rng.uniform(-0.2, 1.3, (2,) + S).astype(F32)
+    for tag, kw in (('default', {}), ('nb8_alpha', dict(nb_bins=8, alpha=3.5)),
+                    ('centers_clip', dict(bin_centers=np.linspace(0, 1, 6).astype(F32), nb_bins=None, alpha=20.,
+                                          min_clip=0.1, max_clip=0.9)),
+                    ('log', dict(nb_bins=5, alpha=2., return_log=True))):
+        out = npy(ne.utils.soft_quantize(T(x), **kw))
+        save('softq_' + tag, ref, x=x, out=out, kw=np.array(repr(kw)))
+
+    # volumes: correlated pair (y = smooth function of x + noise), independent pair, identical pair
+    a = rng.uniform(0, 1, (3,) + S + (1,)).astype(F32)
+    b = np.clip(0.6 * a ** 2 + 0.2 + 0.05 * rng.standard_normal(a.shape), 0, 1).astype(F32)
+    c = rng.uniform(0, 1, a.shape).astype(F32)
+    for nb in (16, 32, 7):
+        mi = make_mi(nb_bins=nb)
+        save('mi_volumes_nb%d' % nb, ref, x=a, y=b, nb_bins=np.array(nb), alpha=npy(mi.soft_bin_alpha),
+             mi=npy(mi.volumes(T(a), T(b))), mi_indep=npy(mi.volumes(T(a), T(c))), mi_self=npy(mi.volumes(T(a), T(a))))
+    mi = make_mi(nb_bins=12, soft_bin_alpha=55.0, min_clip=0.05, max_clip=0.95)
+    save('mi_volumes_clip_alpha', ref, x=a, y=b, nb_bins=np.array(12), alpha=np.array(55.0, F32),
+         min_clip=np.array(0.05, F32), max_clip=np.array(0.95, F32), mi=npy(mi.volumes(T(a), T(b))))
+
+    # channelwise: 3 channels, bins from the min/max of the whole tensor
+    xc = rng.uniform(0, 1, (2,) + S + (3,)).astype(F32)
+    yc = np.clip(xc[..., ::-1] * 0.7 + 0.1 * rng.standard_normal(xc.shape), 0, 1).astype(F32)
+    mi = make_mi()
+    save('mi_channelwise_c3', ref, x=xc, y=yc, mi=npy(mi.channelwise(T(xc), T(yc))))
+
+    # segs / maps: softmax probability maps, 16 and 5 labels
+    for L in (16, 5):
+        lx = rng.standard_normal((2,) + S + (L,)).astype(F32) * 2
+        ly = (lx + rng.standard_normal(lx.shape).astype(F32)).astype(F32)
+        px = (np.exp(lx) / np.exp(lx).sum(-1, keepdims=True)).astype(F32)
+        py = (np.exp(ly) / np.exp(ly).sum(-1, keepdims=True)).astype(F32)
+        save('mi_segs_L%d' % L, ref, x=px, y=py, mi=npy(make_mi().segs(T(px), T(py))))
+        if L == 16:
+            px16 = px
+
+    # volume_seg: volume vs 16-label map (the quantised volume has nb_bins = 16 channels too)
+    v = rng.uniform(0, 1, (2,) + S + (1,)).astype(F32)
+    mi = make_mi(nb_bins=16)
+    save('mi_volume_seg', ref, vol=v, seg=px16, mi_vs=npy(mi.volume_seg(T(v), T(px16))),
+         mi_sv=npy(mi.volume_seg(T(px16), T(v))))
+
+    # error behaviour
+    errs = {}
+    def rec(name, fn):
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                fn()
+            errs[name] = ''
+        except Exception as ex:                                    # noqa: BLE001
+            errs[name] = '%s: %s' % (type(ex).__name__, ex)
+    rec('volumes_two_channels', lambda: make_mi().volumes(T(xc), T(yc)))
+    rec('maps_shape_mismatch', lambda: make_mi().maps(T(px), T(py[..., :3])))
+    rec('volume_seg_bins_ne_labels', lambda: make_mi(nb_bins=16).volume_seg(T(v), T(px)))
+    rec('maps_negative', lambda: make_mi().maps(T(px), T(-py)))
+    rec('volume_seg_two_volumes', lambda: make_mi().volume_seg(T(v), T(v)))
+    rec('both_centers_and_bins', lambda: ne.metrics.MutualInformation(bin_centers=np.linspace(0, 1, 4), nb_bins=4))
+    rec('explicit_centers_volumes', lambda: make_mi(bin_centers=np.linspace(0, 1, 8).astype(F32)).volumes(T(a), T(b)))
+    save('mi_errors', ref, **{k: np.array(val) for k, val in errs.items()})
+
+
+# ---------------------------------------------------------------------------------------
+# gaussian_kernel / separable_conv / GaussianBlur  
+# ---------------------------------------------------------------------------------------
+def gen_blur():
+    ref = ('reference neurite/tf/utils/utils.py:581-751 gaussian_kernel + separable_conv, layers.py:251-364 '
+           'GaussianBlur on tfshim (tf.nn.convolution restated: contract)')
+    rng = np.random.default_rng(80)
+    for tag, sigma in (('s1', 1.0), ('s0p5', 0.5), ('s2p3', 2.3), ('aniso', [1.0, 0.0, 2.0])):
+        ks = ne.utils.gaussian_kernel(sigma, separate=True)
+        ks = ks if isinstance(ks, list) else [ks]
+        save('gausskernel_' + tag, ref, sigma=np.asarray(sigma, F32), n=np.array(len(ks)),
+             **{'k%d' % i: npy(k) for i, k in enumerate(ks)})
+    k2 = npy(ne.utils.gaussian_kernel([1.0, 1.5]))
+    save('gausskernel_2d_full', ref, sigma=np.asarray([1.0, 1.5], F32), k=k2)
+
+    x3 = rng.standard_normal((2, 9, 12, 40, 2)).astype(F32)
+    for tag, sigma in (('s1', 1.0), ('aniso', [1.5, 0.0, 0.7]), ('s3', 3.0)):
+        out = npy(ne.layers.GaussianBlur(sigma=sigma)(T(x3)))
+        save('blur3d_' + tag, ref, x=x3, sigma=np.asarray(sigma, F32), out=out)
+    x2 = rng.standard_normal((3, 17, 70, 1)).astype(F32)
+    save('blur2d_s2', ref, x=x2, sigma=np.asarray(2.0, F32), out=npy(ne.layers.GaussianBlur(sigma=2.0)(T(x2))))
+    x1 = rng.standard_normal((2, 50, 3)).astype(F32)
+    save('blur1d_s1p2', ref, x=x1, sigma=np.asarray(1.2, F32), out=npy(ne.layers.GaussianBlur(sigma=1.2)(T(x1))))
+
+    # separable_conv options: VALID, strides, dilations, single axis, unbatched
+    k5 = rng.standard_normal(5).astype(F32)
+    k4 = rng.standard_normal(4).astype(F32)
+    xs = rng.standard_normal((2, 11, 13, 37, 3)).astype(F32)
+    cases = [
+        ('valid', dict(kernels=[T(k5)], padding='VALID', batched=True)),
+        ('even_same', dict(kernels=[T(k4)], batched=True)),
+        ('stride2', dict(kernels=[T(k5), T(k4), T(k5)], strides=2, batched=True)),
+        ('dil2_axis1', dict(kernels=T(k5), axis=1, dilations=2, batched=True)),
+        ('axes02', dict(kernels=[T(k4), T(k5)], axis=[0, 2], strides=[1, 3], batched=True)),
+    ]
+    for tag, kw in cases:
+        out = npy(ne.utils.separable_conv(T(xs), **kw))
+        save('sepconv_' + tag, ref, x=xs, k5=k5, k4=k4, out=out, kw=np.array(tag))
+    out = npy(ne.utils.separable_conv(T(xs[0]), T(k5)))
+    save('sepconv_unbatched', ref, x=xs[0], k5=k5, k4=k4, out=out, kw=np.array('unbatched'))
+
+
 if __name__ == '__main__':
-    gen_interpn()
-    gen_resize()
-    gen_spatial_transformer()
-    gen_dice()
-    gen_lc3d()
+    only = sys.argv[1:]
+    for fn in (gen_interpn, gen_resize, gen_spatial_transformer, gen_dice, gen_lc3d, gen_mi, gen_blur):
+        if not only or fn.__name__[4:] in only:
+            fn()
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print('total %.1f KB in %s' % (tot / 1024, OUT))

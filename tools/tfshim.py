@@ -49,6 +49,10 @@ class DType:
         self.np = np.dtype(np_dtype)
 
     @property
+    def as_numpy_dtype(self):
+        return self.np.type
+
+    @property
     def is_floating(self):
         return np.issubdtype(self.np, np.floating)
 
@@ -179,6 +183,9 @@ class Tensor:
     def __le__(self, o): return self._bin(o, np.less_equal)
     def __gt__(self, o): return self._bin(o, np.greater)
     def __ge__(self, o): return self._bin(o, np.greater_equal)
+    def __eq__(self, o): return self._bin(o, np.equal)
+    def __ne__(self, o): return self._bin(o, np.not_equal)
+    __hash__ = object.__hash__
     __hash__ = object.__hash__
 
 
@@ -296,6 +303,64 @@ def _install_tf():
     tf.linspace = linspace
     tf.map_fn = lambda fn, elems, **k: Tensor(np.stack([A(fn(e)) for e in (elems if isinstance(elems, Tensor) else zip(*elems))], 0))
 
+
+    # ---- additions for MutualInformation / soft_quantize / gaussian_kernel / separable_conv ----
+    tf.newaxis = None
+    tf.transpose = lambda x, perm=None, **k: Tensor(np.transpose(A(T(x)), perm))
+    tf.minimum = lambda a, b: Tensor(np.minimum(A(T(a)), A(T(b))))
+    tf.maximum = lambda a, b: Tensor(np.maximum(A(T(a)), A(T(b))))
+    tf.square = lambda x: Tensor(np.square(np.asarray(A(T(x)), dtype=np.float32 if isinstance(x, float) else None)))
+    tf.exp = lambda x: Tensor(np.exp(A(x)))
+    tf.shape = lambda x: Tensor(np.asarray(A(T(x)).shape, dtype=np.int32))
+    tf.expand_dims = lambda x, axis: Tensor(np.expand_dims(A(T(x)), axis))
+    tf.is_tensor = lambda x: isinstance(x, Tensor)
+    _red = lambda fn: (lambda x, axis=None, keepdims=False: Tensor(
+        fn(A(T(x)), axis=axis, keepdims=keepdims, dtype=np.float64).astype(A(T(x)).dtype)
+        if A(T(x)).dtype.kind == 'f' else fn(A(T(x)), axis=axis, keepdims=keepdims).astype(A(T(x)).dtype)))
+    tf.reduce_sum = _red(np.sum)
+    tf.reduce_mean = _red(np.mean)
+    tf.reduce_prod = _red(np.prod)
+    dtypes = _InertModule('tensorflow.dtypes')
+    dtypes.as_dtype = lambda d: d if isinstance(d, DType) else DType(d)
+    tf.dtypes = dtypes
+    exp_mod = _InertModule('tensorflow.experimental')
+    exp_np = _InertModule('tensorflow.experimental.numpy')
+    exp_np.diff = lambda x, **k: Tensor(np.diff(A(T(x))))
+    exp_mod.numpy = exp_np
+    tf.experimental = exp_mod
+
+    def convolution(x, k, padding='VALID', strides=None, dilations=None, **kw):
+        """tf.nn.convolution (third party; restated): N-D cross-correlation, one in/out feature,
+        zero 'SAME' padding with the extra element at the end; float64 accumulate, one rounding."""
+        x, k = A(T(x)), A(T(k))
+        nd = x.ndim - 2
+        assert x.shape[-1] == 1 and k.shape[-2:] == (1, 1)
+        ks = k.shape[:nd]
+        st = [1] * nd if strides is None else [int(v) for v in strides]
+        dl = [1] * nd if dilations is None else [int(v) for v in dilations]
+        if any(a > 1 and b > 1 for a, b in zip(st, dl)):
+            raise ValueError('strides > 1 not supported in conjunction with dilation_rate > 1')
+        outs, pads = [], []
+        for n, kk, s_, d_ in zip(x.shape[1:-1], ks, st, dl):
+            eff = (kk - 1) * d_ + 1
+            if padding.upper() == 'SAME':
+                o = -(-n // s_)
+                tot = max((o - 1) * s_ + eff - n, 0)
+                pads.append((tot // 2, tot - tot // 2))
+            else:
+                o = max(-(-(n - eff + 1) // s_), 0)
+                pads.append((0, 0))
+            outs.append(o)
+        xp = np.pad(x[..., 0].astype(np.float64), [(0, 0)] + pads)
+        out = np.zeros((x.shape[0],) + tuple(outs), np.float64)
+        for tap in np.ndindex(*ks):
+            sl = tuple(slice(t * d_, t * d_ + (o - 1) * s_ + 1, s_) for t, d_, o, s_ in zip(tap, dl, outs, st))
+            out += np.float64(k[tap + (0, 0)]) * xp[(slice(None),) + sl]
+        return Tensor(out.astype(x.dtype)[..., None])
+    nn = _InertModule('tensorflow.nn')
+    nn.convolution = convolution
+    tf.nn = nn
+
     # tf.math / tf.debugging
     tfmath = _InertModule('tensorflow.math')
 
@@ -320,6 +385,9 @@ def _install_tf():
     dbg.assert_greater_equal = lambda x, y, message=None, **k: _assert(A(x) >= A(y), message)
     dbg.assert_less_equal = lambda x, y, message=None, **k: _assert(A(x) <= A(y), message)
     dbg.assert_all_finite = lambda x, message=None, **k: _assert(np.isfinite(A(x)), message)
+    dbg.assert_equal = lambda x, y, message=None, **k: _assert(np.array_equal(A(T(x)), A(T(y))), message)
+    dbg.assert_non_negative = lambda x, message=None, **k: _assert(A(T(x)) >= 0, message)
+    dbg.assert_greater = lambda x, y, message=None, **k: _assert(A(T(x)) > A(T(y)), message)
     tf.debugging = dbg
 
     compat = _InertModule('tensorflow.compat')
@@ -336,9 +404,17 @@ def _install_tf():
     K.int_shape = lambda x: tuple(A(x).shape)
     K.ndim = lambda x: A(x).ndim
     # reductions: float64 accumulate, one rounding -- TF's reduction order is unspecified
-    K.sum = lambda x, axis=None, keepdims=False: Tensor(np.sum(A(x), axis=axis, keepdims=keepdims, dtype=np.float64).astype(A(x).dtype))
+    _ax = lambda axis: tuple(axis) if isinstance(axis, list) else axis
+    K.sum = lambda x, axis=None, keepdims=False: Tensor(np.sum(A(x), axis=_ax(axis), keepdims=keepdims, dtype=np.float64).astype(A(x).dtype))
     K.mean = lambda x, axis=None, keepdims=False: Tensor(np.mean(A(x), axis=axis, keepdims=keepdims, dtype=np.float64).astype(A(x).dtype))
     K.square = lambda x: Tensor(np.square(A(x)))
+    K.min = lambda x, axis=None, keepdims=False: Tensor(np.min(A(x), axis=axis, keepdims=keepdims))
+    K.max = lambda x, axis=None, keepdims=False: Tensor(np.max(A(x), axis=axis, keepdims=keepdims))
+    K.exp = lambda x: Tensor(np.exp(A(x)))
+    K.log = lambda x: Tensor(np.log(A(x)))
+    K.epsilon = lambda: 1e-7
+    K.flatten = lambda x: Tensor(np.reshape(A(x), -1))
+    K.stack = lambda xs, axis=0: Tensor(np.stack([A(T(v)) for v in xs], axis=axis))
     K.argmax = lambda x, axis=-1: Tensor(np.argmax(A(x), axis=axis).astype(np.int64))
 
     def one_hot(idx, n):
@@ -416,6 +492,8 @@ def _install_tf():
         'tensorflow.errors': errors, 'tensorflow.compat': compat, 'tensorflow.compat.v1': v1,
         'tensorflow.keras': keras, 'tensorflow.keras.backend': K,
         'tensorflow.keras.layers': layers, 'tensorflow.keras.losses': losses,
+        'tensorflow.nn': nn, 'tensorflow.dtypes': dtypes, 'tensorflow.experimental': exp_mod,
+        'tensorflow.experimental.numpy': exp_np,
     }
     sys.modules.update(mods)
 
