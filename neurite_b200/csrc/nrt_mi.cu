@@ -8,7 +8,7 @@
 // read exactly once (8 B per voxel).
 //
 // Tensor-core path: mma.sync m16n8k8 TF32 with the 3-term split
-//     a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi,   a_hi = tf32(a), a_lo = a - a_hi
+//     a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi,   a_hi = top 11 bits of a, a_lo = a - a_hi
 // (relative error 2^-21 per product, far inside the 1e-5 parity tolerance), accumulators
 // flushed into fp32 registers every 128 voxels so tensor-core accumulation rounding cannot
 // build up, block partials combined in fp64 in a fixed order (deterministic results).
@@ -43,15 +43,17 @@ struct MiArgs {
   MiOperand x, y;
   int64_t nv;              // voxels per item
   float neg_alpha;         // -alpha (utils.py:1166)
+  float neg_alpha_log2e;   // -alpha * log2(e): exp(-alpha d^2) = 2^(neg_alpha_log2e * d^2)
   float lo, hi;            // clip (utils.py:1158)
   float* partial;          // [items, nblk, PS]
   int32_t* flag;           // set to 1 if a map value is negative (metrics.py:262-263)
   int nblk;
 };
 
-__device__ __forceinline__ uint32_t to_tf32(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+// 2^x, denormal results flushed to zero (weights below 1e-38 do not matter)
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
@@ -61,33 +63,43 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// values of one operand for one 8-voxel MMA step: bins g + 8r (r < R) x the lane's two voxels
-template <int R, bool Q>
-__device__ __forceinline__ void mi_fetch(const MiOperand& o, const float* item, int64_t v, int64_t vend, int g,
-                                         const float (&cen)[R], const bool (&binok)[R], float neg_alpha, float lo,
-                                         float hi, float (&val)[R][2], bool& negative) {
+// values of one operand for one 8-voxel MMA step: bins g + 8r (r < R) x the lane's two voxels.
+// vp points at the lane's first voxel of the step; `left` = voxels from there to the end of the item
+// (only read when !FULL).
+template <int R, bool Q, bool FULL>
+__device__ __forceinline__ void mi_fetch(const float* vp, int vs, int left, int g, const float (&cen)[R],
+                                         const bool (&binok)[R], float neg_alpha2, bool clip, float lo, float hi,
+                                         float (&val)[R][2], bool& negative) {
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
-    const bool ok = (v + k) < vend;
-    const float* vp = item + (v + k) * o.vox_stride;
+    const bool ok = FULL || k < left;
+    const float* p = vp + k * vs;
     if (Q) {
       // utils.py:1157-1171: exp(-alpha * square(clip(x) - c)).  An out-of-range voxel becomes a
       // huge intensity whose weight underflows to exactly 0 for every bin.
-      const float xv = ok ? fminf(fmaxf(ld_stream_f(vp), lo), hi) : 3.0e38f;
+      float xv = ok ? ld_stream_f(p) : 3.0e38f;
+      if (clip && ok) xv = fminf(fmaxf(xv, lo), hi);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const float d = xv - cen[r];
-        val[r][k] = __expf(neg_alpha * (d * d));
+        val[r][k] = ex2_ftz(neg_alpha2 * (d * d));
       }
     } else {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const float t = (ok && binok[r]) ? ld_stream_f(vp + g + 8 * r) : 0.0f;
+        const float t = (ok && binok[r]) ? ld_stream_f(p + g + 8 * r) : 0.0f;
         negative |= (t < 0.0f);
         val[r][k] = t;
       }
     }
   }
+}
+
+// a = hi + lo with hi = the top 11 significant bits (a valid TF32 operand); the tensor core drops
+// the low 13 bits of lo, leaving a relative error of 2^-22 in the 3-term product
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v) & 0xffffe000u;
+  lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
 // One CTA = 8 warps; warp w of block b takes 8*SPC-voxel chunks b*8+w, +nblk*8, ...
@@ -135,14 +147,27 @@ __global__ void __launch_bounds__(kMiThreads) mi_hist_mma_kernel(const MiArgs a)
 
   bool negative = false;
   const int64_t nq = (a.nv + CH - 1) / CH;
+  const int vsx = (int)a.x.vox_stride, vsy = (int)a.y.vox_stride;
+  const bool clip = a.lo > -INFINITY || a.hi < INFINITY;
   int since_flush = 0;
   for (int64_t q = (int64_t)blockIdx.x * kMiWarps + warp; q < nq; q += (int64_t)gridDim.x * kMiWarps) {
     float av[SPC][RA][2], bv[SPC][RB][2];
+    const int64_t v0 = q * CH + 2 * t;              // the lane's voxel pair of step 0: k = t -> v, k = t + 4 -> v + 1
+    const float* xq = xi + v0 * a.x.vox_stride;
+    const float* yq = yi + v0 * a.y.vox_stride;
+    if ((q + 1) * CH <= a.nv) {                     // warp-uniform: every chunk but the last is full
 #pragma unroll
-    for (int s = 0; s < SPC; ++s) {                 // all loads of the chunk are issued before any use
-      const int64_t v = q * CH + s * 8 + 2 * t;     // the lane's voxel pair: k = t -> v, k = t + 4 -> v + 1
-      mi_fetch<RA, QX>(a.x, xi, v, a.nv, g, cx, okx, a.neg_alpha, a.lo, a.hi, av[s], negative);
-      mi_fetch<RB, QY>(a.y, yi, v, a.nv, g, cy, oky, a.neg_alpha, a.lo, a.hi, bv[s], negative);
+      for (int s = 0; s < SPC; ++s) {               // all loads of the chunk are issued before any use
+        mi_fetch<RA, QX, true>(xq + s * 8 * vsx, vsx, 0, g, cx, okx, a.neg_alpha_log2e, clip, a.lo, a.hi, av[s], negative);
+        mi_fetch<RB, QY, true>(yq + s * 8 * vsy, vsy, 0, g, cy, oky, a.neg_alpha_log2e, clip, a.lo, a.hi, bv[s], negative);
+      }
+    } else {
+      const int left0 = (int)(a.nv - v0);           // may be <= 0
+#pragma unroll
+      for (int s = 0; s < SPC; ++s) {
+        mi_fetch<RA, QX, false>(xq + s * 8 * vsx, vsx, left0 - s * 8, g, cx, okx, a.neg_alpha_log2e, clip, a.lo, a.hi, av[s], negative);
+        mi_fetch<RB, QY, false>(yq + s * 8 * vsy, vsy, left0 - s * 8, g, cy, oky, a.neg_alpha_log2e, clip, a.lo, a.hi, bv[s], negative);
+      }
     }
 #pragma unroll
     for (int s = 0; s < SPC; ++s) {
@@ -152,20 +177,14 @@ __global__ void __launch_bounds__(kMiThreads) mi_hist_mma_kernel(const MiArgs a)
         // fragment order: (row g, k t), (row g+8, k t), (row g, k t+4), (row g+8, k t+4)
         const float f[4] = {av[s][2 * m][0], av[s][2 * m + 1][0], av[s][2 * m][1], av[s][2 * m + 1][1]};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          ah[m][i] = to_tf32(f[i]);
-          al[m][i] = __float_as_uint(f[i] - __uint_as_float(ah[m][i]));
-        }
+        for (int i = 0; i < 4; ++i) split_tf32(f[i], ah[m][i], al[m][i]);
         sx[2 * m] += f[0] + f[2];
         sx[2 * m + 1] += f[1] + f[3];
       }
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          bh[n][i] = to_tf32(bv[s][n][i]);
-          bl[n][i] = __float_as_uint(bv[s][n][i] - __uint_as_float(bh[n][i]));
-        }
+        for (int i = 0; i < 2; ++i) split_tf32(bv[s][n][i], bh[n][i], bl[n][i]);
         sy[n] += bv[s][n][0] + bv[s][n][1];
       }
 #pragma unroll
@@ -497,6 +516,8 @@ int nrt_mi_hist_f32(const float* x, int64_t x_batch_stride, int64_t x_vox_stride
   NRT_REQUIRE(!y_quant || y_centers, NRT_E_ARG, "y_quant needs bin centres");
   NRT_REQUIRE(C == 1 || (x_quant && y_quant), NRT_E_ARG, "channels > 1 only for two quantised operands");
   NRT_REQUIRE(B <= 65535 && C <= 65535, NRT_E_SIZE, "B or C > 65535");
+  NRT_REQUIRE(x_vox_stride >= 1 && y_vox_stride >= 1 && x_vox_stride <= (1 << 20) && y_vox_stride <= (1 << 20),
+              NRT_E_SIZE, "voxel strides outside 1..2^20");
   const int items = B * C;
   NRT_REQUIRE(workspace_bytes >= nrt_mi_workspace_bytes(items, nbx, nby), NRT_E_ARG, "workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -505,6 +526,7 @@ int nrt_mi_hist_f32(const float* x, int64_t x_batch_stride, int64_t x_vox_stride
   a.y = MiOperand{y, y_batch_stride, y_vox_stride, nby, y_quant, y_centers};
   a.nv = nv;
   a.neg_alpha = -alpha;
+  a.neg_alpha_log2e = (float)(-(double)alpha * 1.4426950408889634);
   a.lo = min_clip;
   a.hi = max_clip;
   a.partial = static_cast<float*>(workspace);

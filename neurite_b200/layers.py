@@ -507,6 +507,7 @@ class GaussianBlur(_Layer):
         self.isotropic = isotropic
         self.seed = seed
         self._calls = 0
+        self._kernel_cache = {}
         super().__init__(**kwargs)
 
     def get_config(self):
@@ -539,9 +540,20 @@ class GaussianBlur(_Layer):
     def call(self, x):
         if not any(s > 0 for s in self.sigma):
             return x
+        if not self.random:
+            # fixed SDs: the 1-D kernels are built once per device and stay resident
+            key = (x.device.type, x.device.index)
+            kernel = self._kernel_cache.get(key)
+            if kernel is None:
+                kernel = utils.gaussian_kernel(sigma=self.sigma, separate=True, device=x.device)
+                kernel = kernel if isinstance(kernel, list) else [kernel]
+                self._kernel_cache[key] = kernel
+            # an axis with sigma 0 gets the 1-tap kernel [1.0] (utils.py:628-633): x * 1 == x, skip the pass
+            axes = [i for i, sg in enumerate(self.sigma) if sg > 0]
+            return utils.separable_conv(x, [kernel[i] for i in axes], axis=axes, batched=True)
         seed = None if self.seed is None else self.seed + self._calls       # a fresh draw per call
         self._calls += 1
-        kernel = utils.gaussian_kernel(sigma=self.sigma, random=self.random, min_sigma=self.min_sigma,
+        kernel = utils.gaussian_kernel(sigma=self.sigma, random=True, min_sigma=self.min_sigma,
                                        separate=True, seed=seed)
         kernel = kernel if isinstance(kernel, list) else [kernel]
         return utils.separable_conv(x, kernel, batched=True)

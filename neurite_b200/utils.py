@@ -575,7 +575,10 @@ def separable_conv(x, kernels, axis=None, batched=False, padding='SAME', strides
         s, d = int(s), int(d)
         if s > 1 and d > 1:
             raise ValueError('strides > 1 not supported in conjunction with dilation_rate > 1')
-        kdev = torch.as_tensor(k, dtype=torch.float32).reshape(-1).to(x.device).contiguous()
+        kdev = torch.as_tensor(k, dtype=torch.float32).reshape(-1)
+        if kdev.device != x.device:
+            kdev = kdev.to(x.device)           # (a host kernel costs one small synchronous copy per pass)
+        kdev = kdev.contiguous()
         K, n = kdev.numel(), y.shape[ax + 1]
         if padding.upper() == 'SAME':
             n_out, pb = _same_padding(n, K, s, d)

@@ -179,7 +179,8 @@ def test_separable_conv_golden(ne, name):
         else torch.from_numpy(kw['kernels'])
     out = ne.utils.separable_conv(dev(g['x']), **kw).cpu().numpy()
     assert out.shape == g['out'].shape
-    np.testing.assert_allclose(out, g['out'], rtol=1e-5, atol=1e-6)
+    # random (not normalised) kernels, outputs up to ~20 in magnitude with cancellation: absolute floor 1e-5
+    np.testing.assert_allclose(out, g['out'], rtol=1e-5, atol=1e-5)
 
 
 def test_blur_shapes_kernels_and_paths_vs_oracle(ne, monkeypatch):

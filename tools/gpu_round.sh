@@ -12,7 +12,7 @@ tail -3 gpurun_out/pytest_gpu.log
 ( timeout 300 python bench.py --steps 50 --warmup 5 ) > gpurun_out/bench_warp.json 2> gpurun_out/bench_warp.err; cut -c1-700 gpurun_out/bench_warp.json
 ( timeout 200 python bench.py --steps 50 --warmup 5 --flow smooth --no-cpu-baseline ) > gpurun_out/bench_warp_smooth.json 2>> gpurun_out/bench_warp.err
 ( timeout 200 python bench.py --steps 50 --warmup 5 --method nearest --no-cpu-baseline ) > gpurun_out/bench_warp_nearest.json 2>> gpurun_out/bench_warp.err
-for op in dice cce lc3d resize; do
+for op in dice cce lc3d resize mi mi_segs blur; do
   ( timeout 300 python bench.py --op $op --steps 20 --warmup 3 ) > gpurun_out/bench_$op.json 2> gpurun_out/bench_$op.err
 done
 ( timeout 300 python bench.py --op lc3d --lc-batch 8 --steps 5 --warmup 3 ) > gpurun_out/bench_lc3d_b8.json 2>> gpurun_out/bench_lc3d.err
