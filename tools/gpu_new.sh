@@ -1,11 +1,9 @@
 #!/bin/bash
-# short gpurun visit for the newest kernels: their tests, probe, per-kernel timings, bench lines
 mkdir -p gpurun_out
-( timeout 600 python -m pytest tests/test_gpu_mi_conv.py -m gpu -q --timeout 120 2>&1 | tail -30 ) > gpurun_out/pytest_new.log 2>&1
+( timeout 900 python -m pytest tests/test_gpu_mi_conv.py tests/test_gpu_parity.py -m gpu -q --timeout 180 2>&1 | tail -30 ) > gpurun_out/pytest_new.log 2>&1
 tail -8 gpurun_out/pytest_new.log
-( timeout 60 ./tools/probe/fp32x2_probe ) > gpurun_out/fp32x2_probe.txt 2>&1; cat gpurun_out/fp32x2_probe.txt
-( timeout 600 python tools/bench_new.py ) > gpurun_out/bench_new.txt 2>&1; cat gpurun_out/bench_new.txt
-for op in mi mi_segs blur; do
+( SKIP_MI=1 timeout 600 python tools/bench_new.py ) > gpurun_out/bench_new.txt 2>&1; cat gpurun_out/bench_new.txt
+for op in resize blur; do
   ( timeout 200 python bench.py --op $op --steps 20 --warmup 3 ) > gpurun_out/bench_$op.json 2> gpurun_out/bench_$op.err
   python - <<PY
 import json
