@@ -224,6 +224,26 @@ NRT_API int nrt_mi_hist_f32(const float* x, int64_t x_batch_stride, int64_t x_vo
 /* metrics.py:265-292 on the sums:  pxy = h/(sum h + eps), px = sx/(sum sx + eps), py likewise,
  * mi[item] = sum_ij pxy * log(pxy / (px*py + eps) + eps);  eps = K.epsilon() = 1e-7. */
 NRT_API int nrt_mi_finalize_f32(const float* stats, int items, int nbx, int nby, float eps, float* mi, void* stream);
+/* ---- gradient of the mutual information (TF autodiff through metrics.py:227-292 and
+ * utils.py:1099-1172).  nrt_mi_finalize_bwd_f32: gstats[item] = grad_mi[item] * d mi / d stats[item]
+ * (same [nbx*nby + nbx + nby] layout).  nrt_mi_bwd_f32: one pass over the voxels (operands as in
+ * nrt_mi_hist_f32, bins <= 32) writing grad_x / grad_y in the operands' own layout (either may be
+ * null); for a quantised operand the clip passes the gradient on [min_clip, max_clip].  If
+ * `dcenters` ([2][34] floats) is non-null it receives, per operand, d L / d centre[i] (i < nb)
+ * followed by the number of elements equal to centre[0] and to centre[nb-1]; when the centres are
+ * linspace(min, max) of the tensor, nrt_mi_minmax_bwd_f32 then adds the share of every element equal
+ * to the minimum / maximum to grad_x (TF's reduce_min / reduce_max gradient).  With voxel-range
+ * sharding, sum `dcenters` over the ranks first. */
+NRT_API int nrt_mi_finalize_bwd_f32(const float* stats, const float* grad_mi, int items, int nbx, int nby, float eps,
+                            float* gstats, void* stream);
+NRT_API int64_t nrt_mi_bwd_workspace_bytes(int items);
+NRT_API int nrt_mi_bwd_f32(const float* x, int64_t x_batch_stride, int64_t x_vox_stride, int x_quant, int nbx,
+                   const float* x_centers, const float* y, int64_t y_batch_stride, int64_t y_vox_stride,
+                   int y_quant, int nby, const float* y_centers, int B, int C, int64_t nv, float alpha,
+                   float min_clip, float max_clip, const float* gstats, float* grad_x, float* grad_y,
+                   float* dcenters, void* workspace, int64_t workspace_bytes, void* stream);
+NRT_API int nrt_mi_minmax_bwd_f32(const float* x, int64_t n, const float* minmax, const float* dcenters, int nb,
+                          float* grad_x, void* stream);
 /* out2 = {min(x), max(x)} over n elements (K.min / K.max, utils.py:1151-1152). */
 NRT_API int64_t nrt_minmax_workspace_bytes(void);
 NRT_API int nrt_minmax_f32(const float* x, int64_t n, float* out2, void* workspace, int64_t workspace_bytes, void* stream);

@@ -61,6 +61,13 @@ SIGNATURES = {
                                         ctypes.c_int, ctypes.c_int, c_i64, c_f32, c_f32, c_f32,
                                         c_vp, c_vp, c_vp, c_i64, c_vp]),
     'nrt_mi_finalize_f32': (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f32, c_vp, c_vp]),
+    'nrt_mi_finalize_bwd_f32': (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_f32, c_vp, c_vp]),
+    'nrt_mi_bwd_workspace_bytes': (c_i64, [ctypes.c_int]),
+    'nrt_mi_bwd_f32': (ctypes.c_int, [c_vp, c_i64, c_i64, ctypes.c_int, ctypes.c_int, c_vp,
+                                       c_vp, c_i64, c_i64, ctypes.c_int, ctypes.c_int, c_vp,
+                                       ctypes.c_int, ctypes.c_int, c_i64, c_f32, c_f32, c_f32,
+                                       c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    'nrt_mi_minmax_bwd_f32': (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, ctypes.c_int, c_vp, c_vp]),
     'nrt_minmax_workspace_bytes': (c_i64, []),
     'nrt_minmax_f32': (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     'nrt_mi_bin_centers_f32': (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp]),

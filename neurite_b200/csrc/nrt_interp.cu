@@ -286,7 +286,13 @@ resize3d_kernel(const float* __restrict__ vol, float* __restrict__ out, ResizeGe
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int ox = x0 + lane, oy = y0 + wid;
-  if (ox >= w.M[2] || oy >= w.M[1]) return;
+  // C = 3: a warp's row is 96 contiguous floats; the lanes exchange their 3 channels through
+  // shared memory so that the row leaves as three fully coalesced 128-byte stores instead of
+  // three 12-byte-strided ones (3x fewer L2 write sectors).  All lanes of a row take part, so
+  // lanes past the x end keep running on the zero table entry (offset 0, weights 0).
+  constexpr bool kRowStore = (METHOD == NRT_LINEAR && CT == 3);
+  __shared__ float s_row[kRowStore ? 8 * 96 : 1];
+  if (oy >= w.M[1] || (!kRowStore && ox >= w.M[2])) return;
   const AxisEntry ey = s_ax[TZ + wid], ex = s_ax[TZ + TY + lane];
   const float* volb = vol + (size_t)b * w.src_batch_stride;
   float* outb = out + ((size_t)b * w.out_vox + ((size_t)z0 * w.M[1] + oy) * w.M[2] + ox) * C;
@@ -302,6 +308,7 @@ resize3d_kernel(const float* __restrict__ vol, float* __restrict__ out, ResizeGe
     constexpr int CN = CT > 0 ? CT : 1;
     float lo[4][CN], hi[4][CN];
     int cur0 = -1, cur1 = -1;
+    const int nrow = min(32, w.M[2] - x0) * 3;           // floats of this warp's row that exist (row store)
 #pragma unroll 1
     for (int z = 0; z < TZ; ++z, outb += plane) {
       if (z0 + z >= w.out_n0) break;
@@ -340,6 +347,7 @@ resize3d_kernel(const float* __restrict__ vol, float* __restrict__ out, ResizeGe
       const float w10 = __fmul_rn(ez.whi, ey.wlo), w11 = __fmul_rn(ez.whi, ey.whi);
       const float k0 = __fmul_rn(w00, ex.wlo), k1 = __fmul_rn(w00, ex.whi), k2 = __fmul_rn(w01, ex.wlo), k3 = __fmul_rn(w01, ex.whi);
       const float k4 = __fmul_rn(w10, ex.wlo), k5 = __fmul_rn(w10, ex.whi), k6 = __fmul_rn(w11, ex.wlo), k7 = __fmul_rn(w11, ex.whi);
+      float res[CN];
 #pragma unroll
       for (int c = 0; c < CT; ++c) {
         float r = __fadd_rn(0.f, __fmul_rn(k0, lo[0][c]));
@@ -350,7 +358,24 @@ resize3d_kernel(const float* __restrict__ vol, float* __restrict__ out, ResizeGe
         r = __fadd_rn(r, __fmul_rn(k5, hi[1][c]));
         r = __fadd_rn(r, __fmul_rn(k6, hi[2][c]));
         r = __fadd_rn(r, __fmul_rn(k7, hi[3][c]));
-        outb[c] = r;
+        res[c] = r;
+      }
+      if (kRowStore) {
+        float* so = s_row + wid * 96;
+        so[lane * 3 + 0] = res[0]; so[lane * 3 + 1] = res[1]; so[lane * 3 + 2] = res[2];
+        __syncwarp();
+        float* rowp = outb - lane * 3;                        // first float of the warp's row
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+          if (lane + 32 * m < nrow) st_stream_f(rowp + lane + 32 * m, so[lane + 32 * m]);
+        __syncwarp();
+      } else if (CT == 4) {
+        *reinterpret_cast<float4*>(outb) = make_float4(res[0], res[1], res[2], res[3]);     // 16-byte aligned: 4 floats per voxel
+      } else if (CT == 2) {
+        *reinterpret_cast<float2*>(outb) = make_float2(res[0], res[1]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) outb[c] = res[c];
       }
     }
     return;
@@ -1252,7 +1277,9 @@ int nrt_resize_f32(const float* vol, float* out, int B, const int32_t* in_shape,
         if (method == NRT_LINEAR) resize3d_kernel<NRT_LINEAR, CT><<<(int)grid, 256, 0, st>>>(vol, out, rg, ntz, nty, ntx); \
         else resize3d_kernel<NRT_NEAREST, CT><<<(int)grid, 256, 0, st>>>(vol, out, rg, ntz, nty, ntx);  \
       } while (0)
-      switch (C) {
+      // the C = 2 / 4 kernels store float2 / float4 per voxel: fall back to the run-time-C kernel for an unaligned output
+      const bool al = (reinterpret_cast<uintptr_t>(out) & (C == 4 ? 15u : 7u)) == 0;
+      switch ((C == 2 || C == 4) && !al ? 0 : C) {
         case 1: NRT_RESIZE3D(1); break;
         case 2: NRT_RESIZE3D(2); break;
         case 3: NRT_RESIZE3D(3); break;

@@ -320,6 +320,77 @@ class CategoricalCrossentropy:
         return (total / count)[0]
 
 
+class _MiFn(torch.autograd.Function):
+    """autograd shell of the mutual information of two operands [B, nv, stride]:
+    forward  = (min/max -> centres) + nrt_mi_hist_f32 + nrt_mi_finalize_f32,
+    backward = nrt_mi_finalize_bwd_f32 + nrt_mi_bwd_f32 (+ nrt_mi_minmax_bwd_f32 for the centres)."""
+
+    @staticmethod
+    def forward(ctx, x, y, mi, xq, yq, nbx, nby, B, C, nv):
+        x, y = x.detach(), y.detach()
+        dev = x.device
+        mmx = mi._range(x) if xq else None
+        mmy = mi._range(y) if yq else None
+        cx = mi._centers(x, mmx) if xq else None
+        cy = mi._centers(y, mmy) if yq else None
+        items = B * C
+        stats = torch.empty((items, nbx * nby + nbx + nby), dtype=torch.float32, device=dev)
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws_bytes = lib.nrt_mi_workspace_bytes(items, nbx, nby)
+        ws = _workspace(dev, ws_bytes)
+        with torch.cuda.device(dev):
+            check(lib.nrt_mi_hist_f32(ptr(x), nv * x.shape[-1], x.shape[-1], int(xq), nbx, ptr(cx),
+                                      ptr(y), nv * y.shape[-1], y.shape[-1], int(yq), nby, ptr(cy),
+                                      B, C, nv, float(mi.soft_bin_alpha), float(mi.min_clip),
+                                      float(mi.max_clip), ptr(stats), ptr(flag), ptr(ws), ws_bytes, stream_ptr(dev)))
+        if mi.group is not None:
+            import torch.distributed as dist
+            packed = torch.cat([stats.reshape(-1), flag.to(torch.float32)])
+            dist.all_reduce(packed, group=mi.group)
+            stats, flag = packed[:-1].reshape(stats.shape).contiguous(), (packed[-1:] > 0).to(torch.int32)
+        if not (xq and yq) and int(flag.item()) != 0:            # only map operands can be negative
+            raise InvalidArgumentError('Condition x >= 0 did not hold element-wise')
+        out = torch.empty(items, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.nrt_mi_finalize_f32(ptr(stats), items, nbx, nby, 1e-7, ptr(out), stream_ptr(dev)))
+        ctx.save_for_backward(x, y, cx, cy, mmx, mmy, stats)
+        ctx.cfg = (mi, xq, yq, nbx, nby, B, C, nv)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, cx, cy, mmx, mmy, stats = ctx.saved_tensors
+        mi, xq, yq, nbx, nby, B, C, nv = ctx.cfg
+        dev = x.device
+        items = B * C
+        g = g.contiguous().to(torch.float32)
+        gstats = torch.empty_like(stats)
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+        if gx is None and gy is None:
+            return (None,) * 10
+        # the centres move with the data only when they come from the tensor's min / max
+        need_dc = (xq and mmx is not None and gx is not None) or (yq and mmy is not None and gy is not None)
+        dcen = torch.zeros((2, 34), dtype=torch.float32, device=dev) if need_dc else None
+        wsb = lib.nrt_mi_bwd_workspace_bytes(items) if need_dc else 0
+        ws = _workspace(dev, wsb) if need_dc else None
+        with torch.cuda.device(dev):
+            check(lib.nrt_mi_finalize_bwd_f32(ptr(stats), ptr(g), items, nbx, nby, 1e-7, ptr(gstats), stream_ptr(dev)))
+            check(lib.nrt_mi_bwd_f32(ptr(x), nv * x.shape[-1], x.shape[-1], int(xq), nbx, ptr(cx),
+                                     ptr(y), nv * y.shape[-1], y.shape[-1], int(yq), nby, ptr(cy),
+                                     B, C, nv, float(mi.soft_bin_alpha), float(mi.min_clip), float(mi.max_clip),
+                                     ptr(gstats), ptr(gx), ptr(gy), ptr(dcen), ptr(ws), wsb, stream_ptr(dev)))
+            if need_dc:
+                if mi.group is not None:
+                    import torch.distributed as dist
+                    dist.all_reduce(dcen, group=mi.group)
+                if xq and mmx is not None and gx is not None:
+                    check(lib.nrt_mi_minmax_bwd_f32(ptr(x), x.numel(), ptr(mmx), ptr(dcen[0]), nbx, ptr(gx), stream_ptr(dev)))
+                if yq and mmy is not None and gy is not None:
+                    check(lib.nrt_mi_minmax_bwd_f32(ptr(y), y.numel(), ptr(mmy), ptr(dcen[1]), nby, ptr(gy), stream_ptr(dev)))
+        return (gx, gy) + (None,) * 8
+
+
 # ---------------------------------------------------------------------------------------
 # MutualInformation (reference metrics.py:41-336)
 # ---------------------------------------------------------------------------------------
@@ -333,7 +404,8 @@ class MutualInformation:
     tensor cores.  Differences from the reference, both where the reference cannot run at all:
     explicit `bin_centers` work here (the reference's `_soft_sim_map` passes both `bin_centers` and
     `nb_bins` to soft_quantize, which asserts -- metrics.py:329-331 vs utils.py:1141-1143), and the
-    constructor does not print alpha (metrics.py:114).  No gradient yet (forward metric only).
+    constructor does not print alpha (metrics.py:114).  Differentiable (nrt_mi_bwd_f32), including the
+    path through the data-dependent bin centres (min / max of the tensor), like TF autodiff.
 
     `group`: torch.distributed group over which every item's voxel range is sharded; the bin range
     (min/max) and the [nb*nb + 2 nb] sums are all-reduced before the finalise kernel.
@@ -363,39 +435,21 @@ class MutualInformation:
         self.group = group
 
     # -- helpers ---------------------------------------------------------------------------
-    def _centers(self, x32):
+    def _range(self, x32):
+        """device [min, max] of the whole tensor (over every rank's shard with `group`), or None
+        when the bin centres are explicit."""
+        from . import utils
+        return None if self.bin_centers is not None else utils.minmax(x32, self.group)
+
+    def _centers(self, x32, mm=None):
         from . import utils
         if self.bin_centers is not None:
             return torch.as_tensor(self.bin_centers, device=x32.device)
-        return utils.bin_centers_from_range(utils.minmax(x32, self.group), self.nb_bins)
+        return utils.bin_centers_from_range(self._range(x32) if mm is None else mm, self.nb_bins)
 
-    def _stats_to_mi(self, stats, flag, items, nbx, nby, check_flag):
-        if self.group is not None:
-            import torch.distributed as dist
-            packed = torch.cat([stats.reshape(-1), flag.to(torch.float32)])
-            dist.all_reduce(packed, group=self.group)
-            stats, flag = packed[:-1].reshape(stats.shape).contiguous(), (packed[-1:] > 0).to(torch.int32)
-        if check_flag and int(flag.item()) != 0:                 # only map operands can be negative
-            raise InvalidArgumentError('Condition x >= 0 did not hold element-wise')
-        mi = torch.empty(items, dtype=torch.float32, device=stats.device)
-        with torch.cuda.device(stats.device):
-            check(lib.nrt_mi_finalize_f32(ptr(stats), items, nbx, nby, 1e-7, ptr(mi), stream_ptr(stats.device)))
-        return mi
-
-    def _hist(self, x, xq, nbx, cx, y, yq, nby, cy, B, C, nv):
-        """x, y: contiguous fp32 [B, nv, stride]; *q = quantise flag, c* = centres or None."""
-        items = B * C
-        stats = torch.empty((items, nbx * nby + nbx + nby), dtype=torch.float32, device=x.device)
-        flag = torch.zeros(1, dtype=torch.int32, device=x.device)
-        ws_bytes = lib.nrt_mi_workspace_bytes(items, nbx, nby)
-        ws = _workspace(x.device, ws_bytes)
-        with torch.cuda.device(x.device):
-            check(lib.nrt_mi_hist_f32(ptr(x), nv * x.shape[-1], x.shape[-1], int(xq), nbx, ptr(cx),
-                                      ptr(y), nv * y.shape[-1], y.shape[-1], int(yq), nby, ptr(cy),
-                                      B, C, nv, float(self.soft_bin_alpha), float(self.min_clip),
-                                      float(self.max_clip), ptr(stats), ptr(flag), ptr(ws), ws_bytes,
-                                      stream_ptr(x.device)))
-        return self._stats_to_mi(stats, flag, items, nbx, nby, not (xq and yq))
+    def _hist(self, x, xq, nbx, y, yq, nby, B, C, nv):
+        """x, y: contiguous fp32 [B, nv, stride]; *q = soft-quantise that operand."""
+        return _MiFn.apply(x, y, self, bool(xq), bool(yq), int(nbx), int(nby), int(B), int(C), int(nv))
 
     @staticmethod
     def _bvc(t):
@@ -426,7 +480,7 @@ class MutualInformation:
         if tuple(vol.shape[:-1]) + (nb,) != tuple(seg.shape):
             raise InvalidArgumentError('shapes %s and %s differ' % (tuple(vol.shape[:-1]) + (nb,), tuple(seg.shape)))
         v, s = self._bvc(vol), self._bvc(seg)
-        return self._hist(v, True, nb, self._centers(v), s, False, s.shape[-1], None, v.shape[0], 1, v.shape[1])
+        return self._hist(v, True, nb, s, False, s.shape[-1], v.shape[0], 1, v.shape[1])
 
     def channelwise(self, x, y):
         """MI(x[..., i], y[..., i]) for every batch item and channel: [bs, ..., C] -> [bs, C]
@@ -437,7 +491,7 @@ class MutualInformation:
         xv, yv = self._bvc(x), self._bvc(y)
         B, nv, C = xv.shape
         nb = int(self.nb_bins)
-        mi = self._hist(xv, True, nb, self._centers(xv), yv, True, nb, self._centers(yv), B, C, nv)
+        mi = self._hist(xv, True, nb, yv, True, nb, B, C, nv)
         return mi.reshape(B, C)
 
     def maps(self, x, y):
@@ -447,7 +501,7 @@ class MutualInformation:
             raise InvalidArgumentError('shapes %s and %s differ' % (tuple(x.shape), tuple(y.shape)))
         xv, yv = self._bvc(x), self._bvc(y)
         B, nv, nb = xv.shape
-        return self._hist(xv, False, nb, None, yv, False, nb, None, B, 1, nv)
+        return self._hist(xv, False, nb, yv, False, nb, B, 1, nv)
 
     def _soft_log_sim_map(self, x):
         from . import utils

@@ -132,3 +132,54 @@ class MutualInformation:
         pxpy_eps = pxpy + EPS
         log_term = np.log(pxy / pxpy_eps + EPS)                                     # :290
         return np.sum(pxy * log_term, axis=(1, 2), dtype=np.float64).astype(F32)    # :291
+
+
+# ---------------------------------------------------------------------------------------
+# differentiable float64 restatement (torch autograd on the CPU): the gradient oracle.
+# TF differentiates the same graph -- clip_by_value passes the gradient on the closed interval,
+# reduce_min / reduce_max send it to the extremal elements (shared evenly among ties), and the
+# linspace centres carry it to min and max.
+# ---------------------------------------------------------------------------------------
+def torch_soft_quantize(x, nb_bins=None, alpha=1.0, min_clip=-np.inf, max_clip=np.inf, bin_centers=None):
+    import torch
+    if bin_centers is None:
+        mn, mx = x.min(), x.max()
+        i = torch.arange(nb_bins, dtype=x.dtype)
+        centers = mn + (mx - mn) / (nb_bins - 1) * i if nb_bins > 1 else mn.reshape(1)
+    else:
+        centers = torch.as_tensor(np.asarray(bin_centers), dtype=x.dtype)
+    xc = torch.clamp(x[..., None], min_clip, max_clip)
+    return torch.exp(-alpha * (xc - centers) ** 2)
+
+
+def torch_maps(x, y):
+    import torch
+    eps = 1e-7
+    x = x.reshape(x.shape[0], -1, x.shape[-1])
+    y = y.reshape(y.shape[0], -1, y.shape[-1])
+    pxy = torch.einsum('bvi,bvj->bij', x, y)
+    pxy = pxy / (pxy.sum(dim=(1, 2), keepdim=True) + eps)
+    px = x.sum(1, keepdim=True)
+    px = px / (px.sum(2, keepdim=True) + eps)
+    py = y.sum(1, keepdim=True)
+    py = py / (py.sum(2, keepdim=True) + eps)
+    pxpy = px.transpose(1, 2) * py
+    return (pxy * torch.log(pxy / (pxpy + eps) + eps)).sum(dim=(1, 2))
+
+
+def torch_channelwise(x, y, nb_bins=16, alpha=None, min_clip=-np.inf, max_clip=np.inf, bin_centers=None):
+    """x, y: torch float64 [bs, ..., C] -> [bs, C] (metrics.py:185-225)."""
+    import torch
+    if alpha is None:
+        alpha = float(default_alpha(nb_bins, bin_centers))
+    x = x.reshape(x.shape[0], -1, x.shape[-1])
+    y = y.reshape(y.shape[0], -1, y.shape[-1])
+    cxq = torch_soft_quantize(x.permute(2, 0, 1), nb_bins, alpha, min_clip, max_clip, bin_centers)   # [C, bs, V, B]
+    cyq = torch_soft_quantize(y.permute(2, 0, 1), nb_bins, alpha, min_clip, max_clip, bin_centers)
+    return torch.stack([torch_maps(a, b) for a, b in zip(cxq, cyq)], 0).T
+
+
+def torch_volume_seg(vol, seg, nb_bins=16, alpha=None, min_clip=-np.inf, max_clip=np.inf):
+    if alpha is None:
+        alpha = float(default_alpha(nb_bins, None))
+    return torch_maps(torch_soft_quantize(vol[..., 0], nb_bins, alpha, min_clip, max_clip), seg)

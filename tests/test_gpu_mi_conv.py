@@ -262,3 +262,78 @@ def test_subsample_vs_oracle(ne):
                for i in range(x.shape[ax])) for ax in (1, 2, 3)]
     assert any(hit)
     assert ne.layers.Subsample(stride_max=1)(dev(x)).shape == x.shape
+
+
+# ------------------------------------------------------------------ MutualInformation gradients
+def _grad_close(got, ref, rtol=2e-4):
+    """gradients are compared relative to the largest reference entry (they span many decades)."""
+    got, ref = got.detach().cpu().double().numpy(), ref.detach().double().numpy()
+    scale = np.abs(ref).max()
+    assert scale > 0
+    np.testing.assert_allclose(got / scale, ref / scale, rtol=0, atol=rtol)
+
+
+@pytest.mark.parametrize('nb,clip', [(16, None), (11, (0.1, 0.85)), (32, None)])
+def test_mi_channelwise_gradient_vs_torch_autograd(ne, nb, clip):
+    rng = np.random.default_rng(100 + nb)
+    x = rng.uniform(0, 1, (2, 6, 7, 9, 2)).astype(F32)
+    y = np.clip(0.6 * x ** 2 + 0.2 + 0.1 * rng.standard_normal(x.shape), 0, 1).astype(F32)
+    w = rng.standard_normal((2, 2))
+    kw = dict(nb_bins=nb)
+    tkw = dict(nb_bins=nb)
+    if clip:
+        kw.update(min_clip=clip[0], max_clip=clip[1])
+        tkw.update(min_clip=clip[0], max_clip=clip[1])
+    xg, yg = dev(x).requires_grad_(True), dev(y).requires_grad_(True)
+    m = ne.metrics.MutualInformation(**kw)
+    out = m.channelwise(xg, yg)
+    (out * dev(w.astype(F32))).sum().backward()
+    xt, yt = torch.from_numpy(x).double().requires_grad_(True), torch.from_numpy(y).double().requires_grad_(True)
+    ref = omi.torch_channelwise(xt, yt, alpha=float(m.soft_bin_alpha), **tkw)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), **MI_TOL)
+    (ref * torch.from_numpy(w)).sum().backward()
+    _grad_close(xg.grad, xt.grad)
+    _grad_close(yg.grad, yt.grad)
+    # the extremal voxels carry the bin-centre path: they must agree too (largest |grad| is often there)
+    for gpu, cpu, src in ((xg.grad, xt.grad, x), (yg.grad, yt.grad, y)):
+        for idx in (np.argmin(src), np.argmax(src)):
+            a, b = float(gpu.flatten()[idx]), float(cpu.flatten()[idx])
+            assert abs(a - b) <= 2e-4 * float(cpu.abs().max()) + 1e-9
+
+
+def test_mi_volumes_explicit_centers_and_one_sided_gradient(ne):
+    rng = np.random.default_rng(7)
+    x = rng.uniform(0, 1, (3, 400, 1)).astype(F32)
+    y = np.clip(x + 0.2 * rng.standard_normal(x.shape), 0, 1).astype(F32)
+    centers = np.linspace(0, 1, 12).astype(F32)
+    m = ne.metrics.MutualInformation(bin_centers=centers, soft_bin_alpha=40.0)
+    xg = dev(x).requires_grad_(True)
+    m.volumes(xg, dev(y)).sum().backward()                     # only x needs a gradient
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    omi.torch_channelwise(xt, torch.from_numpy(y).double(), nb_bins=None, alpha=40.0, bin_centers=centers).sum().backward()
+    _grad_close(xg.grad, xt.grad)
+
+
+def test_mi_segs_and_volume_seg_gradient(ne):
+    rng = np.random.default_rng(8)
+    L = 16
+    lx = rng.standard_normal((2, 5, 6, 7, L)).astype(F32)
+    px = (np.exp(lx) / np.exp(lx).sum(-1, keepdims=True)).astype(F32)
+    py = (0.5 * np.roll(px, 1, -1) + 0.5 * px).astype(F32)
+    w = torch.tensor([0.7, -1.3])
+    a, b = dev(px).requires_grad_(True), dev(py).requires_grad_(True)
+    (ne.metrics.MutualInformation().segs(a, b) * w.cuda().float()).sum().backward()
+    at, bt = torch.from_numpy(px).double().requires_grad_(True), torch.from_numpy(py).double().requires_grad_(True)
+    (omi.torch_maps(at, bt) * w.double()).sum().backward()
+    _grad_close(a.grad, at.grad)
+    _grad_close(b.grad, bt.grad)
+    vol = rng.uniform(0, 1, (2, 5, 6, 7, 1)).astype(F32)
+    m = ne.metrics.MutualInformation(nb_bins=L)
+    for order in (0, 1):
+        v, s = dev(vol).requires_grad_(True), dev(px).requires_grad_(True)
+        out = m.volume_seg(v, s) if order == 0 else m.volume_seg(s, v)
+        (out * w.cuda().float()).sum().backward()
+        vt, st = torch.from_numpy(vol).double().requires_grad_(True), torch.from_numpy(px).double().requires_grad_(True)
+        (omi.torch_volume_seg(vt, st, nb_bins=L, alpha=float(m.soft_bin_alpha)) * w.double()).sum().backward()
+        _grad_close(v.grad, vt.grad)
+        _grad_close(s.grad, st.grad)

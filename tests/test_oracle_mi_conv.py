@@ -159,3 +159,17 @@ def test_subsample_indices_properties():
             assert np.all(np.diff(ind) >= 0) and ind[0] == 0 and ind[-1] == width - 1
             assert len(np.unique(ind)) == int(F32(width) / F32(thick) + F32(0.5))
     np.testing.assert_array_equal(conv.subsample_indices(9, 1.0), np.arange(9))
+
+
+def test_torch_gradient_oracle_matches_numpy_forward():
+    """the float64 torch restatement used as the gradient oracle computes the same forward values."""
+    import torch
+    g = load_golden('mi_channelwise_c3')
+    out = omi.torch_channelwise(torch.from_numpy(g['x']).double(), torch.from_numpy(g['y']).double())
+    np.testing.assert_allclose(out.numpy(), g['mi'], rtol=2e-5, atol=2e-6)
+    g = load_golden('mi_volume_seg')
+    out = omi.torch_volume_seg(torch.from_numpy(g['vol']).double(), torch.from_numpy(g['seg']).double())
+    np.testing.assert_allclose(out.numpy(), g['mi_vs'], rtol=2e-5, atol=2e-6)
+    g = load_golden('mi_segs_L5')
+    out = omi.torch_maps(torch.from_numpy(g['x']).double(), torch.from_numpy(g['y']).double())
+    np.testing.assert_allclose(out.numpy(), g['mi'], rtol=2e-5, atol=2e-6)
