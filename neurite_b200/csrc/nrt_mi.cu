@@ -104,8 +104,8 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 
 // One CTA = 8 warps; warp w of block b takes 8*SPC-voxel chunks b*8+w, +nblk*8, ...
 // grid = (nblk, channels, items)
-template <int MT, int NT, bool QX, bool QY, int SPC>
-__global__ void __launch_bounds__(kMiThreads) mi_hist_mma_kernel(const MiArgs a) {
+template <int MT, int NT, bool QX, bool QY, int SPC, int MINB = 1>
+__global__ void __launch_bounds__(kMiThreads, MINB) mi_hist_mma_kernel(const MiArgs a) {
   constexpr int RA = 2 * MT;      // A rows per lane (bins g + 8r)
   constexpr int RB = NT;          // B columns per lane
   constexpr int NBX = 16 * MT, NBY = 8 * NT;
@@ -475,15 +475,21 @@ __global__ void soft_quantize_kernel(const float* x, int64_t n, const float* cen
 }
 
 template <int MT, int NT, int SPCQ, int SPCM>
-void launch_mma(const MiArgs& a, dim3 grid, cudaStream_t st) {
-  if (a.x.quant && a.y.quant) mi_hist_mma_kernel<MT, NT, true, true, SPCQ><<<grid, kMiThreads, 0, st>>>(a);
-  else if (a.x.quant) mi_hist_mma_kernel<MT, NT, true, false, SPCM><<<grid, kMiThreads, 0, st>>>(a);
+void launch_mma(const MiArgs& a, dim3 grid, cudaStream_t st, int variant) {
+  if (a.x.quant && a.y.quant) {
+    // NRT_MI_VARIANT (dev switch): 1 = 2 steps per chunk and 3 CTAs per SM, 2 = 4 steps and 3 CTAs per SM
+    if (variant == 1) mi_hist_mma_kernel<MT, NT, true, true, 2, 3><<<grid, kMiThreads, 0, st>>>(a);
+    else if (variant == 2) mi_hist_mma_kernel<MT, NT, true, true, SPCQ, 3><<<grid, kMiThreads, 0, st>>>(a);
+    else mi_hist_mma_kernel<MT, NT, true, true, SPCQ><<<grid, kMiThreads, 0, st>>>(a);
+  } else if (a.x.quant) mi_hist_mma_kernel<MT, NT, true, false, SPCM><<<grid, kMiThreads, 0, st>>>(a);
   else if (a.y.quant) mi_hist_mma_kernel<MT, NT, false, true, SPCM><<<grid, kMiThreads, 0, st>>>(a);
   else mi_hist_mma_kernel<MT, NT, false, false, SPCM><<<grid, kMiThreads, 0, st>>>(a);
 }
 
 int mi_blocks(int64_t nv, int items) {
-  int64_t want = ((int64_t)sm_count() * 4 + items - 1) / items;          // ~4 CTAs per SM in total
+  const char* be = getenv("NRT_MI_CTAS_PER_SM");
+  const int per_sm = be ? atoi(be) : 4;
+  int64_t want = ((int64_t)sm_count() * (per_sm > 0 ? per_sm : 4) + items - 1) / items;          // ~4 CTAs per SM in total
   int64_t cap = (nv + 1023) / 1024;                                      // >= 1024 voxels per CTA
   int64_t n = want < cap ? want : cap;
   if (n < 1) n = 1;
@@ -534,15 +540,17 @@ int nrt_mi_hist_f32(const float* x, int64_t x_batch_stride, int64_t x_vox_stride
   const int nblk = mi_blocks(nv, items);
   a.nblk = nblk;
   dim3 grid(nblk, C, B);
+  const char* venv = getenv("NRT_MI_VARIANT");
+  const int variant = venv ? atoi(venv) : 0;
   const char* env = getenv("NRT_MI_GENERIC");
   // alpha <= 0 would turn the padded bins' exp(-alpha * inf) into NaN: no padding in the generic kernel
   const bool generic = (env && atoi(env) != 0) || nbx > 32 || nby > 32 || !(alpha > 0.f);
   if (generic) {
     mi_hist_generic_kernel<<<grid, kMiThreads, 0, st>>>(a);
   } else if (nbx <= 16 && nby <= 16) {
-    launch_mma<1, 2, 4, 4>(a, grid, st);
+    launch_mma<1, 2, 4, 4>(a, grid, st, variant);
   } else {
-    launch_mma<2, 4, 2, 2>(a, grid, st);
+    launch_mma<2, 4, 2, 2>(a, grid, st, 0);
   }
   int rc = check_launch("mi_hist kernel");
   if (rc != NRT_OK) return rc;

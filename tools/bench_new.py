@@ -59,9 +59,25 @@ if not os.environ.get('SKIP_MI'):
                                       float(mm.soft_bin_alpha), float('-inf'), float('inf'), ptr(stats), ptr(flag), ptr(ws), wsb,
                                       stream_ptr(dev)))
         report('  hist+combine quant/quant nb=%d (tensor cores)' % nb, timeit(hist), 8 * B * V)
-        os.environ['NRT_MI_GENERIC'] = '1'
-        report('  hist+combine quant/quant nb=%d (CUDA cores)' % nb, timeit(hist, 3), 8 * B * V)
-        del os.environ['NRT_MI_GENERIC']
+        if nb == 16:
+            for var in (1, 2):
+                os.environ['NRT_MI_VARIANT'] = str(var)
+                report('    variant %d' % var, timeit(hist), 8 * B * V)
+            del os.environ['NRT_MI_VARIANT']
+            for per_sm in (2, 8):
+                os.environ['NRT_MI_CTAS_PER_SM'] = str(per_sm)
+                report('    %d CTAs per SM' % per_sm, timeit(hist), 8 * B * V)
+            del os.environ['NRT_MI_CTAS_PER_SM']
+    xg, yg = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    out = m.volumes(xg, yg)
+    go = torch.ones_like(out)
+
+    def bwd():
+        xg.grad = None
+        yg.grad = None
+        out.backward(go, retain_graph=True)
+    report('mi.volumes backward (gx + gy), B=8', timeit(bwd, 5), 16 * B * V)
+    del xg, yg, out
     del x, y, xv, yv
     for L, Bm in ((16, 2), (32, 1)):
         px = torch.softmax(torch.randn((Bm,) + S + (L,), device=dev), -1)
