@@ -173,10 +173,12 @@ __global__ void __launch_bounds__(256) sepconv_row_kernel(const ConvArgs a) {
   const int64_t rowlen = a.L * a.inner, total = a.outer * rowlen;
   const int64_t p0 = (int64_t)blockIdx.x * kRowTP;
   for (int j = threadIdx.x; j < a.K; j += 256) ks[j] = a.k[j];
-  for (int e = threadIdx.x; e < kRowTP + halo; e += 256) {
-    const int64_t p = p0 - before + e;
-    sm[e] = (p >= 0 && p < total) ? ld_stream_f(a.x + p) : 0.f;
-  }
+  // stage [p0 - before, p0 + kRowTP + halo - before): 32-bit indices relative to one 64-bit base
+  const float* src = a.x + (p0 - before);
+  const int e_lo = p0 >= before ? 0 : (int)(before - p0);                                   // first staged element inside the tensor
+  const int64_t e_end = total - p0 + before;
+  const int e_hi = e_end < (int64_t)(kRowTP + halo) ? (int)e_end : kRowTP + halo;           // one past the last
+  for (int e = threadIdx.x; e < kRowTP + halo; e += 256) sm[e] = (e >= e_lo && e < e_hi) ? ld_stream_f(src + e) : 0.f;
   __syncthreads();
   // warp w owns local positions [256 w, 256 w + 256): lane + 32 u, u < 8 (conflict-free shared loads, one
   // tap weight per 8 FMAs).  The main loop ignores row ends; the few outputs within a kernel radius of a
@@ -194,9 +196,12 @@ __global__ void __launch_bounds__(256) sepconv_row_kernel(const ConvArgs a) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) acc[u] = fmaf(kj, base[u * 32 + j * sp], acc[u]);
   }
+  const int64_t left = total - p0 - wbase - lane;       // outputs from this lane's first one to the end of the tensor
+  const int nleft = left > 256 ? 256 : (int)left;       // (may be <= 0)
+  float* op = a.out + p0 + wbase + lane;
+  const int step = 32 % rl;                             // orow advances by 32 (mod rowlen) per u
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
-    const int64_t p = p0 + wbase + lane + u * 32;
     const bool interior = (orow >= before) && (orow - before + halo < rl);
     float r = acc[u];
     if (!interior) {
@@ -207,9 +212,9 @@ __global__ void __launch_bounds__(256) sepconv_row_kernel(const ConvArgs a) {
         if ((unsigned)t < (unsigned)rl) r = fmaf(ks[j], base[u * 32 + j * sp], r);
       }
     }
-    if (p < total) st_stream_f(a.out + p, r);
-    orow += 32;
-    while (orow >= rl) orow -= rl;
+    if (u * 32 < nleft) st_stream_f(op + u * 32, r);
+    orow += step;
+    if (orow >= rl) orow -= rl;
   }
 }
 

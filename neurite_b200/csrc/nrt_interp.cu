@@ -1273,8 +1273,10 @@ int nrt_resize_f32(const float* vol, float* out, int B, const int32_t* in_shape,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (D == 3 && in_vox * C <= 0x7fffffffLL && getenv("NRT_RESIZE_GENERIC") == nullptr) {
     const char* tze = getenv("NRT_RESIZE_TZ");
-    int TZ = tze ? atoi(tze) : 8;
-    if (TZ != 16 && TZ != 32) TZ = 8;
+    // planes per CTA: 32 measured best on B200 (0.261 ms vs 0.318 at 8 for Resize(2) of [8,80,96,112,3]); short
+    // slabs take fewer so that the grid keeps a few waves
+    int TZ = tze ? atoi(tze) : (out_n0 >= 64 ? 32 : (out_n0 >= 24 ? 16 : 8));
+    if (TZ != 16 && TZ != 32 && TZ != 64) TZ = 8;
     if (method != NRT_LINEAR || C < 1 || C > 4) TZ = 8;          // the marching path is linear, C = 1..4
     const int ntz = (out_n0 + TZ - 1) / TZ, nty = (rg.M[1] + 7) / 8, ntx = (rg.M[2] + 31) / 32;
     const int64_t grid = (int64_t)B * ntz * nty * ntx;
@@ -1284,6 +1286,7 @@ int nrt_resize_f32(const float* vol, float* out, int B, const int32_t* in_shape,
         if (method != NRT_LINEAR) resize3d_kernel<NRT_NEAREST, CT><<<(int)grid, 256, 0, st>>>(vol, out, rg, ntz, nty, ntx);  \
         else if (TZ == 16) resize3d_kernel<NRT_LINEAR, CT, 16><<<(int)grid, 256, 0, st>>>(vol, out, rg, ntz, nty, ntx);     \
         else if (TZ == 32) resize3d_kernel<NRT_LINEAR, CT, 32><<<(int)grid, 256, 0, st>>>(vol, out, rg, ntz, nty, ntx);     \
+        else if (TZ == 64) resize3d_kernel<NRT_LINEAR, CT, 64><<<(int)grid, 256, 0, st>>>(vol, out, rg, ntz, nty, ntx);     \
         else resize3d_kernel<NRT_LINEAR, CT><<<(int)grid, 256, 0, st>>>(vol, out, rg, ntz, nty, ntx); \
       } while (0)
       // the C = 2 / 4 kernels store float2 / float4 per voxel: fall back to the run-time-C kernel for an unaligned output

@@ -150,54 +150,37 @@ __global__ void __launch_bounds__(kMiThreads, MINB) mi_hist_mma_kernel(const MiA
   const int vsx = (int)a.x.vox_stride, vsy = (int)a.y.vox_stride;
   const bool clip = a.lo > -INFINITY || a.hi < INFINITY;
   int since_flush = 0;
-  for (int64_t q = (int64_t)blockIdx.x * kMiWarps + warp; q < nq; q += (int64_t)gridDim.x * kMiWarps) {
-    float av[SPC][RA][2], bv[SPC][RB][2];
-    const int64_t v0 = q * CH + 2 * t;              // the lane's voxel pair of step 0: k = t -> v, k = t + 4 -> v + 1
-    const float* xq = xi + v0 * a.x.vox_stride;
-    const float* yq = yi + v0 * a.y.vox_stride;
-    if ((q + 1) * CH <= a.nv) {                     // warp-uniform: every chunk but the last is full
+
+  // one 8-voxel MMA step on the lane's weights: marginal sums, 3xTF32 split, 3 MMAs per output tile
+  auto mma_step = [&](const float (&avs)[RA][2], const float (&bvs)[RB][2]) {
+    uint32_t ah[MT][4], al[MT][4], bh[NT][2], bl[NT][2];
 #pragma unroll
-      for (int s = 0; s < SPC; ++s) {               // all loads of the chunk are issued before any use
-        mi_fetch<RA, QX, true>(xq + s * 8 * vsx, vsx, 0, g, cx, okx, a.neg_alpha_log2e, clip, a.lo, a.hi, av[s], negative);
-        mi_fetch<RB, QY, true>(yq + s * 8 * vsy, vsy, 0, g, cy, oky, a.neg_alpha_log2e, clip, a.lo, a.hi, bv[s], negative);
-      }
-    } else {
-      const int left0 = (int)(a.nv - v0);           // may be <= 0
+    for (int m = 0; m < MT; ++m) {
+      // fragment order: (row g, k t), (row g+8, k t), (row g, k t+4), (row g+8, k t+4)
+      const float f[4] = {avs[2 * m][0], avs[2 * m + 1][0], avs[2 * m][1], avs[2 * m + 1][1]};
 #pragma unroll
-      for (int s = 0; s < SPC; ++s) {
-        mi_fetch<RA, QX, false>(xq + s * 8 * vsx, vsx, left0 - s * 8, g, cx, okx, a.neg_alpha_log2e, clip, a.lo, a.hi, av[s], negative);
-        mi_fetch<RB, QY, false>(yq + s * 8 * vsy, vsy, left0 - s * 8, g, cy, oky, a.neg_alpha_log2e, clip, a.lo, a.hi, bv[s], negative);
-      }
+      for (int i = 0; i < 4; ++i) split_tf32(f[i], ah[m][i], al[m][i]);
+      sx[2 * m] += f[0] + f[2];
+      sx[2 * m + 1] += f[1] + f[3];
     }
 #pragma unroll
-    for (int s = 0; s < SPC; ++s) {
-      uint32_t ah[MT][4], al[MT][4], bh[NT][2], bl[NT][2];
+    for (int n = 0; n < NT; ++n) {
 #pragma unroll
-      for (int m = 0; m < MT; ++m) {
-        // fragment order: (row g, k t), (row g+8, k t), (row g, k t+4), (row g+8, k t+4)
-        const float f[4] = {av[s][2 * m][0], av[s][2 * m + 1][0], av[s][2 * m][1], av[s][2 * m + 1][1]};
+      for (int i = 0; i < 2; ++i) split_tf32(bvs[n][i], bh[n][i], bl[n][i]);
+      sy[n] += bvs[n][0] + bvs[n][1];
+    }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) split_tf32(f[i], ah[m][i], al[m][i]);
-        sx[2 * m] += f[0] + f[2];
-        sx[2 * m + 1] += f[1] + f[3];
-      }
+    for (int m = 0; m < MT; ++m)
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) split_tf32(bv[s][n][i], bh[n][i], bl[n][i]);
-        sy[n] += bv[s][n][0] + bv[s][n][1];
+        mma_tf32(acc[m][n], al[m], bh[n]);
+        mma_tf32(acc[m][n], ah[m], bl[n]);
+        mma_tf32(acc[m][n], ah[m], bh[n]);
       }
-#pragma unroll
-      for (int m = 0; m < MT; ++m)
-#pragma unroll
-        for (int n = 0; n < NT; ++n) {
-          mma_tf32(acc[m][n], al[m], bh[n]);
-          mma_tf32(acc[m][n], ah[m], bl[n]);
-          mma_tf32(acc[m][n], ah[m], bh[n]);
-        }
-    }
+  };
+  auto flush_if_due = [&]() {
     since_flush += SPC;
-    if (since_flush >= 16) {                       // 128 voxels per tensor-core accumulation run
+    if (since_flush >= 16) {                         // 128 voxels per tensor-core accumulation run
       since_flush = 0;
 #pragma unroll
       for (int m = 0; m < MT; ++m)
@@ -208,6 +191,105 @@ __global__ void __launch_bounds__(kMiThreads, MINB) mi_hist_mma_kernel(const MiA
             tot[m][n][i] += acc[m][n][i];
             acc[m][n][i] = 0.f;
           }
+    }
+  };
+
+  const int64_t qstride = (int64_t)gridDim.x * kMiWarps;
+  if constexpr (QX && QY) {
+    // Two intensity images: only 2 + 2 floats per lane and step come from memory.  The raw values
+    // of the NEXT chunk are loaded before the current chunk's 32 exponentials and 24 MMAs are
+    // issued, so the global-load latency hides behind a full chunk of arithmetic.
+    auto load_raw = [&](int64_t q, float (&xo)[SPC][2], float (&yo)[SPC][2]) {
+      const int64_t v0 = q * CH + 2 * t;            // the lane's voxel pair of step 0: k = t -> v, k = t + 4 -> v + 1
+      const float* xq = xi + v0 * a.x.vox_stride;
+      const float* yq = yi + v0 * a.y.vox_stride;
+      if ((q + 1) * CH <= a.nv) {                   // warp-uniform: every chunk but the last is full
+#pragma unroll
+        for (int s = 0; s < SPC; ++s)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            xo[s][k] = ld_stream_f(xq + (s * 8 + k) * vsx);
+            yo[s][k] = ld_stream_f(yq + (s * 8 + k) * vsy);
+          }
+        if (clip) {
+#pragma unroll
+          for (int s = 0; s < SPC; ++s)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              xo[s][k] = fminf(fmaxf(xo[s][k], a.lo), a.hi);
+              yo[s][k] = fminf(fmaxf(yo[s][k], a.lo), a.hi);
+            }
+        }
+      } else {
+        // an out-of-range voxel becomes a huge intensity whose weight underflows to exactly 0
+        const int left0 = (int)(a.nv - v0);         // may be <= 0
+#pragma unroll
+        for (int s = 0; s < SPC; ++s)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const bool ok = s * 8 + k < left0;
+            xo[s][k] = ok ? fminf(fmaxf(ld_stream_f(xq + (s * 8 + k) * vsx), a.lo), a.hi) : 3.0e38f;
+            yo[s][k] = ok ? fminf(fmaxf(ld_stream_f(yq + (s * 8 + k) * vsy), a.lo), a.hi) : 3.0e38f;
+          }
+      }
+    };
+    float xr[SPC][2], yr[SPC][2];
+    int64_t q = (int64_t)blockIdx.x * kMiWarps + warp;
+    if (q < nq) load_raw(q, xr, yr);
+    for (; q < nq; q += qstride) {
+      float xn[SPC][2], yn[SPC][2];
+      const bool more = q + qstride < nq;
+      if (more) load_raw(q + qstride, xn, yn);
+#pragma unroll
+      for (int s = 0; s < SPC; ++s) {
+        float avs[RA][2], bvs[RB][2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          // utils.py:1157-1171: exp(-alpha * square(clip(x) - c)); padded bins have c = +inf -> weight 0
+#pragma unroll
+          for (int r = 0; r < RA; ++r) {
+            const float d = xr[s][k] - cx[r];
+            avs[r][k] = ex2_ftz(a.neg_alpha_log2e * (d * d));
+          }
+#pragma unroll
+          for (int r = 0; r < RB; ++r) {
+            const float d = yr[s][k] - cy[r];
+            bvs[r][k] = ex2_ftz(a.neg_alpha_log2e * (d * d));
+          }
+        }
+        mma_step(avs, bvs);
+      }
+      flush_if_due();
+      if (more) {
+#pragma unroll
+        for (int s = 0; s < SPC; ++s)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) { xr[s][k] = xn[s][k]; yr[s][k] = yn[s][k]; }
+      }
+    }
+  } else {
+    for (int64_t q = (int64_t)blockIdx.x * kMiWarps + warp; q < nq; q += qstride) {
+      float av[SPC][RA][2], bv[SPC][RB][2];
+      const int64_t v0 = q * CH + 2 * t;
+      const float* xq = xi + v0 * a.x.vox_stride;
+      const float* yq = yi + v0 * a.y.vox_stride;
+      if ((q + 1) * CH <= a.nv) {
+#pragma unroll
+        for (int s = 0; s < SPC; ++s) {             // all loads of the chunk are issued before any use
+          mi_fetch<RA, QX, true>(xq + s * 8 * vsx, vsx, 0, g, cx, okx, a.neg_alpha_log2e, clip, a.lo, a.hi, av[s], negative);
+          mi_fetch<RB, QY, true>(yq + s * 8 * vsy, vsy, 0, g, cy, oky, a.neg_alpha_log2e, clip, a.lo, a.hi, bv[s], negative);
+        }
+      } else {
+        const int left0 = (int)(a.nv - v0);
+#pragma unroll
+        for (int s = 0; s < SPC; ++s) {
+          mi_fetch<RA, QX, false>(xq + s * 8 * vsx, vsx, left0 - s * 8, g, cx, okx, a.neg_alpha_log2e, clip, a.lo, a.hi, av[s], negative);
+          mi_fetch<RB, QY, false>(yq + s * 8 * vsy, vsy, left0 - s * 8, g, cy, oky, a.neg_alpha_log2e, clip, a.lo, a.hi, bv[s], negative);
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < SPC; ++s) mma_step(av[s], bv[s]);
+      flush_if_due();
     }
   }
 #pragma unroll
@@ -477,10 +559,10 @@ __global__ void soft_quantize_kernel(const float* x, int64_t n, const float* cen
 template <int MT, int NT, int SPCQ, int SPCM>
 void launch_mma(const MiArgs& a, dim3 grid, cudaStream_t st, int variant) {
   if (a.x.quant && a.y.quant) {
-    // NRT_MI_VARIANT (dev switch): 1 = 2 steps per chunk and 3 CTAs per SM, 2 = 4 steps and 3 CTAs per SM
+    // 3 CTAs per SM (<= 80 registers, no spills).  NRT_MI_VARIANT (dev switch): 1 = 2 steps per chunk, 2 = 2 CTAs per SM
     if (variant == 1) mi_hist_mma_kernel<MT, NT, true, true, 2, 3><<<grid, kMiThreads, 0, st>>>(a);
-    else if (variant == 2) mi_hist_mma_kernel<MT, NT, true, true, SPCQ, 3><<<grid, kMiThreads, 0, st>>>(a);
-    else mi_hist_mma_kernel<MT, NT, true, true, SPCQ><<<grid, kMiThreads, 0, st>>>(a);
+    else if (variant == 2) mi_hist_mma_kernel<MT, NT, true, true, SPCQ, 2><<<grid, kMiThreads, 0, st>>>(a);
+    else mi_hist_mma_kernel<MT, NT, true, true, SPCQ, 3><<<grid, kMiThreads, 0, st>>>(a);
   } else if (a.x.quant) mi_hist_mma_kernel<MT, NT, true, false, SPCM><<<grid, kMiThreads, 0, st>>>(a);
   else if (a.y.quant) mi_hist_mma_kernel<MT, NT, false, true, SPCM><<<grid, kMiThreads, 0, st>>>(a);
   else mi_hist_mma_kernel<MT, NT, false, false, SPCM><<<grid, kMiThreads, 0, st>>>(a);
@@ -550,7 +632,7 @@ int nrt_mi_hist_f32(const float* x, int64_t x_batch_stride, int64_t x_vox_stride
   } else if (nbx <= 16 && nby <= 16) {
     launch_mma<1, 2, 4, 4>(a, grid, st, variant);
   } else {
-    launch_mma<2, 4, 2, 2>(a, grid, st, 0);
+    launch_mma<2, 4, 2, 2>(a, grid, st, 2);          // 32 x 32 bins: 64 accumulators, 2 CTAs per SM
   }
   int rc = check_launch("mi_hist kernel");
   if (rc != NRT_OK) return rc;
