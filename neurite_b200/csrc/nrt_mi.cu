@@ -559,10 +559,12 @@ __global__ void soft_quantize_kernel(const float* x, int64_t n, const float* cen
 template <int MT, int NT, int SPCQ, int SPCM>
 void launch_mma(const MiArgs& a, dim3 grid, cudaStream_t st, int variant) {
   if (a.x.quant && a.y.quant) {
-    // 3 CTAs per SM (<= 80 registers, no spills).  NRT_MI_VARIANT (dev switch): 1 = 2 steps per chunk, 2 = 2 CTAs per SM
+    // 2 CTAs per SM measured best (1.02 ms vs 1.18 ms at 3 CTAs per SM for 8 volume pairs: the MUFU and
+    // tensor pipes are the limit, more resident warps only add contention).  NRT_MI_VARIANT (dev switch):
+    // 1 = 2 steps per chunk at 3 CTAs per SM, 2 = 4 steps at 3 CTAs per SM
     if (variant == 1) mi_hist_mma_kernel<MT, NT, true, true, 2, 3><<<grid, kMiThreads, 0, st>>>(a);
-    else if (variant == 2) mi_hist_mma_kernel<MT, NT, true, true, SPCQ, 2><<<grid, kMiThreads, 0, st>>>(a);
-    else mi_hist_mma_kernel<MT, NT, true, true, SPCQ, 3><<<grid, kMiThreads, 0, st>>>(a);
+    else if (variant == 2) mi_hist_mma_kernel<MT, NT, true, true, SPCQ, 3><<<grid, kMiThreads, 0, st>>>(a);
+    else mi_hist_mma_kernel<MT, NT, true, true, SPCQ, 2><<<grid, kMiThreads, 0, st>>>(a);
   } else if (a.x.quant) mi_hist_mma_kernel<MT, NT, true, false, SPCM><<<grid, kMiThreads, 0, st>>>(a);
   else if (a.y.quant) mi_hist_mma_kernel<MT, NT, false, true, SPCM><<<grid, kMiThreads, 0, st>>>(a);
   else mi_hist_mma_kernel<MT, NT, false, false, SPCM><<<grid, kMiThreads, 0, st>>>(a);
@@ -632,7 +634,7 @@ int nrt_mi_hist_f32(const float* x, int64_t x_batch_stride, int64_t x_vox_stride
   } else if (nbx <= 16 && nby <= 16) {
     launch_mma<1, 2, 4, 4>(a, grid, st, variant);
   } else {
-    launch_mma<2, 4, 2, 2>(a, grid, st, 2);          // 32 x 32 bins: 64 accumulators, 2 CTAs per SM
+    launch_mma<2, 4, 2, 2>(a, grid, st, 0);          // 32 x 32 bins: 64 accumulators, 2 CTAs per SM
   }
   int rc = check_launch("mi_hist kernel");
   if (rc != NRT_OK) return rc;
