@@ -395,7 +395,7 @@ def bench_resize(args):
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': 'Resize(2) on [%d,80,96,112,3] (reference models.py:803-804)' % B},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': peak_src, 'bytes_model': '4C/z^3 + 4C per output voxel', 'per': 'GPU'},
+                         'traffic': ncu_traffic('resize'), 'peak_source': peak_src, 'bytes_model': '4C/z^3 + 4C per output voxel', 'per': 'GPU'},
             'gpu_launches': args.steps, 'clocks': clocks}), flush=True)
     finish(world)
 
@@ -434,7 +434,7 @@ def bench_mi(args, segs=False):
                                    'min/max + histogram + combine + finalise kernels per step'
                                    % ('segs, 16 labels' if segs else 'volumes', B)},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': peak_src,
+                         'traffic': ncu_traffic('mi_segs' if segs else 'mi'), 'peak_source': peak_src,
                          'bytes_model': '%d B/voxel (two fp32 %s read once; the quantised [V,16] maps never exist)'
                                         % (per_voxel, 'maps' if segs else 'volumes'),
                          'kernel': kern, 'per': 'GPU',
@@ -467,7 +467,7 @@ def bench_blur(args):
             'config': {'workload': 'GaussianBlur(sigma=%g) on [%d,160,192,224,1] (reference layers.py:251-364): '
                                    'three separable passes' % (args.sigma, B)},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': peak_src,
+                         'traffic': ncu_traffic('blur'), 'peak_source': peak_src,
                          'bytes_model': '8 B/voxel for the whole blur (read once, write once); the three-pass '
                                         'implementation moves 24 B/voxel, so 0.33 is its ceiling',
                          'kernel': 'sepconv_col_kernel x2 + sepconv_row_kernel', 'per': 'GPU'},

@@ -570,7 +570,7 @@ struct BoxBounds { int lo_z, hi_z, lo_y, hi_y, lo_x, hi_x; };
 // clamped (legal, meaningless) address and is recorded in `slow`; it is recomputed through
 // global memory after the loop.  Without a divergent branch in the body the compiler can
 // overlap the LDS latency of one iteration with the multiply/add chain of the previous one.
-template <int TZ, int TY, int HALO, int NW, int METHOD, int U, bool EZ, bool EY, bool EX, int CC>
+template <int TZ, int TY, int HALO, int NW, int METHOD, int U, bool EZ, bool EY, bool EX, int CC, bool ABS>
 __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, const float* __restrict__ s_box,
                                           const float* __restrict__ volb, float* __restrict__ outb,
                                           const TileGeo& w, int x0, int y0, int z0l, int ox, int oy, int oz,
@@ -586,7 +586,7 @@ __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, cons
   const int gz0 = w.out_z0 + z0l;
   const int gx = x0 + lane;
   // with absolute locations the grid term is 0 (0 + x == x exactly): same instruction count
-  const float fx = w.abs_loc ? 0.f : (float)gx;
+  const float fx = ABS ? 0.f : (float)gx;
   BoxBounds bb;
   bb.lo_z = max(oz, g.src_z0); bb.hi_z = min(oz + BZ - 1, g.src_z0 + g.src_n0 - 1);
   bb.lo_y = max(oy, 0); bb.hi_y = min(oy + BY - 1, H - 1);
@@ -597,9 +597,9 @@ __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, cons
     const int yy = (NW >= TY ? wid % TY : wid) + yr * NW;
     const int gy = y0 + yy;
     if (partial && (gx >= W || gy >= H)) continue;
-    const float fy = w.abs_loc ? 0.f : (float)gy;
-    float zf = w.abs_loc ? 0.f : (float)(gz0 + zs);                 // running z coordinate (exact small integers)
-    const float zstep = w.abs_loc ? 0.f : (float)ZSTEP;
+    const float fy = ABS ? 0.f : (float)gy;
+    float zf = ABS ? 0.f : (float)(gz0 + zs);                 // running z coordinate (exact small integers)
+    const float zstep = ABS ? 0.f : (float)ZSTEP;
     const float* fl = s_flow + ((zs * TY + yy) * TX + lane) * 3;
     float* op = outb + (((size_t)(z0l + zs) * H + gy) * W + gx) * CC;
     unsigned slow = 0;
@@ -661,7 +661,7 @@ __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, cons
       slow &= slow - 1;
       const int z = zs + it * ZSTEP;
       const float* f2 = fl0 + (size_t)it * ZSTEP * TY * TX * 3;
-      const float lz = __fadd_rn(w.abs_loc ? 0.f : (float)(gz0 + z), f2[0]);
+      const float lz = __fadd_rn(ABS ? 0.f : (float)(gz0 + z), f2[0]);
       const float ly = __fadd_rn(fy, f2[1]);
       const float lx = __fadd_rn(fx, f2[2]);
       float res[CC];
@@ -677,7 +677,7 @@ __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, cons
 
 // Process one staged tile.  Warp w owns row y = w % TY of planes z = w / TY, + NW/TY, ...
 // The per-axis EDGE flags are tile-uniform, so the dispatch below costs one uniform switch.
-template <int TZ, int TY, int HALO, int NW, int METHOD, int U = 2, int CC = 1>
+template <int TZ, int TY, int HALO, int NW, int METHOD, int U = 2, int CC = 1, bool ABS = false>
 __device__ __forceinline__ void compute_tile(const float* __restrict__ s_flow, const float* __restrict__ s_box,
                                              const float* __restrict__ volb, float* __restrict__ outb,
                                              const TileGeo& w, int x0, int y0, int z0l, int ox, int oy, int oz) {
@@ -688,7 +688,7 @@ __device__ __forceinline__ void compute_tile(const float* __restrict__ s_flow, c
   const bool ey = !((oy >= 0) && (oy + Cfg::BY <= g.S[1]));
   const bool ex = !((ox >= 0) && (ox + Cfg::BX <= g.S[2]));
   const bool partial = (z0l + TZ > w.out_n0) || (y0 + TY > g.S[1]) || (x0 + Cfg::TX > g.S[2]);
-#define NRT_ROWS(a, b, c) tile_rows<TZ, TY, HALO, NW, METHOD, U, a, b, c, CC>(s_flow, s_box, volb, outb, w, x0, y0, z0l, ox, oy, oz, partial)
+#define NRT_ROWS(a, b, c) tile_rows<TZ, TY, HALO, NW, METHOD, U, a, b, c, CC, ABS>(s_flow, s_box, volb, outb, w, x0, y0, z0l, ox, oy, oz, partial)
   switch ((ez ? 4 : 0) | (ey ? 2 : 0) | (ex ? 1 : 0)) {
     case 0: NRT_ROWS(false, false, false); break;
     case 1: NRT_ROWS(false, false, true); break;
@@ -705,7 +705,9 @@ __device__ __forceinline__ void compute_tile(const float* __restrict__ s_flow, c
 // v1: one tile per CTA, several CTAs per SM overlap each other's load phase.  3-D grid
 // (x tiles, y tiles, z tiles * batch) keeps the per-CTA prologue free of div/mod chains:
 // with only 8-16 voxels per thread the prologue is a visible part of the instruction count.
-template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8, int CC = 1>
+// ABS = the 'flow' tensor holds absolute sample locations (interpn on the volume's own grid): compile-time, so
+// that the displacement kernels carry no trace of it
+template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8, int CC = 1, bool ABS = false>
 __global__ void __launch_bounds__(NW * 32)
 warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
                    const __grid_constant__ CUtensorMap tm_flow,
@@ -745,7 +747,7 @@ warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
         const int cx = min(x0 + (jx * (Cfg::TX - 1)) / 2, w.g.S[2] - 1);
         const float* f = flow + ((((size_t)b * w.out_n0 + cz) * w.g.S[1] + cy) * w.g.S[2] + cx) * 3;
         const float lim = 1048576.f;
-        const float gz_ = w.abs_loc ? (float)(w.out_z0 + cz) : 0.f, gy_ = w.abs_loc ? (float)cy : 0.f, gx_ = w.abs_loc ? (float)cx : 0.f;
+        const float gz_ = ABS ? (float)(w.out_z0 + cz) : 0.f, gy_ = ABS ? (float)cy : 0.f, gx_ = ABS ? (float)cx : 0.f;
         mz = fminf(fmaxf(__ldg(f + 0) - gz_, -lim), lim);
         my = fminf(fmaxf(__ldg(f + 1) - gy_, -lim), lim);
         mx = fminf(fmaxf(__ldg(f + 2) - gx_, -lim), lim);
@@ -776,7 +778,7 @@ warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
     }
     mbar_wait(bar, 1);
   }
-  compute_tile<TZ, TY, HALO, NW, METHOD, U, CC>(s_flow, s_box, vol + (size_t)b * w.src_batch_stride,
+  compute_tile<TZ, TY, HALO, NW, METHOD, U, CC, ABS>(s_flow, s_box, vol + (size_t)b * w.src_batch_stride,
                                                 out + (size_t)b * w.out_vox * CC, w, x0, y0, z0l, ox, oy, oz);
 }
 
@@ -1029,7 +1031,7 @@ int warp3d_bwd_tile(const float* vol, const float* flow, const float* gout, floa
   return check_launch("warp3d_bwd_tile_kernel");
 }
 
-template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8, int CC = 1>
+template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8, int CC = 1, bool ABS = false>
 static int launch_tile(const float* vol, const float* flow, float* out, TileGeo tg, int H, int W, int src_n0,
                        int out_n0, cudaStream_t st) {
   using Cfg = TileCfg<TZ, TY, HALO, CC>;
@@ -1046,7 +1048,7 @@ static int launch_tile(const float* vol, const float* flow, float* out, TileGeo 
   if (rc != NRT_OK) return rc;
   rc = encode_f32_4d(&tmf, flow, fd, fb);
   if (rc != NRT_OK) return rc;
-  auto kern = warp3d_tile_kernel<TZ, TY, HALO, METHOD, U, NW, CC>;
+  auto kern = warp3d_tile_kernel<TZ, TY, HALO, METHOD, U, NW, CC, ABS>;
   // set on every launch: the attribute is per device and the call costs ~1 us of host time
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM) != cudaSuccess)
     return check_launch("cudaFuncSetAttribute(warp3d_tile)");
@@ -1132,6 +1134,19 @@ static int try_tile_path(const float* vol, const float* flow, float* out, int B,
   tg.src_batch_stride = (int64_t)src_n0 * H * W;
   tg.out_vox = (int64_t)out_n0 * H * W;
   int rc = 1;
+  if (abs_loc) {
+    // absolute locations: instantiated for the default tile shapes only (other shapes: generic gather kernel)
+#define NRT_TILE_ABS(cc, tz)                                                                                 \
+    if (C == (cc))                                                                                           \
+      rc = method == NRT_LINEAR                                                                              \
+               ? launch_tile<tz, 8, 3, NRT_LINEAR, 2, 8, cc, true>(vol, flow, out, tg, H, W, src_n0, out_n0, st)   \
+               : launch_tile<tz, 8, 3, NRT_NEAREST, 2, 8, cc, true>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
+    NRT_TILE_ABS(1, 8) NRT_TILE_ABS(2, 4) NRT_TILE_ABS(3, 4) NRT_TILE_ABS(4, 4)
+#undef NRT_TILE_ABS
+    if (rc == 1) return NRT_OK;
+    *used = true;
+    return rc;
+  }
   if (C > 1) {
     // 2-4 channels: (x, channel) is one contiguous TMA dimension; 4x8x32 tiles keep the
     // staged box (22 KB per channel) small enough for two CTAs per SM
