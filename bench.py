@@ -444,7 +444,8 @@ def bench_mi(args, segs=False):
 
 
 def bench_blur(args):
-    """GaussianBlur(sigma=1) (7 taps per axis) of B single-channel 160x192x224 volumes."""
+    """GaussianBlur(sigma=1) (7 taps per axis) of B single-channel 160x192x224 volumes: one fused kernel
+    (NRT_BLUR_FUSED=0: the three separable passes)."""
     import torch
     import neurite_b200 as ne
     world, rank, local = dist_setup(args.gpus)
@@ -458,20 +459,22 @@ def bench_blur(args):
     clocks = sampler.stop()
     peak, peak_src = measured_peak()
     achieved = 8.0 * B * V * args.steps / (ms * 1e-3) / 1e9
+    fused = os.environ.get('NRT_BLUR_FUSED', '1') != '0' and round(args.sigma * 3) * 2 + 1 <= 15
     if rank == 0:
         print(json.dumps({
             'metric': 'voxels/s, GaussianBlur(sigma=%g), 160x192x224 fp32' % args.sigma,
             'value': world * B * V * args.steps / (ms * 1e-3), 'unit': 'voxels/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'GaussianBlur(sigma=%g) on [%d,160,192,224,1] (reference layers.py:251-364): '
-                                   'three separable passes' % (args.sigma, B)},
+            'config': {'workload': 'GaussianBlur(sigma=%g) on [%d,160,192,224,1] (reference layers.py:251-364): %s'
+                                   % (args.sigma, B, 'one fused kernel' if fused else 'three separable passes')},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': ncu_traffic('blur'), 'peak_source': peak_src,
-                         'bytes_model': '8 B/voxel for the whole blur (read once, write once); the three-pass '
-                                        'implementation moves 24 B/voxel, so 0.33 is its ceiling',
-                         'kernel': 'sepconv_col_kernel x2 + sepconv_row_kernel', 'per': 'GPU'},
-            'gpu_launches': args.steps * 3, 'clocks': clocks}), flush=True)
+                         'traffic': ncu_traffic('blur_fused' if fused else 'blur'), 'peak_source': peak_src,
+                         'bytes_model': '8 B/voxel for the whole blur (read once, write once)'
+                                        + ('' if fused else '; the three-pass path moves 24 B/voxel, so 0.33 is its ceiling'),
+                         'kernel': 'blur3d_fused_kernel' if fused else 'sepconv_col4_kernel x2 + sepconv_row_kernel',
+                         'per': 'GPU'},
+            'gpu_launches': args.steps * (1 if fused else 3), 'clocks': clocks}), flush=True)
     finish(world)
 
 

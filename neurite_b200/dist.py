@@ -158,3 +158,30 @@ def resize_slab(vol, zoom_factor, interp_method='linear', group=None):
     m0 = int(vol.shape[1] * zoom_factor[0])
     z0, nz = slab_bounds(m0, world, rank)
     return utils._resize_batched(vol, list(zoom_factor), interp_method, out_z0=z0, out_n0=nz)
+
+
+def blur_slab(x_slab, sigma, full_s0, group=None, blur_fn=None):
+    """GaussianBlur of ONE volume sharded in z-slabs: x_slab = this rank's planes [B, nz_r, *rest, C].
+
+    The blur along axis 0 needs round(3 sigma_0) planes beyond the slab on either side
+    (utils.gaussian_kernel's window, reference utils.py:633); they come from the neighbours
+    (`exchange_halo`).  The extended slab is blurred with zero 'SAME' padding -- right at the
+    true ends of the volume, wrong only inside the halo planes, which are cropped.
+    `blur_fn(x, sigma)` defaults to layers.GaussianBlur (injectable so the exchange-and-crop logic
+    is testable on the CPU with the oracle's blur)."""
+    import numpy as np
+    nd_sp = x_slab.dim() - 2
+    sig = np.ravel(sigma).tolist()
+    sig = sig * nd_sp if len(sig) == 1 else sig
+    halo = int(np.round(max(sig[0], np.finfo(np.float32).eps) * 3))
+    if blur_fn is None:
+        from . import layers
+        lay = layers.GaussianBlur(sigma=sig)
+        blur_fn = lambda t, s: lay(t)                      # noqa: E731
+    if halo == 0 or dist.get_world_size(group) == 1:
+        return blur_fn(x_slab, sig)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    z0, nz = slab_bounds(full_s0, world, rank)
+    ext, src_z0 = exchange_halo(x_slab, halo, full_s0, group)
+    out = blur_fn(ext, sig)
+    return out[:, z0 - src_z0:z0 - src_z0 + nz].contiguous()

@@ -77,3 +77,35 @@ def test_halo_exchange_and_gather_gloo(world, full_s0, halo):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(r, True) for r in range(world)]
+
+
+def _blur_worker(rank, world, port, full_s0, sigma, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from oracle import conv as oconv
+        g = torch.Generator().manual_seed(1)
+        full = torch.randn(2, full_s0, 6, 7, 2, generator=g)
+        z0, nz = nd.slab_bounds(full_s0, world, rank)
+        blur = lambda t, s: torch.from_numpy(oconv.gaussian_blur(t.numpy(), s))      # noqa: E731
+        part = nd.blur_slab(full[:, z0:z0 + nz].contiguous(), sigma, full_s0, blur_fn=blur)
+        whole = blur(full, sigma if isinstance(sigma, list) else [sigma] * 3)
+        q.put((rank, bool(torch.allclose(part, whole[:, z0:z0 + nz], rtol=0, atol=1e-6))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,full_s0,sigma', [(2, 12, 1.0), (3, 20, [1.5, 0.0, 0.7]), (2, 9, [0.0, 1.0, 1.0])])
+def test_blur_slab_exchange_and_crop_gloo(world, full_s0, sigma):
+    """z-slab GaussianBlur = halo exchange + blur + crop; checked with the oracle's blur on CPU tensors."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_blur_worker, args=(r, world, port, full_s0, sigma, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(30)
+    assert all(ok for _, ok in res), res

@@ -61,9 +61,94 @@ def _worker(rank, world, port, q):
         full = ne.layers.Resize(2)(x)
         z0, nz = nd.slab_bounds(full.shape[1], world, rank)
         ok = ok and torch.equal(nd.resize_slab(x, 2), full[:, z0:z0 + nz])
+        ok = ok and _mi_and_blur_sharded(ne, nd, dist, dev, S, g, world, rank)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
+
+
+def _mi_and_blur_sharded(ne, nd, dist, dev, S, g, world, rank, with_blur=True):
+    """MutualInformation with the voxel range sharded (bins from the all-reduced min/max, one all-reduce of
+    the sums, gradient incl. the min/max path) and the z-slab GaussianBlur must equal the unsharded results."""
+    ok = True
+    x = torch.rand((2,) + S + (1,), generator=g).to(dev)
+    y = (0.7 * x * x + 0.1 + 0.1 * torch.rand((2,) + S + (1,), generator=g).to(dev)).clamp_(0, 1)
+    z0, nz = nd.slab_bounds(S[0], world, rank)
+    xw, yw = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    ref = ne.metrics.MutualInformation(nb_bins=16).volumes(xw, yw)
+    ref.sum().backward()
+    xs = x[:, z0:z0 + nz].contiguous().requires_grad_(True)
+    ys = y[:, z0:z0 + nz].contiguous().requires_grad_(True)
+    sh = ne.metrics.MutualInformation(nb_bins=16, group=dist.group.WORLD).volumes(xs, ys)
+    ok = ok and bool(torch.allclose(sh, ref, rtol=1e-5, atol=2e-6))
+    sh.sum().backward()
+    scale = float(xw.grad.abs().max())
+    ok = ok and bool((xs.grad - xw.grad[:, z0:z0 + nz]).abs().max() <= 2e-4 * scale)
+    ok = ok and bool((ys.grad - yw.grad[:, z0:z0 + nz]).abs().max() <= 2e-4 * float(yw.grad.abs().max()))
+    # probability maps: segs
+    L = 16
+    p1 = torch.softmax(torch.randn((2,) + S + (L,), generator=g), -1).to(dev)
+    p2 = torch.softmax(torch.randn((2,) + S + (L,), generator=g), -1).to(dev)
+    ref = ne.metrics.MutualInformation().segs(p1, p2)
+    sh = ne.metrics.MutualInformation(group=dist.group.WORLD).segs(p1[:, z0:z0 + nz].contiguous(), p2[:, z0:z0 + nz].contiguous())
+    ok = ok and bool(torch.allclose(sh, ref, rtol=1e-5, atol=2e-6))
+    if with_blur:
+        v = torch.randn((2,) + S + (2,), generator=g).to(dev)
+        whole = ne.layers.GaussianBlur(sigma=[1.5, 1.0, 0.5])(v)
+        part = nd.blur_slab(v[:, z0:z0 + nz].contiguous(), [1.5, 1.0, 0.5], S[0])
+        ok = ok and bool(torch.allclose(part, whole[:, z0:z0 + nz], rtol=0, atol=1e-5))
+    return ok
+
+
+def _one_gpu_worker(rank, world, port, q):
+    """two ranks sharing cuda:0 over gloo: the sharding logic of the all-reduce based ops without a second GPU."""
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import neurite_b200 as ne
+        from neurite_b200 import dist as nd
+        dev = torch.device('cuda', 0)
+        try:
+            probe = torch.ones(4, device=dev)
+            dist.all_reduce(probe)
+            dist.all_reduce(probe, op=dist.ReduceOp.MIN)
+        except RuntimeError as ex:                      # this gloo build cannot reduce CUDA tensors
+            q.put((rank, 'skip: %s' % str(ex)[:80]))
+            return
+        g = torch.Generator().manual_seed(0)
+        S = (24, 16, 32)
+        ok = _mi_and_blur_sharded(ne, nd, dist, dev, S, g, world, rank, with_blur=False)
+        L = 16
+        lab = torch.randint(0, L, (2,) + S, generator=g)
+        t = torch.nn.functional.one_hot(lab, L).float().to(dev)
+        p = torch.softmax(torch.randn((2,) + S + (L,), generator=g), -1).to(dev)
+        z0, nz = nd.slab_bounds(S[0], world, rank)
+        sh = ne.losses.Dice(group=dist.group.WORLD).loss(t[:, z0:z0 + nz].contiguous(), p[:, z0:z0 + nz].contiguous())
+        ok = ok and bool(torch.allclose(sh, ne.losses.Dice().loss(t, p), rtol=1e-6, atol=1e-7))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_voxel_range_sharding_two_ranks_on_one_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_one_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+    if any(isinstance(v, str) for _, v in res):
+        pytest.skip(str(res))
+    assert all(v is True for _, v in res), res
 
 
 @pytest.mark.parametrize('world', [2, 4, 8])
