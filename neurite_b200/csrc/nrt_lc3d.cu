@@ -70,7 +70,10 @@ __device__ __forceinline__ int64_t patch_origin(const LcGeo& g, int64_t p) {
 constexpr int kLcMaxWarps = 7;              // consumer groups (<= ring slots - 1) + 1 producer warp
 constexpr int kLcMaxStages = 8;
 
-template <int BB, int WPP>
+// P2: the 4 x BB accumulators are updated with packed fma.rn.f32x2 (two fused multiply-adds per issue slot on
+// sm_100): the weight pairs are the halves of the LDS.128 result, the input value is broadcast to both halves.
+// Bit-identical to the scalar chain (the same fused operation per accumulator).
+template <int BB, int WPP, bool P2 = false>
 __global__ void __launch_bounds__((kLcMaxWarps * WPP + 1) * 32, 1)
 lc3d_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel,
                    const float* __restrict__ bias, float* __restrict__ out, LcGeo g, int b_base,
@@ -134,8 +137,9 @@ lc3d_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel
     const uint32_t ph = (uint32_t)((k / stages) & 1);
     const float* xp = x + (int64_t)b0 * g.x_batch + patch_origin(g, g.p0 + n);
     float acc[BB][4];
+    unsigned long long acc2[BB][2];                           // P2: (acc0, acc1), (acc2, acc3) as packed pairs
 #pragma unroll
-    for (int b = 0; b < BB; ++b) { acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.f; }
+    for (int b = 0; b < BB; ++b) { acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.f; acc2[b][0] = acc2[b][1] = 0ull; }
     const float4* w4 = reinterpret_cast<const float4*>(smem_raw + (size_t)slot * blk_stride);
     for (int i0 = 0; i0 < iters; i0 += CH) {
       float xv[CH][BB];
@@ -150,14 +154,28 @@ lc3d_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         const int i = lane + ((i0 + c) << 5);
-        if (i < n4) {
-          const float4 wv = w4[i];
+        {
+          // past the end of the block the weights are zero (no branch: the packed accumulators stay in place)
+          const float4 wv = (i < n4) ? w4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (P2) {
+            unsigned long long w01, w23;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(w01) : "f"(wv.x), "f"(wv.y));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(w23) : "f"(wv.z), "f"(wv.w));
 #pragma unroll
-          for (int b = 0; b < BB; ++b) {
-            acc[b][0] = fmaf(xv[c][b], wv.x, acc[b][0]);
-            acc[b][1] = fmaf(xv[c][b], wv.y, acc[b][1]);
-            acc[b][2] = fmaf(xv[c][b], wv.z, acc[b][2]);
-            acc[b][3] = fmaf(xv[c][b], wv.w, acc[b][3]);
+            for (int b = 0; b < BB; ++b) {
+              unsigned long long xx;
+              asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(xv[c][b]));
+              asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[b][0]) : "l"(xx), "l"(w01));
+              asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[b][1]) : "l"(xx), "l"(w23));
+            }
+          } else {
+#pragma unroll
+            for (int b = 0; b < BB; ++b) {
+              acc[b][0] = fmaf(xv[c][b], wv.x, acc[b][0]);
+              acc[b][1] = fmaf(xv[c][b], wv.y, acc[b][1]);
+              acc[b][2] = fmaf(xv[c][b], wv.z, acc[b][2]);
+              acc[b][3] = fmaf(xv[c][b], wv.w, acc[b][3]);
+            }
           }
         }
       }
@@ -165,6 +183,13 @@ lc3d_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel
     __syncwarp();
     if (lane == 0) {                             // slot free: every lane has read its share
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(empty + slot)) : "memory");
+    }
+    if (P2) {
+#pragma unroll
+      for (int b = 0; b < BB; ++b) {
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[b][0]), "=f"(acc[b][1]) : "l"(acc2[b][0]));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[b][2]), "=f"(acc[b][3]) : "l"(acc2[b][1]));
+      }
     }
     // fold the 32/CQ lanes that share an output quad
 #pragma unroll
@@ -266,7 +291,7 @@ lc3d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ kernel, c
   }
 }
 
-template <int BB, int WPP>
+template <int BB, int WPP, bool P2 = false>
 static int launch_stream(const float* x, const float* kernel, const float* bias, float* out, const LcGeo& g,
                          int b_base, int cq_log2, cudaStream_t st) {
   const uint32_t blk_bytes = (uint32_t)g.F * g.Cout * sizeof(float);
@@ -276,7 +301,7 @@ static int launch_stream(const float* x, const float* kernel, const float* bias,
   if (stages < 2) return 1;                      // caller falls back to the generic kernel
   if (stages > kLcMaxStages) stages = kLcMaxStages;
   const size_t smem = (size_t)stages * blk_stride + (size_t)stages * 16 + (size_t)g.F * sizeof(int) + 16;
-  auto kern = lc3d_stream_kernel<BB, WPP>;
+  auto kern = lc3d_stream_kernel<BB, WPP, P2>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("cudaFuncSetAttribute(lc3d_stream)");
   int grid = sm_count();
@@ -329,11 +354,14 @@ extern "C" int nrt_lc3d_fwd_f32(const float* x, const float* kernel, const float
     int cq_log2 = 0;
     while ((1 << cq_log2) < cq) ++cq_log2;
     int b = 0, rc = NRT_OK;
+    const char* pe = getenv("NRT_LC3D_FFMA2");
+    const bool p2 = !(pe && atoi(pe) == 0);
     while (b < B && rc == NRT_OK) {              // batch items per pass = BB * WPP (weights streamed once per pass)
       const int left = B - b;
-      if (left >= 8) { rc = launch_stream<4, 2>(x, kernel, bias, out, g, b, cq_log2, st); b += 8; }
-      else if (left >= 4) { rc = launch_stream<2, 2>(x, kernel, bias, out, g, b, cq_log2, st); b += 4; }
-      else if (left >= 2) { rc = launch_stream<2, 1>(x, kernel, bias, out, g, b, cq_log2, st); b += 2; }
+      // batch > 1 is FMA-issue bound: packed fp32x2 FMAs (NRT_LC3D_FFMA2=0 restores the scalar chain)
+      if (left >= 8) { rc = p2 ? launch_stream<4, 2, true>(x, kernel, bias, out, g, b, cq_log2, st) : launch_stream<4, 2>(x, kernel, bias, out, g, b, cq_log2, st); b += 8; }
+      else if (left >= 4) { rc = p2 ? launch_stream<2, 2, true>(x, kernel, bias, out, g, b, cq_log2, st) : launch_stream<2, 2>(x, kernel, bias, out, g, b, cq_log2, st); b += 4; }
+      else if (left >= 2) { rc = p2 ? launch_stream<2, 1, true>(x, kernel, bias, out, g, b, cq_log2, st) : launch_stream<2, 1>(x, kernel, bias, out, g, b, cq_log2, st); b += 2; }
       else { rc = launch_stream<1, 1>(x, kernel, bias, out, g, b, cq_log2, st); b += 1; }
     }
     if (rc <= 0) return rc;       // rc == 1: weight block does not fit the ring -> generic

@@ -317,8 +317,12 @@ def test_lc3d_golden(ne, monkeypatch, name, generic):
     np.testing.assert_allclose(out, g['out'], rtol=1e-5, atol=2e-5)
 
 
-def test_lc3d_vs_oracle_batches_activations_and_sharding(ne):
+@pytest.mark.parametrize('ffma2', ['1', '0'])
+def test_lc3d_vs_oracle_batches_activations_and_sharding(ne, monkeypatch, ffma2):
+    """batch 11 = passes of 8 + 2 + 1 items: the packed-FMA (fp32x2) and the scalar accumulation chains are
+    bit-identical, both within 1e-5 of the oracle."""
     from neurite_b200.layers import local_conv3d
+    monkeypatch.setenv('NRT_LC3D_FFMA2', ffma2)
     rng = np.random.default_rng(13)
     x = rng.standard_normal((11, 8, 9, 10, 16)).astype(F32)
     O = (6, 7, 8)
@@ -328,6 +332,11 @@ def test_lc3d_vs_oracle_batches_activations_and_sharding(ne):
         ref = olc3d.locally_connected_3d(x, kernel, bias, (3, 3, 3), activation=act, literal=False)
         out = local_conv3d(dev(x), dev(kernel), dev(bias), (3, 3, 3), (1, 1, 1), O, activation=act).cpu().numpy()
         np.testing.assert_allclose(out, ref, rtol=1e-5, atol=2e-5)
+    if ffma2 == '1':
+        monkeypatch.setenv('NRT_LC3D_FFMA2', '0')
+        scalar = local_conv3d(dev(x), dev(kernel), dev(bias), (3, 3, 3), (1, 1, 1), O, activation='sigmoid').cpu().numpy()
+        np.testing.assert_array_equal(out, scalar)
+        monkeypatch.setenv('NRT_LC3D_FFMA2', '1')
     # position sharding: two ranks each own half of the positions AND of the weights
     ref = olc3d.locally_connected_3d(x, kernel, bias, (3, 3, 3), literal=False).reshape(11, -1, 16)
     P = kernel.shape[0]
