@@ -444,8 +444,8 @@ def bench_mi(args, segs=False):
 
 
 def bench_blur(args):
-    """GaussianBlur(sigma=1) (7 taps per axis) of B single-channel 160x192x224 volumes: one fused kernel
-    (NRT_BLUR_FUSED=0: the three separable passes)."""
+    """GaussianBlur(sigma=1) (7 taps per axis) of B single-channel 160x192x224 volumes: three separable passes
+    (NRT_BLUR_FUSED=1: the single fused kernel, measured slower)."""
     import torch
     import neurite_b200 as ne
     world, rank, local = dist_setup(args.gpus)
@@ -459,7 +459,7 @@ def bench_blur(args):
     clocks = sampler.stop()
     peak, peak_src = measured_peak()
     achieved = 8.0 * B * V * args.steps / (ms * 1e-3) / 1e9
-    fused = os.environ.get('NRT_BLUR_FUSED', '1') != '0' and round(args.sigma * 3) * 2 + 1 <= 15
+    fused = os.environ.get('NRT_BLUR_FUSED', '0') == '1' and round(args.sigma * 3) * 2 + 1 <= 15
     if rank == 0:
         print(json.dumps({
             'metric': 'voxels/s, GaussianBlur(sigma=%g), 160x192x224 fp32' % args.sigma,

@@ -157,13 +157,12 @@ def test_gaussian_kernel_golden_bit_exact(ne, name):
         np.testing.assert_array_equal(k.numpy(), g['k%d' % i])
 
 
-@pytest.mark.parametrize('generic', [False, True, 'passes'])
+@pytest.mark.parametrize('generic', [False, True, 'fused'])
 @pytest.mark.parametrize('name', golden_names('blur'))
 def test_gaussian_blur_golden(ne, monkeypatch, name, generic):
     if generic is True:
         monkeypatch.setenv('NRT_CONV_GENERIC', '1')
-    if generic:
-        monkeypatch.setenv('NRT_BLUR_FUSED', '0')
+    monkeypatch.setenv('NRT_BLUR_FUSED', '1' if generic == 'fused' else '0')
     g = load_golden(name)
     sigma = g['sigma'].tolist()
     lay = ne.layers.GaussianBlur(sigma=sigma)
