@@ -7,7 +7,6 @@ plain slicing of the full volume, which is exactly what the kernel consumes.
 import os
 import socket
 
-import numpy as np
 import pytest
 import torch
 import torch.distributed as dist

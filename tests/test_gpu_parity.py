@@ -9,7 +9,6 @@ Tolerances: interpolation family is BIT-EXACT (np.array_equal) -- the kernels ro
 multiply/add separately like the reference's unfused TF ops.  Reductions (Dice, CCE, LC3D)
 use rtol 1e-5 (north_star), because TF's reduction order is unspecified.
 """
-import os
 
 import numpy as np
 import pytest

@@ -7,7 +7,6 @@ reductions).
 import os
 import socket
 
-import numpy as np
 import pytest
 import torch
 

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from conftest import golden_names, load_golden
-from oracle import cport, interp, lc3d, metrics
+from oracle import cport, interp
 
 F32 = np.float32
 
