@@ -400,6 +400,23 @@ def bench_resize(args):
     finish(world)
 
 
+def cpu_baseline_timed(fn, nunits, unit, sample, budget_s=8.0):
+    """best-of-n wall time of a C/OpenMP oracle call on the host cores (bounded: ~budget_s seconds)."""
+    from oracle import cport
+    cport.build()
+    cport.use_all_cores()
+    fn()                                                   # warm-up
+    best, n, t_all = None, 0, time.time()
+    while n < 2 or (time.time() - t_all < budget_s and n < 20):
+        t = time.time()
+        fn()
+        dt = time.time() - t
+        best = dt if best is None else min(best, dt)
+        n += 1
+    return {'value': nunits / best, 'unit': unit, 'cores': cport.num_threads(), 'kind': 'port',
+            'sample': sample + ', best of %d runs' % n}
+
+
 def bench_mi(args, segs=False):
     """MutualInformation: `mi` = volumes() on B pairs of 160x192x224 volumes (soft quantisation
     fused, 8 B/voxel); `mi_segs` = segs() on two [2,160,192,224,16] probability maps (128 B/voxel)."""
@@ -425,7 +442,7 @@ def bench_mi(args, segs=False):
     peak, peak_src = measured_peak()
     achieved = per_voxel * B * V * args.steps / (ms * 1e-3) / 1e9
     if rank == 0:
-        print(json.dumps({
+        line = ({
             'metric': 'voxels/s, MutualInformation.%s (16 bins), 160x192x224 fp32' % ('segs' if segs else 'volumes'),
             'value': world * B * V * args.steps / (ms * 1e-3), 'unit': 'voxels/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -439,7 +456,17 @@ def bench_mi(args, segs=False):
                                         % (per_voxel, 'maps' if segs else 'volumes'),
                          'kernel': kern, 'per': 'GPU',
                          'note': '' if segs else 'volumes(): bound by issue slots / MUFU (32 exp per voxel pair), not HBM'},
-            'gpu_launches': args.steps * (4 if segs else 10), 'clocks': clocks}), flush=True)
+            'gpu_launches': args.steps * (4 if segs else 10), 'clocks': clocks})
+        if world == 1 and not segs and not args.no_cpu_baseline:
+            import numpy as np
+            from oracle import cport
+            xs = np.random.default_rng(0).uniform(0, 1, (1,) + SHAPE + (1,)).astype(np.float32)
+            ys = np.clip(0.7 * xs * xs + 0.1 + 0.1 * np.random.default_rng(1).uniform(0, 1, xs.shape), 0, 1).astype(np.float32)
+            line['cpu_baseline'] = cpu_baseline_timed(
+                lambda: cport.mi_channelwise(xs, ys, nb_bins=16), V, 'voxels/s',
+                'oracle/c oracle_mi_channelwise_f32 (C99+OpenMP restatement of metrics.py:185-292 with soft_quantize '
+                'fused), ONE 160x192x224 volume pair')
+        print(json.dumps(line), flush=True)
     finish(world)
 
 
@@ -461,7 +488,7 @@ def bench_blur(args):
     achieved = 8.0 * B * V * args.steps / (ms * 1e-3) / 1e9
     fused = os.environ.get('NRT_BLUR_FUSED', '0') == '1' and round(args.sigma * 3) * 2 + 1 <= 15
     if rank == 0:
-        print(json.dumps({
+        line = ({
             'metric': 'voxels/s, GaussianBlur(sigma=%g), 160x192x224 fp32' % args.sigma,
             'value': world * B * V * args.steps / (ms * 1e-3), 'unit': 'voxels/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -474,7 +501,15 @@ def bench_blur(args):
                                         + ('' if fused else '; the three-pass path moves 24 B/voxel, so 0.33 is its ceiling'),
                          'kernel': 'blur3d_fused_kernel' if fused else 'sepconv_col4_kernel x2 + sepconv_row_kernel',
                          'per': 'GPU'},
-            'gpu_launches': args.steps * (1 if fused else 3), 'clocks': clocks}), flush=True)
+            'gpu_launches': args.steps * (1 if fused else 3), 'clocks': clocks})
+        if world == 1 and not args.no_cpu_baseline:
+            import numpy as np
+            from oracle import cport
+            xs = np.random.default_rng(0).standard_normal((1,) + SHAPE + (1,)).astype(np.float32)
+            line['cpu_baseline'] = cpu_baseline_timed(
+                lambda: cport.gaussian_blur(xs, args.sigma), V, 'voxels/s',
+                'oracle/c oracle_sepconv_axis_f32 x3 (C99+OpenMP restatement of utils.py:665-751), ONE 160x192x224 volume')
+        print(json.dumps(line), flush=True)
     finish(world)
 
 

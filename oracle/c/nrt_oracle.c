@@ -13,6 +13,10 @@
  *   oracle_dice_sums_f32 reference neurite/tf/metrics.py:471-477 (the three reductions)
  *   oracle_cce_f32       reference neurite/tf/metrics.py:640-650 + Keras CCE formula
  *   oracle_lc3d_f32      reference neurite/tf/layers.py:1126-1197, 1098-1099
+ *   oracle_mi_volumes_f32  reference neurite/tf/metrics.py:185-292 (channelwise -> maps) with
+ *                        neurite/tf/utils/utils.py:1099-1172 soft_quantize fused in
+ *   oracle_sepconv_axis_f32  one pass of neurite/tf/utils/utils.py:665-751 separable_conv
+ *                        (tf.nn.convolution: zero-padded cross-correlation, third party)
  */
 #include <math.h>
 #include <stdint.h>
@@ -191,4 +195,100 @@ void oracle_lc3d_f32(const float* x, const float* kernel, const float* bias, flo
       }
     }
   }
+}
+
+
+/* ---- MutualInformation.channelwise (metrics.py:185-225) on [B, V, C] intensity tensors --------
+ * bins = tf.linspace(min, max, nb) of the WHOLE tensor (utils.py:1151-1153) unless `centers` is
+ * given for both; w[bin] = exp(-alpha (clip(x) - c)^2) (utils.py:1157-1171); joint and marginal
+ * sums in double (TF's matmul / reduce order is unspecified); maps() arithmetic in fp32
+ * (metrics.py:265-292).  mi[b*C + c]. */
+static void linspace_f32(float mn, float mx, int nb, float* c) {
+  if (nb == 1) { c[0] = mn; return; }
+  const float delta = (mx - mn) / (float)(nb - 1);
+  c[0] = mn;
+  for (int i = 1; i < nb - 1; ++i) c[i] = mn + delta * (float)i;
+  c[nb - 1] = mx;
+}
+
+void oracle_mi_channelwise_f32(const float* x, const float* y, int B, int64_t V, int C, int nb, float alpha,
+                               float lo, float hi, const float* centers_x, const float* centers_y, float* mi) {
+  float cx[64], cy[64];
+  if (nb > 64) return;
+  const int64_t n = (int64_t)B * V * C;
+  if (centers_x && centers_y) {
+    memcpy(cx, centers_x, sizeof(float) * nb);
+    memcpy(cy, centers_y, sizeof(float) * nb);
+  } else {
+    float mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
+#pragma omp parallel for reduction(min : mnx, mny) reduction(max : mxx, mxy) schedule(static)
+    for (int64_t e = 0; e < n; ++e) {
+      mnx = fminf(mnx, x[e]); mxx = fmaxf(mxx, x[e]);
+      mny = fminf(mny, y[e]); mxy = fmaxf(mxy, y[e]);
+    }
+    linspace_f32(mnx, mxx, nb, cx);
+    linspace_f32(mny, mxy, nb, cy);
+  }
+  const float eps = 1e-7f;
+  for (int item = 0; item < B * C; ++item) {
+    const int b = item / C, c = item - b * C;
+    double H[64 * 64], sx[64], sy[64];
+    memset(H, 0, sizeof(H)); memset(sx, 0, sizeof(sx)); memset(sy, 0, sizeof(sy));
+#pragma omp parallel
+    {
+      double h[64 * 64], px[64], py[64];
+      memset(h, 0, sizeof(double) * nb * nb); memset(px, 0, sizeof(px)); memset(py, 0, sizeof(py));
+#pragma omp for schedule(static) nowait
+      for (int64_t v = 0; v < V; ++v) {
+        const float xv = clipf(x[((int64_t)b * V + v) * C + c], lo, hi);
+        const float yv = clipf(y[((int64_t)b * V + v) * C + c], lo, hi);
+        float wx[64], wy[64];
+        for (int i = 0; i < nb; ++i) {
+          const float dx = xv - cx[i], dy = yv - cy[i];
+          wx[i] = expf(-alpha * (dx * dx));
+          wy[i] = expf(-alpha * (dy * dy));
+          px[i] += wx[i]; py[i] += wy[i];
+        }
+        for (int i = 0; i < nb; ++i)
+          for (int j = 0; j < nb; ++j) h[i * nb + j] += (double)wx[i] * (double)wy[j];
+      }
+#pragma omp critical
+      {
+        for (int i = 0; i < nb * nb; ++i) H[i] += h[i];
+        for (int i = 0; i < nb; ++i) { sx[i] += px[i]; sy[i] += py[i]; }
+      }
+    }
+    double th = 0, tx = 0, ty = 0;
+    for (int i = 0; i < nb * nb; ++i) th += (double)(float)H[i];
+    for (int i = 0; i < nb; ++i) { tx += (double)(float)sx[i]; ty += (double)(float)sy[i]; }
+    const float N = (float)th + eps, Nx = (float)tx + eps, Ny = (float)ty + eps;
+    double acc = 0;
+    for (int i = 0; i < nb; ++i)
+      for (int j = 0; j < nb; ++j) {
+        const float pxy = (float)H[i * nb + j] / N;
+        const float px_ = (float)sx[i] / Nx, py_ = (float)sy[j] / Ny;
+        const float q = px_ * py_ + eps;
+        acc += (double)(pxy * logf(pxy / q + eps));
+      }
+    mi[item] = (float)acc;
+  }
+}
+
+/* one pass of separable_conv along the middle axis of [outer, L, inner] -> [outer, L_out, inner]:
+ * out[o, l, i] = sum_j k[j] x[o, l*stride - pad_before + j*dil, i], zero outside; double accumulate. */
+void oracle_sepconv_axis_f32(const float* x, float* out, int64_t outer, int64_t L, int64_t inner, const float* k, int K,
+                             int stride, int dil, int pad_before, int64_t L_out) {
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int64_t o = 0; o < outer; ++o)
+    for (int64_t l = 0; l < L_out; ++l) {
+      float* op = out + (o * L_out + l) * inner;
+      for (int64_t i = 0; i < inner; ++i) {
+        double acc = 0;
+        for (int j = 0; j < K; ++j) {
+          const int64_t s = l * stride - pad_before + (int64_t)j * dil;
+          if (s >= 0 && s < L) acc += (double)k[j] * (double)x[(o * L + s) * inner + i];
+        }
+        op[i] = (float)acc;
+      }
+    }
 }

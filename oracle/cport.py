@@ -127,3 +127,53 @@ def lc3d(x, kernel, bias, kernel_size, strides=(1, 1, 1)):
     lib().oracle_lc3d_f32(_p(x), _p(kernel), None if b is None else _p(b), _p(out), ctypes.c_int(B),
                           _ints(x.shape[1:4]), ctypes.c_int(Cin), ctypes.c_int(Cout), _ints(kernel_size), _ints(strides))
     return out
+
+
+def mi_channelwise(x, y, nb_bins=16, alpha=None, min_clip=-np.inf, max_clip=np.inf, bin_centers=None):
+    """MutualInformation.channelwise on [B, ..., C] intensity tensors -> [B, C] (metrics.py:185-292)."""
+    from . import mi as _mi
+    x = np.ascontiguousarray(x, dtype=F32)
+    y = np.ascontiguousarray(y, dtype=F32)
+    B, C = x.shape[0], x.shape[-1]
+    V = x.size // (B * C)
+    if bin_centers is not None:
+        cen = np.ascontiguousarray(bin_centers, dtype=F32)
+        nb_bins = cen.shape[0]
+    if alpha is None:
+        alpha = _mi.default_alpha(nb_bins, bin_centers)
+    out = np.empty((B, C), dtype=F32)
+    lib().oracle_mi_channelwise_f32(_p(x), _p(y), ctypes.c_int(B), ctypes.c_int64(V), ctypes.c_int(C),
+                                    ctypes.c_int(int(nb_bins)), ctypes.c_float(float(alpha)),
+                                    ctypes.c_float(float(min_clip)), ctypes.c_float(float(max_clip)),
+                                    _p(cen) if bin_centers is not None else None,
+                                    _p(cen) if bin_centers is not None else None, _p(out))
+    return out
+
+
+def gaussian_blur(x, sigma, out=None):
+    """layers.GaussianBlur(sigma)(x) for x [B, *space, C] (non-random): one C pass per blurred axis."""
+    from . import conv as _conv
+    x = np.ascontiguousarray(x, dtype=F32)
+    nd = x.ndim - 2
+    sig = np.ravel(sigma).tolist()
+    sig = sig * nd if len(sig) == 1 else sig
+    if not any(s > 0 for s in sig):
+        return x
+    ks = _conv.gaussian_kernel(sig, separate=True)
+    ks = ks if isinstance(ks, list) else [ks]
+    cur = x
+    for ax, k in enumerate(ks):
+        K = len(k)
+        if K == 1 and k[0] == 1:
+            continue
+        shp = cur.shape
+        outer = int(np.prod(shp[:ax + 1], dtype=np.int64))
+        L = shp[ax + 1]
+        inner = int(np.prod(shp[ax + 2:], dtype=np.int64))
+        nxt = np.empty_like(cur)
+        k = np.ascontiguousarray(k, dtype=F32)
+        lib().oracle_sepconv_axis_f32(_p(cur), _p(nxt), ctypes.c_int64(outer), ctypes.c_int64(L), ctypes.c_int64(inner),
+                                      _p(k), ctypes.c_int(K), ctypes.c_int(1), ctypes.c_int(1),
+                                      ctypes.c_int((K - 1) // 2), ctypes.c_int64(L))
+        cur = nxt
+    return cur

@@ -52,3 +52,28 @@ def test_c_dice_cce_lc3d():
     g = load_golden('lc3d_k321_s212_cl')
     out = cport.lc3d(g['x'], g['kernel'], g['bias'].reshape(-1, 5), tuple(g['kernel_size']), tuple(g['strides']))
     np.testing.assert_allclose(out, g['out'], rtol=1e-5, atol=2e-5)
+
+
+def test_c_mi_and_blur_match_golden_and_numpy_oracle():
+    """the C/OpenMP restatements used as bench.py's cpu_baseline for --op mi / --op blur."""
+    from oracle import conv as oconv, mi as omi
+    g = load_golden('mi_channelwise_c3')
+    np.testing.assert_allclose(cport.mi_channelwise(g['x'], g['y']), g['mi'], rtol=1e-5, atol=2e-6)
+    g = load_golden('mi_volumes_nb16')
+    np.testing.assert_allclose(cport.mi_channelwise(g['x'], g['y'], nb_bins=16).reshape(-1), g['mi'], rtol=1e-5, atol=2e-6)
+    g = load_golden('mi_volumes_clip_alpha')
+    out = cport.mi_channelwise(g['x'], g['y'], nb_bins=12, alpha=float(g['alpha']), min_clip=float(g['min_clip']),
+                               max_clip=float(g['max_clip']))
+    np.testing.assert_allclose(out.reshape(-1), g['mi'], rtol=1e-5, atol=2e-6)
+    centers = np.linspace(0, 1, 9).astype(np.float32)
+    rng = np.random.default_rng(2)
+    x = rng.uniform(0, 1, (2, 300, 2)).astype(np.float32)
+    y = rng.uniform(0, 1, (2, 300, 2)).astype(np.float32)
+    np.testing.assert_allclose(cport.mi_channelwise(x, y, bin_centers=centers, alpha=30.0),
+                               omi.MutualInformation(bin_centers=centers, soft_bin_alpha=30.0).channelwise(x, y),
+                               rtol=1e-5, atol=2e-6)
+    for name in ('blur3d_s1', 'blur3d_aniso', 'blur3d_s3', 'blur2d_s2', 'blur1d_s1p2'):
+        g = load_golden(name)
+        np.testing.assert_allclose(cport.gaussian_blur(g['x'], g['sigma'].tolist()), g['out'], rtol=1e-6, atol=1e-6)
+    v = rng.standard_normal((1, 20, 21, 22, 1)).astype(np.float32)
+    np.testing.assert_array_equal(cport.gaussian_blur(v, 1.3), oconv.gaussian_blur(v, 1.3))
