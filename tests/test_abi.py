@@ -8,6 +8,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 import torch
 
@@ -64,6 +65,72 @@ def test_no_cpu_fallback():
         ne.losses.Dice().loss(torch.zeros(1, 4, 4, 2), torch.zeros(1, 4, 4, 2))
     with pytest.raises(ne._lib.NeuriteB200Error, match='no CPU path'):
         ne.layers.SpatialTransformer()([torch.zeros(1, 4, 4, 4, 1), torch.zeros(1, 4, 4, 4, 3)])
+    # the 'next' rows: mutual information, soft quantisation, blur, subsample, separable convolution
+    v = torch.rand(1, 4, 4, 4, 1)
+    with pytest.raises(ne._lib.NeuriteB200Error, match='no CPU path'):
+        ne.metrics.MutualInformation().volumes(v, v)
+    with pytest.raises(ne._lib.NeuriteB200Error, match='no CPU path'):
+        ne.metrics.MutualInformation().segs(torch.rand(1, 8, 3), torch.rand(1, 8, 3))
+    with pytest.raises(ne._lib.NeuriteB200Error, match='no CPU path'):
+        ne.utils.soft_quantize(v)
+    with pytest.raises(ne._lib.NeuriteB200Error, match='no CPU path'):
+        ne.layers.GaussianBlur(sigma=1.0)(v)
+    with pytest.raises(ne._lib.NeuriteB200Error, match='no CPU path'):
+        ne.layers.Subsample(seed=0)(v)
+    with pytest.raises(ne._lib.NeuriteB200Error, match='no CPU path'):
+        ne.utils.separable_conv(v, torch.ones(3), batched=True)
+
+
+def test_mi_blur_subsample_argument_checks_and_configs():
+    """reference-side checks that do not need a device: metrics.py:69-114, layers.py:268-343, 380-423."""
+    import neurite_b200 as ne
+    m = ne.metrics.MutualInformation()
+    assert m.nb_bins == 16 and np.float32(m.soft_bin_alpha) == np.float32(1) / (np.float32(2) * np.float32(0.5 / 15) ** 2)
+    with pytest.raises(AssertionError, match='cannot provide both'):
+        ne.metrics.MutualInformation(bin_centers=np.linspace(0, 1, 4), nb_bins=4)
+    c = ne.metrics.MutualInformation(bin_centers=np.linspace(0, 1, 5))
+    assert c.nb_bins == 5 and abs(float(c.soft_bin_alpha) - 1 / (2 * (0.5 * 0.25) ** 2)) < 1e-3
+    assert ne.losses.MutualInformation is ne.metrics.MutualInformation          # losses.py:40-43 re-export
+
+    with pytest.raises(AssertionError, match='sigma or level'):
+        ne.layers.GaussianBlur()
+    with pytest.raises(AssertionError, match='only sigma or level'):
+        ne.layers.GaussianBlur(sigma=1, level=2)
+    with pytest.raises(ValueError, match='isotropy is implicitly'):
+        ne.layers.GaussianBlur(sigma=1, isotropic=True)
+    with pytest.raises(ValueError, match='must not be less than 1'):
+        ne.layers.GaussianBlur(level=0.5)
+    g = ne.layers.GaussianBlur(sigma=[1.0, 2.0, 0.0], name='blur')
+    cfg = g.get_config()
+    assert cfg == {'name': 'blur', 'sigma': [1.0, 2.0, 0.0], 'random': False, 'min_sigma': 0, 'isotropic': False, 'seed': None}
+    assert ne.layers.GaussianBlur.from_config(cfg).sigma == [1.0, 2.0, 0.0]
+    g.build((1, 8, 8, 8, 1))
+    assert g.sigma == [1.0, 2.0, 0.0] and g.min_sigma == [0, 0, 0]
+    with pytest.raises(ValueError, match='1 or 3 sigmas expected'):
+        ne.layers.GaussianBlur(sigma=[1.0, 2.0]).build((1, 8, 8, 8, 1))
+    with pytest.raises(ValueError, match='must not be less than 0'):
+        ne.layers.GaussianBlur(sigma=-1.0).build((1, 8, 8, 1))
+    x = torch.zeros(1, 4, 4, 1)
+    assert ne.layers.GaussianBlur(sigma=0)(x) is x                            # layers.py:347-348: no positive sigma -> input
+
+    k = ne.utils.gaussian_kernel(1.0)
+    assert k.shape == (7,) and abs(float(k.sum()) - 1) < 1e-6 and torch.equal(k, k.flip(0))
+    ks = ne.utils.gaussian_kernel([0.5, 2.0], separate=True)
+    assert [int(t.numel()) for t in ks] == [5, 13]
+    assert ne.utils.gaussian_kernel([1.0, 1.0]).shape == (7, 7)
+    with pytest.raises(ValueError, match='differ in length'):
+        ne.utils.gaussian_kernel([1.0, 2.0], windowsize=[3])
+
+    s = ne.layers.Subsample(stride_min=2, stride_max=4, axes=[1, 3], prob=0.5, upsample=False, seed=7)
+    assert s.get_config() == {'name': 'subsample', 'stride_min': 2, 'stride_max': 4, 'axes': [1, 3], 'prob': 0.5,
+                              'upsample': False, 'seed': 7}
+    s.build((1, 8, 8, 8, 2))
+    assert s.axes == [1, 3]
+    with pytest.raises(ValueError):
+        ne.layers.Subsample(axes=[4]).build((1, 8, 8, 8, 2))                   # the channel axis is not spatial
+    assert ne.layers.Subsample(stride_max=1)(x) is x and ne.layers.Subsample(prob=0)(x) is x
+    idx = ne.utils.subsample_indices(10, 2.0)
+    assert idx.tolist() == [0, 0, 2, 2, 5, 5, 7, 7, 9, 9]
 
 
 def test_reference_exceptions_and_config_round_trip():
