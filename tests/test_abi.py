@@ -53,6 +53,33 @@ def test_argument_validation_returns_status_codes():
     assert lib.nrt_lc3d_fwd_f32(one, one, null, one, 1, _lib.i32_array([2, 8, 8]), 1, 1, k, k, 0, 0, 0, 1, null) == -1
     with pytest.raises(_lib.NeuriteB200Error, match='bad argument'):
         _lib.check(-1)
+    # the MI / convolution entry points validate before touching the device too
+    f = ctypes.c_float
+    inf = float('inf')
+    assert lib.nrt_mi_hist_f32(null, 1, 1, 1, 16, one, one, 1, 1, 1, 16, one, 1, 1, 10, f(1.0), f(-inf), f(inf),
+                               one, null, one, 1 << 30, null) == -1                                     # null x
+    assert lib.nrt_mi_hist_f32(one, 1, 1, 1, 65, one, one, 1, 1, 1, 16, one, 1, 1, 10, f(1.0), f(-inf), f(inf),
+                               one, null, one, 1 << 30, null) == -2                                     # 65 bins
+    assert b'bins' in lib.nrt_last_error_string()
+    assert lib.nrt_mi_hist_f32(one, 1, 1, 1, 16, null, one, 1, 1, 1, 16, one, 1, 1, 10, f(1.0), f(-inf), f(inf),
+                               one, null, one, 1 << 30, null) == -1                                     # quantise without centres
+    assert lib.nrt_mi_hist_f32(one, 1, 1, 0, 16, null, one, 1, 1, 0, 16, null, 1, 3, 10, f(1.0), f(-inf), f(inf),
+                               one, null, one, 1 << 30, null) == -1                                     # channels need two quantised operands
+    assert lib.nrt_mi_hist_f32(one, 1, 1, 1, 16, one, one, 1, 1, 1, 16, one, 1, 1, 10, f(1.0), f(-inf), f(inf),
+                               one, null, one, 16, null) == -1                                          # workspace too small
+    assert lib.nrt_mi_workspace_bytes(2, 16, 16) == 2 * 592 * (256 + 32) * 4
+    assert lib.nrt_mi_bwd_f32(one, 1, 1, 1, 33, one, one, 1, 1, 1, 16, one, 1, 1, 10, f(1.0), f(-inf), f(inf),
+                              one, one, one, null, null, 0, null) == -2                                 # gradient: <= 32 bins
+    assert lib.nrt_mi_bwd_f32(one, 1, 1, 1, 16, one, one, 1, 1, 1, 16, one, 1, 1, 10, f(1.0), f(-inf), f(inf),
+                              one, null, null, null, null, 0, null) == -1                               # no gradient requested
+    assert lib.nrt_minmax_f32(one, 0, one, one, 1 << 20, null) == -1                                    # empty tensor
+    assert lib.nrt_sepconv_axis_f32(one, one, 1, 8, 1, one, 3, 1, 1, 1, 8, null) == -1                  # in place
+    assert b'in-place' in lib.nrt_last_error_string()
+    two = ctypes.c_void_p(32)
+    assert lib.nrt_sepconv_axis_f32(one, two, 1, 8, 1, one, 0, 1, 1, 0, 8, null) == -1                  # K = 0
+    assert lib.nrt_blur3d_f32(one, two, 1, 8, 8, 8, one, one, one, 4, null) == -2                       # even K
+    assert lib.nrt_blur3d_f32(one, two, 1, 8, 8, 8, one, one, one, 17, null) == -2                      # K > 15
+    assert lib.nrt_gather_axis_f32(one, null, two, 1, 8, 1, 8, null) == -1
 
 
 def test_no_cpu_fallback():
