@@ -707,8 +707,9 @@ __device__ __forceinline__ void compute_tile(const float* __restrict__ s_flow, c
 // with only 8-16 voxels per thread the prologue is a visible part of the instruction count.
 // ABS = the 'flow' tensor holds absolute sample locations (interpn on the volume's own grid): compile-time, so
 // that the displacement kernels carry no trace of it
-template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8, int CC = 1, bool ABS = false>
-__global__ void __launch_bounds__(NW * 32)
+// MINB = CTAs per SM the register allocation is capped for (1 = uncapped)
+template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8, int CC = 1, bool ABS = false, int MINB = 1>
+__global__ void __launch_bounds__(NW * 32, MINB)
 warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
                    const __grid_constant__ CUtensorMap tm_flow,
                    const float* __restrict__ vol, const float* __restrict__ flow,
@@ -1031,7 +1032,7 @@ int warp3d_bwd_tile(const float* vol, const float* flow, const float* gout, floa
   return check_launch("warp3d_bwd_tile_kernel");
 }
 
-template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8, int CC = 1, bool ABS = false>
+template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8, int CC = 1, bool ABS = false, int MINB = 1>
 static int launch_tile(const float* vol, const float* flow, float* out, TileGeo tg, int H, int W, int src_n0,
                        int out_n0, cudaStream_t st) {
   using Cfg = TileCfg<TZ, TY, HALO, CC>;
@@ -1048,7 +1049,7 @@ static int launch_tile(const float* vol, const float* flow, float* out, TileGeo 
   if (rc != NRT_OK) return rc;
   rc = encode_f32_4d(&tmf, flow, fd, fb);
   if (rc != NRT_OK) return rc;
-  auto kern = warp3d_tile_kernel<TZ, TY, HALO, METHOD, U, NW, CC, ABS>;
+  auto kern = warp3d_tile_kernel<TZ, TY, HALO, METHOD, U, NW, CC, ABS, MINB>;
   // set on every launch: the attribute is per device and the call costs ~1 us of host time
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM) != cudaSuccess)
     return check_launch("cudaFuncSetAttribute(warp3d_tile)");
@@ -1120,8 +1121,11 @@ static int try_tile_path(const float* vol, const float* flow, float* out, int B,
   if (W % 4 != 0 || !aligned16(vol) || !aligned16(flow) || W < 32) return NRT_OK;
   // tile shapes (TZ x TY x 32) and halos built: the default 8x8x32 runs 4 CTAs per SM (best
   // measured on B200, profiles/); `halo` picks the smallest built halo that covers it.
-  int cfg = env_int("NRT_WARP_TILE_CFG", 2);         // 0: 8x16x32, 2: 8x8x32 (default), 3: 4x8x32
-  if (cfg != 0 && cfg != 2 && cfg != 3) cfg = 2;
+  // 0: 8x16x32, 2: 8x8x32 (default), 3: 4x8x32; 4 / 5: 4x8x32 with the registers capped for 5 / 6 CTAs per SM
+  // (experiment for the tile-load barrier stall; halos 3 and 4 only)
+  int cfg = env_int("NRT_WARP_TILE_CFG", 2);
+  if (cfg != 0 && cfg != 2 && cfg != 3 && cfg != 4 && cfg != 5) cfg = 2;
+  if ((cfg == 4 || cfg == 5) && halo > 4) cfg = 3;
   if (halo <= 0) halo = 3;
   const int hsel = halo <= 3 ? 3 : (halo <= 4 ? 4 : (halo <= 6 ? 6 : 8));
   TileGeo tg;
@@ -1170,6 +1174,13 @@ static int try_tile_path(const float* vol, const float* flow, float* out, int B,
   NRT_TILE_CASE(2, 8, 8, 3) NRT_TILE_CASE(2, 8, 8, 4) NRT_TILE_CASE(2, 8, 8, 6) NRT_TILE_CASE(2, 8, 8, 8)
   NRT_TILE_CASE(3, 4, 8, 3) NRT_TILE_CASE(3, 4, 8, 4) NRT_TILE_CASE(3, 4, 8, 6) NRT_TILE_CASE(3, 4, 8, 8)
 #undef NRT_TILE_CASE
+#define NRT_TILE_OCC(i, hh, minb)                                                                                  \
+  if (cfg == (i) && hsel == (hh))                                                                                  \
+    rc = method == NRT_LINEAR                                                                                      \
+             ? launch_tile<4, 8, hh, NRT_LINEAR, 2, 8, 1, false, minb>(vol, flow, out, tg, H, W, src_n0, out_n0, st)   \
+             : launch_tile<4, 8, hh, NRT_NEAREST, 2, 8, 1, false, minb>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
+  NRT_TILE_OCC(4, 3, 5) NRT_TILE_OCC(4, 4, 5) NRT_TILE_OCC(5, 3, 6) NRT_TILE_OCC(5, 4, 6)
+#undef NRT_TILE_OCC
   if (rc == 1) return NRT_OK;                              // not launched: fall back
   *used = true;
   return rc;
