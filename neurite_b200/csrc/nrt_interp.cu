@@ -15,143 +15,10 @@
 //
 // Arithmetic is bit-faithful to the reference's unfused TF ops: every multiply and add is
 // a separate fp32 rounding (__fmul_rn/__fadd_rn), corner order is itertools.product order.
-#include <cuda.h>   // CUtensorMap (types only; the encode entry point is fetched at run time)
-
-#include "nrt_common.cuh"
+#include "nrt_interp.cuh"
 
 namespace nrt {
 
-struct Geo {
-  int S[3];        // full spatial extent of the source volume per axis (clip bounds)
-  int src_z0;      // global index of the first resident source plane (axis 0)
-  int src_n0;      // resident source planes
-  int C;
-  int has_fill;
-  float fill;
-  int32_t* err;    // device flag: corner outside the resident planes
-};
-
-// flat row-major index over the RESIDENT source (src_n0, S1, S2), reference sub2ind2d
-template <int D>
-__device__ __forceinline__ int flat_index(const Geo& g, const int (&sub)[D]) {
-  int ndx = sub[0];
-#pragma unroll
-  for (int d = 1; d < D; ++d) ndx = ndx * g.S[d] + sub[d];
-  return ndx;
-}
-
-__device__ __forceinline__ int to_resident(const Geo& g, int i) {
-  int l = i - g.src_z0;
-  if (l < 0 || l >= g.src_n0) {
-    if (g.err) atomicOr(g.err, 1);
-    l = min(max(l, 0), g.src_n0 - 1);
-  }
-  return l;
-}
-
-template <int D>
-__device__ __forceinline__ bool out_of_bounds(const Geo& g, const float (&loc)[D]) {
-  bool oob = false;
-#pragma unroll
-  for (int d = 0; d < D; ++d) oob = oob || (loc[d] < 0.0f) || (loc[d] > (float)(g.S[d] - 1));
-  return oob;
-}
-
-// Corner indices (flat, resident) and weights of one output point.
-template <int D, int METHOD>
-struct Corners {
-  int idx[METHOD == NRT_LINEAR ? (1 << D) : 1];
-  float w[METHOD == NRT_LINEAR ? (1 << D) : 1];
-};
-
-template <int D, int METHOD>
-__device__ __forceinline__ void setup_point(const Geo& g, const float (&loc)[D], Corners<D, METHOD>& k) {
-  if (METHOD == NRT_LINEAR) {
-    Axis a[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) a[d] = axis_linear(loc[d], (float)(g.S[d] - 1), g.S[d] - 1);
-    a[0].i0 = to_resident(g, a[0].i0);
-    a[0].i1 = to_resident(g, a[0].i1);
-#pragma unroll
-    for (int c = 0; c < (1 << D); ++c) {
-      int sub[D];
-      float w = 0.f;
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const int bit = (c >> (D - 1 - d)) & 1;          // first axis = most significant
-        sub[d] = bit ? a[d].i1 : a[d].i0;
-        const float wd = bit ? a[d].whi : a[d].wlo;
-        w = (d == 0) ? wd : __fmul_rn(w, wd);             // prod_n: ((w0*w1)*w2)
-      }
-      k.idx[c] = flat_index<D>(g, sub);
-      k.w[c] = w;
-    }
-  } else {
-    int sub[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) sub[d] = axis_nearest(loc[d], g.S[d] - 1);
-    sub[0] = to_resident(g, sub[0]);
-    k.idx[0] = flat_index<D>(g, sub);
-    k.w[0] = 1.f;
-  }
-}
-
-// channels [c0, c0+VEC) of one point from precomputed corners -- global-memory gather
-template <int D, int VEC, int METHOD>
-__device__ __forceinline__ void gather_point(const float* __restrict__ vol, const Geo& g,
-                                             const Corners<D, METHOD>& k, bool oob, int c0, float (&res)[VEC]) {
-  if (METHOD == NRT_LINEAR) {
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) res[v] = 0.0f;
-#pragma unroll
-    for (int c = 0; c < (1 << D); ++c) {
-      const size_t off = (size_t)k.idx[c] * g.C + c0;
-      const float w = k.w[c];
-      if (VEC == 4) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(vol + off));
-        res[0] = __fadd_rn(res[0], __fmul_rn(w, q.x));
-        res[1 % VEC] = __fadd_rn(res[1 % VEC], __fmul_rn(w, q.y));
-        res[2 % VEC] = __fadd_rn(res[2 % VEC], __fmul_rn(w, q.z));
-        res[3 % VEC] = __fadd_rn(res[3 % VEC], __fmul_rn(w, q.w));
-      } else {
-        res[0] = __fadd_rn(res[0], __fmul_rn(w, __ldg(vol + off)));
-      }
-    }
-  } else {
-    const size_t off = (size_t)k.idx[0] * g.C + c0;
-    if (VEC == 4) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(vol + off));
-      res[0] = q.x; res[1 % VEC] = q.y; res[2 % VEC] = q.z; res[3 % VEC] = q.w;
-    } else {
-      res[0] = __ldg(vol + off);
-    }
-  }
-  if (g.has_fill) {
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) res[v] = apply_fill(res[v], oob, g.fill);
-  }
-}
-
-// One output point: VEC == 4 -> this thread's 4-channel chunk [c0, c0+4);
-//                   VEC == 1 -> all C channels (corner setup is done once per point).
-template <int D, int VEC, int METHOD>
-__device__ __forceinline__ void sample_store(const float* __restrict__ vol, const Geo& g,
-                                             const float (&loc)[D], int c0, float* __restrict__ dst) {
-  Corners<D, METHOD> k;
-  setup_point<D, METHOD>(g, loc, k);
-  const bool oob = g.has_fill ? out_of_bounds<D>(g, loc) : false;
-  if (VEC == 4) {
-    float r[VEC];
-    gather_point<D, VEC, METHOD>(vol, g, k, oob, c0, r);
-    *reinterpret_cast<float4*>(dst + c0) = make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]);
-  } else {
-    for (int c = 0; c < g.C; ++c) {
-      float r[VEC];
-      gather_point<D, VEC, METHOD>(vol, g, k, oob, c, r);
-      dst[c] = r[0];
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------------
 // generic kernels
@@ -463,19 +330,18 @@ __device__ __forceinline__ float trilerp(const float (&v)[8], float wz0, float w
   return r;
 }
 
-// the same, split: corner weights once per voxel, accumulation once per channel
-__device__ __forceinline__ void corner_weights(float wz0, float wz1, float wy0, float wy1, float wx0, float wx1,
-                                               float (&k)[8]) {
-  const float w00 = __fmul_rn(wz0, wy0), w01 = __fmul_rn(wz0, wy1);
-  const float w10 = __fmul_rn(wz1, wy0), w11 = __fmul_rn(wz1, wy1);
-  k[0] = __fmul_rn(w00, wx0); k[1] = __fmul_rn(w00, wx1); k[2] = __fmul_rn(w01, wx0); k[3] = __fmul_rn(w01, wx1);
-  k[4] = __fmul_rn(w10, wx0); k[5] = __fmul_rn(w10, wx1); k[6] = __fmul_rn(w11, wx0); k[7] = __fmul_rn(w11, wx1);
-}
-__device__ __forceinline__ float acc8(const float (&k)[8], const float (&v)[8]) {
-  float r = __fadd_rn(0.f, __fmul_rn(k[0], v[0]));
+
+// CC channels of one voxel, as one vector store where the alignment allows it
+template <int CC>
+__device__ __forceinline__ void store_channels(float* __restrict__ op, const float (&res)[CC]) {
+  if (CC == 4) {
+    *reinterpret_cast<float4*>(op) = make_float4(res[0], res[1 % CC], res[2 % CC], res[3 % CC]);
+  } else if (CC == 2) {
+    *reinterpret_cast<float2*>(op) = make_float2(res[0], res[1 % CC]);
+  } else {
 #pragma unroll
-  for (int c = 1; c < 8; ++c) r = __fadd_rn(r, __fmul_rn(k[c], v[c]));
-  return r;
+    for (int c = 0; c < CC; ++c) op[c] = res[c];
+  }
 }
 
 // general (any position, any flow) sample through global memory -- the semantics baseline
@@ -508,73 +374,21 @@ __device__ __forceinline__ void sample_global3(const float* __restrict__ volb, c
   }
 }
 
-__device__ __forceinline__ float fill_if_oob(const Geo& g, float res, float lz, float ly, float lx) {
-  const bool oob = (lz < 0.f) | (lz > (float)(g.S[0] - 1)) | (ly < 0.f) | (ly > (float)(g.S[1] - 1)) |
-                   (lx < 0.f) | (lx > (float)(g.S[2] - 1));
-  return apply_fill(res, oob, g.fill);
-}
-
-// Per-axis corner setup against the staged box.
-//   EDGE = false: the box does not overhang the volume on this axis, so a sample whose two
-//     corners are in the box satisfies 0 <= loc < max: clip() is the identity, i1 = i0 + 1
-//     and the second corner sits at a compile-time stride.
-//   EDGE = true: the reference's clip / min(i0+1, max) is applied first; the second corner's
-//     offset becomes a run-time 0-or-stride.
-// `c0` is clamped into the box so the (unconditional) shared-memory loads are always legal;
-// `ok` says whether they were the right addresses.
-template <bool EDGE, int BDIM>
-struct AxisBox {
-  int c0;        // first corner, box-relative, clamped
-  int d;         // (second corner - first corner) in elements of this axis (EDGE only)
-  float wlo, whi;
-  bool ok;
-  __device__ __forceinline__ void setup(float loc, int o, int lo, int hi, int maxi) {
-    if (!EDGE) {
-      const int i0 = __float2int_rd(loc);
-      const unsigned r = (unsigned)(i0 - o);
-      const unsigned c = min(r, (unsigned)(BDIM - 2));
-      ok = (c == r);
-      c0 = (int)c;
-      d = 1;
-      wlo = __fsub_rn(__fadd_rn((float)i0, 1.f), loc);
-    } else {
-      const float x = fminf(fmaxf(loc, 0.f), (float)maxi);
-      const int i0 = __float2int_rd(x);
-      const int i1 = min(i0 + 1, maxi);
-      ok = (i0 >= lo) & (i1 <= hi);
-      d = i1 - i0;                                   // 0 at the volume's far edge, else 1
-      c0 = min(max(i0 - o, 0), BDIM - 1 - d);        // c0 + d stays inside the box
-      wlo = __fsub_rn((float)i1, x);
-    }
-    whi = __fsub_rn(1.f, wlo);
-  }
-};
-
-template <bool EDGE, int BDIM>
-__device__ __forceinline__ int nearest_box(float loc, int o, int lo, int hi, int maxi, bool& ok) {
-  const int i = EDGE ? axis_nearest(loc, maxi) : __float2int_rn(loc);
-  if (EDGE) {
-    ok = ok & (i >= lo) & (i <= hi);
-    return min(max(i - o, 0), BDIM - 1);
-  }
-  const unsigned r = (unsigned)(i - o);
-  const unsigned c = min(r, (unsigned)(BDIM - 1));
-  ok = ok & (c == r);
-  return (int)c;
-}
-
-struct BoxBounds { int lo_z, hi_z, lo_y, hi_y, lo_x, hi_x; };
 
 // The rows of one staged tile owned by this warp.  Branch-free main loop: a voxel whose
 // corners are not all inside the staged box still runs the shared-memory arithmetic on a
-// clamped (legal, meaningless) address and is recorded in `slow`; it is recomputed through
-// global memory after the loop.  Without a divergent branch in the body the compiler can
-// overlap the LDS latency of one iteration with the multiply/add chain of the previous one.
-template <int TZ, int TY, int HALO, int NW, int METHOD, int U, bool EZ, bool EY, bool EX, int CC, bool ABS>
+// clamped (legal, meaningless) address; the thread only remembers THAT it happened (one
+// predicate for all its voxels) and re-checks its voxels after the loop, recomputing the
+// affected ones through global memory.  Without a divergent branch or mask bookkeeping in the
+// body the compiler can overlap the LDS latency of one iteration with the multiply/add chain
+// of the previous one.
+//   GENERAL = true : run-time `partial` (tile overhangs the output) and `has_fill` handling
+//   GENERAL = false: full tile, no fill value -- neither test exists in the loop
+template <int TZ, int TY, int HALO, int NW, int METHOD, int U, bool EZ, bool EY, bool EX, int CC, bool ABS, bool GENERAL>
 __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, const float* __restrict__ s_box,
                                           const float* __restrict__ volb, float* __restrict__ outb,
                                           const TileGeo& w, int x0, int y0, int z0l, int ox, int oy, int oz,
-                                          bool partial) {
+                                          bool partial_rt) {
   using Cfg = TileCfg<TZ, TY, HALO, CC>;
   constexpr int TX = Cfg::TX, BX = Cfg::BX, BY = Cfg::BY, BZ = Cfg::BZ;
   constexpr int ZSTEP = NW >= TY ? NW / TY : 1;          // planes between a warp's rows
@@ -585,6 +399,8 @@ __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, cons
   const int zs = NW >= TY ? wid / TY : 0;
   const int gz0 = w.out_z0 + z0l;
   const int gx = x0 + lane;
+  const bool partial = GENERAL && partial_rt;
+  const bool has_fill = GENERAL && g.has_fill;
   // with absolute locations the grid term is 0 (0 + x == x exactly): same instruction count
   const float fx = ABS ? 0.f : (float)gx;
   BoxBounds bb;
@@ -602,11 +418,11 @@ __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, cons
     const float zstep = ABS ? 0.f : (float)ZSTEP;
     const float* fl = s_flow + ((zs * TY + yy) * TX + lane) * 3;
     float* op = outb + (((size_t)(z0l + zs) * H + gy) * W + gx) * CC;
-    unsigned slow = 0;
+    bool all_ok = true;
     const float* fl0 = fl;
     float* op0 = op;
 #pragma unroll U
-    for (int z = zs, it = 0; z < TZ; z += ZSTEP, ++it, fl += ZSTEP * TY * TX * 3, op += (size_t)ZSTEP * H * W * CC, zf += zstep) {
+    for (int z = zs; z < TZ; z += ZSTEP, fl += ZSTEP * TY * TX * 3, op += (size_t)ZSTEP * H * W * CC, zf += zstep) {
       if (partial && z >= nz_out) break;
       const float lz = __fadd_rn(zf, fl[0]);
       const float ly = __fadd_rn(fy, fl[1]);
@@ -640,7 +456,7 @@ __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, cons
             res[c] = acc8(k, v);
           }
         }
-        slow |= ((az.ok & ay.ok & ax.ok) ? 0u : 1u) << it;
+        all_ok = all_ok & az.ok & ay.ok & ax.ok;
       } else {
         bool ok = true;
         const int cz = nearest_box<EZ, BZ>(lz, oz, bb.lo_z, bb.hi_z, g.S[0] - 1, ok);
@@ -648,35 +464,49 @@ __device__ __forceinline__ void tile_rows(const float* __restrict__ s_flow, cons
         const int cx = nearest_box<EX, BX>(lx, ox, bb.lo_x, bb.hi_x, W - 1, ok);
 #pragma unroll
         for (int c = 0; c < CC; ++c) res[c] = s_box[((cz * BY + cy) * BX + cx) * CC + c];
-        slow |= (ok ? 0u : 1u) << it;
+        all_ok = all_ok & ok;
       }
+      if (has_fill) {
 #pragma unroll
-      for (int c = 0; c < CC; ++c) {
-        if (g.has_fill) res[c] = fill_if_oob(g, res[c], lz, ly, lx);
-        op[c] = res[c];
+        for (int c = 0; c < CC; ++c) res[c] = fill_if_oob(g, res[c], lz, ly, lx);
       }
+      store_channels<CC>(op, res);
     }
-    while (slow) {                                     // rare: corners outside the staged box
-      const int it = __ffs(slow) - 1;
-      slow &= slow - 1;
-      const int z = zs + it * ZSTEP;
-      const float* f2 = fl0 + (size_t)it * ZSTEP * TY * TX * 3;
-      const float lz = __fadd_rn(ABS ? 0.f : (float)(gz0 + z), f2[0]);
-      const float ly = __fadd_rn(fy, f2[1]);
-      const float lx = __fadd_rn(fx, f2[2]);
-      float res[CC];
-      sample_global3<METHOD, CC>(volb, g, lz, ly, lx, res);
+    if (!all_ok) {                                     // rare: some corner of some voxel outside the staged box
+#pragma unroll 1
+      for (int z = zs, it = 0; z < nz_out; z += ZSTEP, ++it) {
+        const float* f2 = fl0 + (size_t)it * ZSTEP * TY * TX * 3;
+        const float lz = __fadd_rn(ABS ? 0.f : (float)(gz0 + z), f2[0]);
+        const float ly = __fadd_rn(fy, f2[1]);
+        const float lx = __fadd_rn(fx, f2[2]);
+        bool ok = true;
+        if (METHOD == NRT_LINEAR) {
+          AxisBox<EZ, BZ> az; AxisBox<EY, BY> ay; AxisBox<EX, BX> ax;           // the very test of the main loop
+          az.setup(lz, oz, bb.lo_z, bb.hi_z, g.S[0] - 1);
+          ay.setup(ly, oy, bb.lo_y, bb.hi_y, H - 1);
+          ax.setup(lx, ox, bb.lo_x, bb.hi_x, W - 1);
+          ok = az.ok & ay.ok & ax.ok;
+        } else {
+          (void)nearest_box<EZ, BZ>(lz, oz, bb.lo_z, bb.hi_z, g.S[0] - 1, ok);
+          (void)nearest_box<EY, BY>(ly, oy, bb.lo_y, bb.hi_y, H - 1, ok);
+          (void)nearest_box<EX, BX>(lx, ox, bb.lo_x, bb.hi_x, W - 1, ok);
+        }
+        if (ok) continue;                              // this one was computed from the box: keep it
+        float res[CC];
+        sample_global3<METHOD, CC>(volb, g, lz, ly, lx, res);
+        if (g.has_fill) {
 #pragma unroll
-      for (int c = 0; c < CC; ++c) {
-        if (g.has_fill) res[c] = fill_if_oob(g, res[c], lz, ly, lx);
-        op0[(size_t)it * ZSTEP * H * W * CC + c] = res[c];
+          for (int c = 0; c < CC; ++c) res[c] = fill_if_oob(g, res[c], lz, ly, lx);
+        }
+        store_channels<CC>(op0 + (size_t)it * ZSTEP * H * W * CC, res);
       }
     }
   }
 }
 
 // Process one staged tile.  Warp w owns row y = w % TY of planes z = w / TY, + NW/TY, ...
-// The per-axis EDGE flags are tile-uniform, so the dispatch below costs one uniform switch.
+// The per-axis EDGE flags are tile-uniform, so the dispatch below costs one uniform switch.  Tiles that overhang
+// the output and launches with a fill value take the one general variant (all edges, run-time checks).
 template <int TZ, int TY, int HALO, int NW, int METHOD, int U = 2, int CC = 1, bool ABS = false>
 __device__ __forceinline__ void compute_tile(const float* __restrict__ s_flow, const float* __restrict__ s_box,
                                              const float* __restrict__ volb, float* __restrict__ outb,
@@ -688,16 +518,17 @@ __device__ __forceinline__ void compute_tile(const float* __restrict__ s_flow, c
   const bool ey = !((oy >= 0) && (oy + Cfg::BY <= g.S[1]));
   const bool ex = !((ox >= 0) && (ox + Cfg::BX <= g.S[2]));
   const bool partial = (z0l + TZ > w.out_n0) || (y0 + TY > g.S[1]) || (x0 + Cfg::TX > g.S[2]);
-#define NRT_ROWS(a, b, c) tile_rows<TZ, TY, HALO, NW, METHOD, U, a, b, c, CC, ABS>(s_flow, s_box, volb, outb, w, x0, y0, z0l, ox, oy, oz, partial)
+#define NRT_ROWS(a, b, c, gen) tile_rows<TZ, TY, HALO, NW, METHOD, U, a, b, c, CC, ABS, gen>(s_flow, s_box, volb, outb, w, x0, y0, z0l, ox, oy, oz, partial)
+  if (partial || g.has_fill) { NRT_ROWS(true, true, true, true); return; }
   switch ((ez ? 4 : 0) | (ey ? 2 : 0) | (ex ? 1 : 0)) {
-    case 0: NRT_ROWS(false, false, false); break;
-    case 1: NRT_ROWS(false, false, true); break;
-    case 2: NRT_ROWS(false, true, false); break;
-    case 3: NRT_ROWS(false, true, true); break;
-    case 4: NRT_ROWS(true, false, false); break;
-    case 5: NRT_ROWS(true, false, true); break;
-    case 6: NRT_ROWS(true, true, false); break;
-    default: NRT_ROWS(true, true, true); break;
+    case 0: NRT_ROWS(false, false, false, false); break;
+    case 1: NRT_ROWS(false, false, true, false); break;
+    case 2: NRT_ROWS(false, true, false, false); break;
+    case 3: NRT_ROWS(false, true, true, false); break;
+    case 4: NRT_ROWS(true, false, false, false); break;
+    case 5: NRT_ROWS(true, false, true, false); break;
+    case 6: NRT_ROWS(true, true, false, false); break;
+    default: NRT_ROWS(true, true, true, false); break;
   }
 #undef NRT_ROWS
 }
@@ -707,69 +538,59 @@ __device__ __forceinline__ void compute_tile(const float* __restrict__ s_flow, c
 // with only 8-16 voxels per thread the prologue is a visible part of the instruction count.
 // ABS = the 'flow' tensor holds absolute sample locations (interpn on the volume's own grid): compile-time, so
 // that the displacement kernels carry no trace of it
-// MINB = CTAs per SM the register allocation is capped for (1 = uncapped)
-template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8, int CC = 1, bool ABS = false, int MINB = 1>
-__global__ void __launch_bounds__(NW * 32, MINB)
+template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8, int CC = 1, bool ABS = false>
+__global__ void __launch_bounds__(NW * 32)
 warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
                    const __grid_constant__ CUtensorMap tm_flow,
-                   const float* __restrict__ vol, const float* __restrict__ flow,
-                   float* __restrict__ out, TileGeo w, int follow) {
+                   const float* __restrict__ vol, float* __restrict__ out, TileGeo w, int follow) {
   using Cfg = TileCfg<TZ, TY, HALO, CC>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* s_flow = reinterpret_cast<float*>(smem_raw);                       // [TZ][TY][TX][3]
   float* s_box = s_flow + Cfg::FLOW_ELEMS;                                  // [BZ][BY][BX]
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_box + Cfg::BOX_ELEMS);
-  int* s_org = reinterpret_cast<int*>(bar + 1);                             // box origin (global coords)
   const int b = blockIdx.z / w.ntz;
   const int x0 = blockIdx.x * Cfg::TX, y0 = blockIdx.y * TY, z0l = (blockIdx.z - b * w.ntz) * TZ;
-  if (threadIdx.x < 32) {
-    if (threadIdx.x == 0) {
-      // speculative load: flow tile + the box centred on the tile itself (right for small or
-      // incoherent displacements), issued before anything is known about the flow
-      mbar_init(bar, 1);
-      fence_mbar_init();
-      mbar_expect_tx(bar, (uint32_t)((Cfg::FLOW_ELEMS + Cfg::BOX_ELEMS) * sizeof(float)));
-      tma_load_4d(s_flow, &tm_flow, bar, x0 * 3, y0, z0l, b);
-      tma_load_4d(s_box, &tm_vol, bar, (x0 - Cfg::HX) * CC, y0 - HALO, w.out_z0 + z0l - HALO - w.g.src_z0, b);
+  if (threadIdx.x == 0) {
+    // speculative load: flow tile + the box centred on the tile itself (right for small or
+    // incoherent displacements), issued before anything is known about the flow
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(bar, (uint32_t)((Cfg::FLOW_ELEMS + Cfg::BOX_ELEMS) * sizeof(float)));
+    tma_load_4d(s_flow, &tm_flow, bar, x0 * 3, y0, z0l, b);
+    tma_load_4d(s_box, &tm_vol, bar, (x0 - Cfg::HX) * CC, y0 - HALO, w.out_z0 + z0l - HALO - w.g.src_z0, b);
+  }
+  __syncthreads();                                   // the barrier is initialised
+  mbar_wait(bar, 0);
+  // Where does the tile land ON AVERAGE?  Every warp computes the mean shift over the same 3x3x3 lattice of
+  // the STAGED flow tile (27 lanes, one LDS each: no global latency, no block-wide hand-off; all warps get the
+  // same numbers, so the decision is block-uniform).  A large coherent displacement means the speculative box is
+  // useless; the box is then re-staged around the displaced position, so that the halo only has to cover the
+  // variation of the flow inside the tile.  An incoherent flow averages out and keeps the speculative box.
+  int sz = 0, sy = 0, sx = 0;
+  if (follow) {
+    float mz = 0.f, my = 0.f, mx = 0.f;
+    const int l = threadIdx.x & 31;
+    if (l < 27) {
+      const int jz = l / 9, jy = (l / 3) % 3, jx = l % 3;
+      const int cz = min(z0l + (jz * (TZ - 1)) / 2, w.out_n0 - 1);
+      const int cy = min(y0 + (jy * (TY - 1)) / 2, w.g.S[1] - 1);
+      const int cx = min(x0 + (jx * (Cfg::TX - 1)) / 2, w.g.S[2] - 1);
+      const float* f = s_flow + (((cz - z0l) * TY + (cy - y0)) * Cfg::TX + (cx - x0)) * 3;
+      const float lim = 1048576.f;
+      const float gz_ = ABS ? (float)(w.out_z0 + cz) : 0.f, gy_ = ABS ? (float)cy : 0.f, gx_ = ABS ? (float)cx : 0.f;
+      mz = fminf(fmaxf(f[0] - gz_, -lim), lim);
+      my = fminf(fmaxf(f[1] - gy_, -lim), lim);
+      mx = fminf(fmaxf(f[2] - gx_, -lim), lim);
     }
-    // Meanwhile warp 0 looks at where the tile lands ON AVERAGE (mean shift over a 3x3x3
-    // lattice of its voxels, one lane each).  A large coherent displacement means the
-    // speculative box is useless; the box is then re-staged around the displaced position,
-    // so that the halo only has to cover the variation of the flow inside the tile.  An
-    // incoherent flow averages out and keeps the speculative box at no extra latency.
-    int sz = 0, sy = 0, sx = 0;
-    if (follow) {
-      float mz = 0.f, my = 0.f, mx = 0.f;
-      const int l = threadIdx.x;
-      if (l < 27) {
-        const int jz = l / 9, jy = (l / 3) % 3, jx = l % 3;
-        const int cz = min(z0l + (jz * (TZ - 1)) / 2, w.out_n0 - 1);
-        const int cy = min(y0 + (jy * (TY - 1)) / 2, w.g.S[1] - 1);
-        const int cx = min(x0 + (jx * (Cfg::TX - 1)) / 2, w.g.S[2] - 1);
-        const float* f = flow + ((((size_t)b * w.out_n0 + cz) * w.g.S[1] + cy) * w.g.S[2] + cx) * 3;
-        const float lim = 1048576.f;
-        const float gz_ = ABS ? (float)(w.out_z0 + cz) : 0.f, gy_ = ABS ? (float)cy : 0.f, gx_ = ABS ? (float)cx : 0.f;
-        mz = fminf(fmaxf(__ldg(f + 0) - gz_, -lim), lim);
-        my = fminf(fmaxf(__ldg(f + 1) - gy_, -lim), lim);
-        mx = fminf(fmaxf(__ldg(f + 2) - gx_, -lim), lim);
-      }
-      mz = warp_sum(mz) * (1.f / 27.f); my = warp_sum(my) * (1.f / 27.f); mx = warp_sum(mx) * (1.f / 27.f);
-      // dead band: 2 voxels in z/y, 4 in x (the TMA needs the x start 16-byte aligned and
-      // the x halo is already rounded up to 4)
-      if (fabsf(mz) >= 2.f || fabsf(my) >= 2.f || fabsf(mx) >= 4.f) {
-        sz = __float2int_rn(mz); sy = __float2int_rn(my); sx = __float2int_rn(mx * 0.25f) * 4;
-      }
-    }
-    if (threadIdx.x == 0) {
-      s_org[0] = w.out_z0 + z0l - HALO + sz; s_org[1] = y0 - HALO + sy; s_org[2] = x0 - Cfg::HX + sx;
-      s_org[3] = (sz | sy | sx) != 0;
+    mz = warp_sum(mz) * (1.f / 27.f); my = warp_sum(my) * (1.f / 27.f); mx = warp_sum(mx) * (1.f / 27.f);
+    // dead band: 2 voxels in z/y, 4 in x (the TMA needs the x start 16-byte aligned and
+    // the x halo is already rounded up to 4)
+    if (fabsf(mz) >= 2.f || fabsf(my) >= 2.f || fabsf(mx) >= 4.f) {
+      sz = __float2int_rn(mz); sy = __float2int_rn(my); sx = __float2int_rn(mx * 0.25f) * 4;
     }
   }
-  __syncthreads();
-  const int oz = s_org[0], oy = s_org[1], ox = s_org[2];
-  const bool restage = s_org[3] != 0;
-  mbar_wait(bar, 0);
-  if (restage) {                                   // block-uniform
+  const int oz = w.out_z0 + z0l - HALO + sz, oy = y0 - HALO + sy, ox = x0 - Cfg::HX + sx;
+  if ((sz | sy | sx) != 0) {                         // block-uniform
     // every thread must have observed phase 0 before phase 1 is armed: an mbarrier waiter
     // can be at most one phase behind (parity aliasing), found with compute-sanitizer
     __syncthreads();
@@ -969,23 +790,26 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int encode_f32_4d(CUtensorMap* tm, const void* base, const uint64_t dims[4], const uint32_t box[4]) {
+int encode_f32_tiled(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error(NRT_E_NODEV, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t gdim[4], gstr[3];
-  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
-  for (int i = 0; i < 4; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
   gstr[0] = dims[0] * sizeof(float);
-  gstr[1] = gstr[0] * dims[1];
-  gstr[2] = gstr[1] * dims[2];
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstr, bx, es,
+  for (int i = 1; i < rank - 1; ++i) gstr[i] = gstr[i - 1] * dims[i];
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(NRT_E_LAUNCH, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
   return NRT_OK;
 }
 
-static int env_int(const char* name, int dflt) {
+static int encode_f32_4d(CUtensorMap* tm, const void* base, const uint64_t dims[4], const uint32_t box[4]) {
+  return encode_f32_tiled(tm, base, 4, dims, box);
+}
+
+int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return (s && *s) ? atoi(s) : dflt;
 }
@@ -1032,7 +856,7 @@ int warp3d_bwd_tile(const float* vol, const float* flow, const float* gout, floa
   return check_launch("warp3d_bwd_tile_kernel");
 }
 
-template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8, int CC = 1, bool ABS = false, int MINB = 1>
+template <int TZ, int TY, int HALO, int METHOD, int U = 2, int NW = 8, int CC = 1, bool ABS = false>
 static int launch_tile(const float* vol, const float* flow, float* out, TileGeo tg, int H, int W, int src_n0,
                        int out_n0, cudaStream_t st) {
   using Cfg = TileCfg<TZ, TY, HALO, CC>;
@@ -1049,12 +873,12 @@ static int launch_tile(const float* vol, const float* flow, float* out, TileGeo 
   if (rc != NRT_OK) return rc;
   rc = encode_f32_4d(&tmf, flow, fd, fb);
   if (rc != NRT_OK) return rc;
-  auto kern = warp3d_tile_kernel<TZ, TY, HALO, METHOD, U, NW, CC, ABS, MINB>;
+  auto kern = warp3d_tile_kernel<TZ, TY, HALO, METHOD, U, NW, CC, ABS>;
   // set on every launch: the attribute is per device and the call costs ~1 us of host time
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM) != cudaSuccess)
     return check_launch("cudaFuncSetAttribute(warp3d_tile)");
   const dim3 grid(tg.ntx, tg.nty, tg.ntz * tg.B);
-  kern<<<grid, NW * 32, Cfg::SMEM, st>>>(tmv, tmf, vol, flow, out, tg, env_int("NRT_WARP_FOLLOW", 1));
+  kern<<<grid, NW * 32, Cfg::SMEM, st>>>(tmv, tmf, vol, out, tg, env_int("NRT_WARP_FOLLOW", 1));
   return check_launch("warp3d_tile_kernel");
 }
 
@@ -1118,14 +942,12 @@ static int try_tile_path(const float* vol, const float* flow, float* out, int B,
   *used = false;
   const int H = shape[1], W = shape[2];
   if (env_int("NRT_WARP_TILE", 1) == 0) return NRT_OK;
-  if (W % 4 != 0 || !aligned16(vol) || !aligned16(flow) || W < 32) return NRT_OK;
+  if (W % 4 != 0 || !aligned16(vol) || !aligned16(flow) || !aligned16(out) || W < 32) return NRT_OK;
   // tile shapes (TZ x TY x 32) and halos built: the default 8x8x32 runs 4 CTAs per SM (best
   // measured on B200, profiles/); `halo` picks the smallest built halo that covers it.
-  // 0: 8x16x32, 2: 8x8x32 (default), 3: 4x8x32; 4 / 5: 4x8x32 with the registers capped for 5 / 6 CTAs per SM
-  // (experiment for the tile-load barrier stall; halos 3 and 4 only)
+  // 2: 8x8x32 (default), 3: 4x8x32
   int cfg = env_int("NRT_WARP_TILE_CFG", 2);
-  if (cfg != 0 && cfg != 2 && cfg != 3 && cfg != 4 && cfg != 5) cfg = 2;
-  if ((cfg == 4 || cfg == 5) && halo > 4) cfg = 3;
+  if (cfg != 2 && cfg != 3) cfg = 2;
   if (halo <= 0) halo = 3;
   const int hsel = halo <= 3 ? 3 : (halo <= 4 ? 4 : (halo <= 6 ? 6 : 8));
   TileGeo tg;
@@ -1170,17 +992,9 @@ static int try_tile_path(const float* vol, const float* flow, float* out, int B,
     rc = method == NRT_LINEAR                                                                            \
              ? launch_tile<tz, ty, hh, NRT_LINEAR>(vol, flow, out, tg, H, W, src_n0, out_n0, st)         \
              : launch_tile<tz, ty, hh, NRT_NEAREST>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
-  NRT_TILE_CASE(0, 8, 16, 3) NRT_TILE_CASE(0, 8, 16, 4) NRT_TILE_CASE(0, 8, 16, 6) NRT_TILE_CASE(0, 8, 16, 8)
   NRT_TILE_CASE(2, 8, 8, 3) NRT_TILE_CASE(2, 8, 8, 4) NRT_TILE_CASE(2, 8, 8, 6) NRT_TILE_CASE(2, 8, 8, 8)
   NRT_TILE_CASE(3, 4, 8, 3) NRT_TILE_CASE(3, 4, 8, 4) NRT_TILE_CASE(3, 4, 8, 6) NRT_TILE_CASE(3, 4, 8, 8)
 #undef NRT_TILE_CASE
-#define NRT_TILE_OCC(i, hh, minb)                                                                                  \
-  if (cfg == (i) && hsel == (hh))                                                                                  \
-    rc = method == NRT_LINEAR                                                                                      \
-             ? launch_tile<4, 8, hh, NRT_LINEAR, 2, 8, 1, false, minb>(vol, flow, out, tg, H, W, src_n0, out_n0, st)   \
-             : launch_tile<4, 8, hh, NRT_NEAREST, 2, 8, 1, false, minb>(vol, flow, out, tg, H, W, src_n0, out_n0, st);
-  NRT_TILE_OCC(4, 3, 5) NRT_TILE_OCC(4, 4, 5) NRT_TILE_OCC(5, 3, 6) NRT_TILE_OCC(5, 4, 6)
-#undef NRT_TILE_OCC
   if (rc == 1) return NRT_OK;                              // not launched: fall back
   *used = true;
   return rc;
@@ -1256,6 +1070,13 @@ int nrt_warp_f32(const float* vol, const float* flow, float* out, int B, const i
               "slab too large for int32 indexing");
   if (B == 0 || out_n0 == 0) return NRT_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (D == 3 && C >= 2 && (C > 4 || env_int("NRT_MARCH_SMALLC", 0))) {
+    // many channels: z-marching ring kernel (all channels of a voxel side by side in shared memory)
+    bool used = false;
+    rc = warp3d_march(vol, flow, out, B, shape, C, method, has_fill, fill, src_z0, src_n0, out_z0, out_n0,
+                      halo, err_flag, st, &used);
+    if (rc != NRT_OK || used) return rc;
+  }
   if (D == 3 && C <= 4) {
     bool used = false;
     rc = try_tile_path(vol, flow, out, B, shape, C, method, has_fill, fill, src_z0, src_n0, out_z0, out_n0,
