@@ -90,6 +90,16 @@ NRT_API int nrt_warp_f32(const float* vol, const float* flow, float* out, int B,
                  const int32_t* shape, int D, int C, int method, int has_fill, float fill,
                  int src_z0, int src_n0, int out_z0, int out_n0, int halo,
                  int32_t* err_flag, void* stream);
+/* The same warp on batch items that are not densely packed: *_batch_stride = elements between consecutive batch
+ * items of vol / flow / out (0 = dense).  This is what lets a z-slab-sharded warp (call sites
+ * neurite/tf/models.py:806-807) produce the INTERIOR planes of a slab from the rank's own planes while the halo
+ * planes of the neighbours are still in flight, and the boundary planes afterwards, all inside one [B, planes, ...]
+ * buffer: plane sub-ranges of a batched slab are strided in the batch dimension. */
+NRT_API int nrt_warp_strided_f32(const float* vol, const float* flow, float* out, int B,
+                 const int32_t* shape, int D, int C, int method, int has_fill, float fill,
+                 int src_z0, int src_n0, int out_z0, int out_n0, int halo,
+                 int32_t* err_flag, int64_t vol_batch_stride, int64_t flow_batch_stride,
+                 int64_t out_batch_stride, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * resize -- replaces neurite/tf/utils/utils.py:223-265 (resize/zoom) and the per-batch

@@ -28,6 +28,9 @@ SIGNATURES = {
     'nrt_warp_f32': (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, P_I32, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_int, ctypes.c_int, c_f32, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
+    'nrt_warp_strided_f32': (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, P_I32, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_int, c_f32, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_i64, c_i64, c_i64, c_vp]),
     'nrt_resize_f32': (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, P_I32, P_I32, ctypes.c_int, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]),
     'nrt_dice_workspace_bytes': (c_i64, [ctypes.c_int, ctypes.c_int]),

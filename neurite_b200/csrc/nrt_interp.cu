@@ -44,6 +44,7 @@ struct WarpGeo {
   Geo g;
   int out_z0, out_n0;   // produced planes of axis 0
   int64_t src_batch_stride, out_vox;   // elements per batch item of vol; voxels per batch item of out
+  int64_t flow_bstride, out_bstride;   // elements between batch items of flow / out (dense: out_vox*D, out_vox*C)
   int B;
 };
 
@@ -65,9 +66,12 @@ warp_generic_kernel(const float* __restrict__ vol, const float* __restrict__ flo
     for (int d = D - 1; d >= 1; --d) { coord[d] = rem % g.S[d]; rem /= g.S[d]; }
     coord[0] = rem + w.out_z0;
     float loc[D];
+    const int64_t vox = pv - (int64_t)b * w.out_vox;
+    const float* fl = flow + (size_t)b * w.flow_bstride + vox * D;
 #pragma unroll
-    for (int d = 0; d < D; ++d) loc[d] = __fadd_rn((float)coord[d], __ldg(flow + pv * D + d));
-    sample_store<D, VEC, METHOD>(vol + (size_t)b * w.src_batch_stride, g, loc, c0, out + pv * g.C);
+    for (int d = 0; d < D; ++d) loc[d] = __fadd_rn((float)coord[d], __ldg(fl + d));
+    sample_store<D, VEC, METHOD>(vol + (size_t)b * w.src_batch_stride, g, loc, c0,
+                                 out + (size_t)b * w.out_bstride + vox * g.C);
   }
 }
 
@@ -294,6 +298,7 @@ struct TileGeo {
   int B;
   int ntz, nty, ntx;     // tiles per axis
   int64_t src_batch_stride, out_vox;
+  int64_t flow_bstride, out_bstride;   // elements between batch items of flow / out
   int abs_loc;           // 1: the 'flow' tensor holds absolute sample locations (interpn on the volume's own grid)
 };
 
@@ -601,7 +606,7 @@ warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
     mbar_wait(bar, 1);
   }
   compute_tile<TZ, TY, HALO, NW, METHOD, U, CC, ABS>(s_flow, s_box, vol + (size_t)b * w.src_batch_stride,
-                                                out + (size_t)b * w.out_vox * CC, w, x0, y0, z0l, ox, oy, oz);
+                                                out + (size_t)b * w.out_bstride, w, x0, y0, z0l, ox, oy, oz);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -790,7 +795,8 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-int encode_f32_tiled(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+int encode_f32_tiled(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint32_t* box,
+                     uint64_t last_stride_elems) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error(NRT_E_NODEV, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[5], gstr[4];
@@ -798,6 +804,7 @@ int encode_f32_tiled(CUtensorMap* tm, const void* base, int rank, const uint64_t
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
   gstr[0] = dims[0] * sizeof(float);
   for (int i = 1; i < rank - 1; ++i) gstr[i] = gstr[i - 1] * dims[i];
+  if (last_stride_elems) gstr[rank - 2] = last_stride_elems * sizeof(float);     // batch items not densely packed
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -805,8 +812,9 @@ int encode_f32_tiled(CUtensorMap* tm, const void* base, int rank, const uint64_t
   return NRT_OK;
 }
 
-static int encode_f32_4d(CUtensorMap* tm, const void* base, const uint64_t dims[4], const uint32_t box[4]) {
-  return encode_f32_tiled(tm, base, 4, dims, box);
+static int encode_f32_4d(CUtensorMap* tm, const void* base, const uint64_t dims[4], const uint32_t box[4],
+                         uint64_t batch_stride_elems = 0) {
+  return encode_f32_tiled(tm, base, 4, dims, box, batch_stride_elems);
 }
 
 int env_int(const char* name, int dflt) {
@@ -829,6 +837,7 @@ int warp3d_bwd_tile(const float* vol, const float* flow, const float* gout, floa
   tg.out_z0 = 0; tg.out_n0 = D0; tg.B = B; tg.abs_loc = 0;
   tg.ntz = (D0 + TZ - 1) / TZ; tg.nty = (H + TY - 1) / TY; tg.ntx = (W + Cfg::TX - 1) / Cfg::TX;
   tg.src_batch_stride = (int64_t)D0 * H * W; tg.out_vox = tg.src_batch_stride;
+  tg.flow_bstride = tg.out_vox * 3; tg.out_bstride = tg.out_vox;
   if ((int64_t)B * tg.ntz > 65535 || tg.nty > 65535) return NRT_OK;
   constexpr size_t SMEM = (size_t)(Cfg::FLOW_ELEMS + 2 * Cfg::BOX_ELEMS + TZ * TY * Cfg::TX) * sizeof(float) + 16;
   CUtensorMap tmv, tmf, tmg;
@@ -863,15 +872,14 @@ static int launch_tile(const float* vol, const float* flow, float* out, TileGeo 
   tg.ntz = (out_n0 + TZ - 1) / TZ; tg.nty = (H + TY - 1) / TY; tg.ntx = (W + Cfg::TX - 1) / Cfg::TX;
   if ((int64_t)tg.B * tg.ntz > 65535 || tg.nty > 65535 || Cfg::SMEM > 227 * 1024) return 1;   // caller falls back
   tg.g.C = CC;
-  tg.src_batch_stride = (int64_t)src_n0 * H * W * CC;
   CUtensorMap tmv, tmf;
   const uint64_t vd[4] = {(uint64_t)W * CC, (uint64_t)H, (uint64_t)src_n0, (uint64_t)tg.B};
   const uint32_t vb[4] = {(uint32_t)(Cfg::BX * CC), (uint32_t)Cfg::BY, (uint32_t)Cfg::BZ, 1};
   const uint64_t fd[4] = {(uint64_t)W * 3, (uint64_t)H, (uint64_t)out_n0, (uint64_t)tg.B};
   const uint32_t fb[4] = {(uint32_t)Cfg::TX * 3, (uint32_t)TY, (uint32_t)TZ, 1};
-  int rc = encode_f32_4d(&tmv, vol, vd, vb);
+  int rc = encode_f32_4d(&tmv, vol, vd, vb, (uint64_t)tg.src_batch_stride);
   if (rc != NRT_OK) return rc;
-  rc = encode_f32_4d(&tmf, flow, fd, fb);
+  rc = encode_f32_4d(&tmf, flow, fd, fb, (uint64_t)tg.flow_bstride);
   if (rc != NRT_OK) return rc;
   auto kern = warp3d_tile_kernel<TZ, TY, HALO, METHOD, U, NW, CC, ABS>;
   // set on every launch: the attribute is per device and the call costs ~1 us of host time
@@ -884,7 +892,7 @@ static int launch_tile(const float* vol, const float* flow, float* out, TileGeo 
 
 template <int D, int METHOD>
 static int launch_warp_generic(const float* vol, const float* flow, float* out, const WarpGeo& wg, cudaStream_t st) {
-  const bool vec = (wg.g.C % 4 == 0) && aligned16(vol) && aligned16(out);
+  const bool vec = (wg.g.C % 4 == 0) && aligned16(vol) && aligned16(out) && ((wg.src_batch_stride | wg.out_bstride) & 3) == 0;
   const int64_t total = (int64_t)wg.B * wg.out_vox * (vec ? wg.g.C / 4 : 1);
   if (total == 0) return NRT_OK;
   const int grid = (int)imin64((total + 255) / 256, (int64_t)sm_count() * 32);
@@ -938,7 +946,8 @@ static int check_common(int D, int C, int method) {
 
 static int try_tile_path(const float* vol, const float* flow, float* out, int B, const int32_t* shape, int C,
                          int method, int has_fill, float fill, int src_z0, int src_n0, int out_z0,
-                         int out_n0, int halo, int32_t* err_flag, cudaStream_t st, bool* used, int abs_loc = 0) {
+                         int out_n0, int halo, int32_t* err_flag, cudaStream_t st, bool* used, int abs_loc = 0,
+                         int64_t vbs = 0, int64_t fbs = 0, int64_t obs = 0) {
   *used = false;
   const int H = shape[1], W = shape[2];
   if (env_int("NRT_WARP_TILE", 1) == 0) return NRT_OK;
@@ -957,8 +966,11 @@ static int try_tile_path(const float* vol, const float* flow, float* out, int B,
   tg.out_z0 = out_z0; tg.out_n0 = out_n0; tg.B = B;
   tg.ntz = tg.nty = tg.ntx = 0;
   tg.abs_loc = abs_loc;
-  tg.src_batch_stride = (int64_t)src_n0 * H * W;
   tg.out_vox = (int64_t)out_n0 * H * W;
+  tg.src_batch_stride = vbs ? vbs : (int64_t)src_n0 * H * W * C;
+  tg.flow_bstride = fbs ? fbs : tg.out_vox * 3;
+  tg.out_bstride = obs ? obs : tg.out_vox * C;
+  if ((tg.src_batch_stride | tg.flow_bstride | tg.out_bstride) & 3) return NRT_OK;   // TMA strides: multiples of 16 bytes
   int rc = 1;
   if (abs_loc) {
     // absolute locations: instantiated for the default tile shapes only (other shapes: generic gather kernel)
@@ -1048,9 +1060,9 @@ int nrt_interpn_grid_f32(const float* vol, const float* loc, float* out, const i
   return nrt_interpn_f32(vol, shape, 3, C, loc, nvox, method, has_fill, fill, out, stream);
 }
 
-int nrt_warp_f32(const float* vol, const float* flow, float* out, int B, const int32_t* shape, int D,
-                 int C, int method, int has_fill, float fill, int src_z0, int src_n0, int out_z0,
-                 int out_n0, int halo, int32_t* err_flag, void* stream) {
+static int warp_impl(const float* vol, const float* flow, float* out, int B, const int32_t* shape, int D,
+                     int C, int method, int has_fill, float fill, int src_z0, int src_n0, int out_z0,
+                     int out_n0, int halo, int32_t* err_flag, int64_t vbs, int64_t fbs, int64_t obs, void* stream) {
   int rc = check_common(D, C, method);
   if (rc != NRT_OK) return rc;
   NRT_REQUIRE(vol && flow && out && shape, NRT_E_ARG, "null pointer");
@@ -1068,29 +1080,49 @@ int nrt_warp_f32(const float* vol, const float* flow, float* out, int B, const i
               "output planes [%d,%d) outside [0,%d)", out_z0, out_z0 + out_n0, shape[0]);
   NRT_REQUIRE(plane * src_n0 <= 0x7fffffffLL && plane * out_n0 * 3 <= 0x7fffffffLL * 4, NRT_E_SIZE,
               "slab too large for int32 indexing");
+  NRT_REQUIRE(vbs >= 0 && fbs >= 0 && obs >= 0, NRT_E_ARG, "negative batch stride");
+  NRT_REQUIRE((vbs == 0 || vbs >= plane * src_n0 * C) && (fbs == 0 || fbs >= plane * out_n0 * D) &&
+              (obs == 0 || obs >= plane * out_n0 * C), NRT_E_ARG, "batch stride smaller than one batch item");
   if (B == 0 || out_n0 == 0) return NRT_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (D == 3 && C >= 2 && (C > 4 || env_int("NRT_MARCH_SMALLC", 0))) {
     // many channels: z-marching ring kernel (all channels of a voxel side by side in shared memory)
     bool used = false;
     rc = warp3d_march(vol, flow, out, B, shape, C, method, has_fill, fill, src_z0, src_n0, out_z0, out_n0,
-                      halo, err_flag, st, &used);
+                      halo, err_flag, vbs, fbs, obs, st, &used);
     if (rc != NRT_OK || used) return rc;
   }
   if (D == 3 && C <= 4) {
     bool used = false;
     rc = try_tile_path(vol, flow, out, B, shape, C, method, has_fill, fill, src_z0, src_n0, out_z0, out_n0,
-                       halo, err_flag, st, &used);
+                       halo, err_flag, st, &used, 0, vbs, fbs, obs);
     if (rc != NRT_OK || used) return rc;
   }
   wg.g.src_z0 = src_z0; wg.g.src_n0 = src_n0; wg.g.C = C;
   wg.g.has_fill = has_fill; wg.g.fill = fill; wg.g.err = err_flag;
   wg.out_z0 = out_z0; wg.out_n0 = out_n0; wg.B = B;
-  wg.src_batch_stride = plane * src_n0 * C;
   wg.out_vox = plane * out_n0;
+  wg.src_batch_stride = vbs ? vbs : plane * src_n0 * C;
+  wg.flow_bstride = fbs ? fbs : wg.out_vox * D;
+  wg.out_bstride = obs ? obs : wg.out_vox * C;
 #define CALL(DD, MM) launch_warp_generic<DD, MM>(vol, flow, out, wg, st)
   NRT_DISPATCH_D_METHOD(D, method, CALL);
 #undef CALL
+}
+
+int nrt_warp_f32(const float* vol, const float* flow, float* out, int B, const int32_t* shape, int D,
+                 int C, int method, int has_fill, float fill, int src_z0, int src_n0, int out_z0,
+                 int out_n0, int halo, int32_t* err_flag, void* stream) {
+  return warp_impl(vol, flow, out, B, shape, D, C, method, has_fill, fill, src_z0, src_n0, out_z0, out_n0, halo,
+                   err_flag, 0, 0, 0, stream);
+}
+
+int nrt_warp_strided_f32(const float* vol, const float* flow, float* out, int B, const int32_t* shape, int D,
+                         int C, int method, int has_fill, float fill, int src_z0, int src_n0, int out_z0,
+                         int out_n0, int halo, int32_t* err_flag, int64_t vol_batch_stride,
+                         int64_t flow_batch_stride, int64_t out_batch_stride, void* stream) {
+  return warp_impl(vol, flow, out, B, shape, D, C, method, has_fill, fill, src_z0, src_n0, out_z0, out_n0, halo,
+                   err_flag, vol_batch_stride, flow_batch_stride, out_batch_stride, stream);
 }
 
 int nrt_resize_f32(const float* vol, float* out, int B, const int32_t* in_shape, const int32_t* out_shape,

@@ -213,12 +213,14 @@ __device__ __forceinline__ int nearest_box(float loc, int o, int lo, int hi, int
 struct BoxBounds { int lo_z, hi_z, lo_y, hi_y, lo_x, hi_x; };
 
 // tensor-map encoding through the runtime's driver entry point (no -lcuda needed); rank 4 or 5, fp32, dense
-int encode_f32_tiled(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint32_t* box);
+// last_stride_elems != 0: element stride of the LAST dimension (batch items not densely packed; multiple of 4)
+int encode_f32_tiled(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint32_t* box,
+                     uint64_t last_stride_elems = 0);
 int env_int(const char* name, int dflt);
 
 // multi-channel D = 3 warp through the z-marching ring kernel (nrt_warp_march.cu); *used = false when not covered
 int warp3d_march(const float* vol, const float* flow, float* out, int B, const int32_t* shape, int C, int method,
                  int has_fill, float fill, int src_z0, int src_n0, int out_z0, int out_n0, int halo,
-                 int32_t* err_flag, cudaStream_t st, bool* used);
+                 int32_t* err_flag, int64_t vbs, int64_t fbs, int64_t obs, cudaStream_t st, bool* used);
 
 }  // namespace nrt

@@ -28,6 +28,7 @@ struct MarchGeo {
   int out_z0, out_n0;           // produced planes of axis 0 (global start, count)
   int B, nchunk, nseg, seg_len; // channel chunks of CCH, z segments per column and their length
   int64_t src_batch_stride, out_vox;
+  int64_t flow_bstride, out_bstride;   // elements between batch items of flow / out
 };
 
 // CCH = channels staged per voxel (a chunk of the volume's C); VEC: lanes own 4-channel quads, else all CCH channels
@@ -113,7 +114,7 @@ warp3d_march_kernel(const __grid_constant__ CUtensorMap tm_vol, const __grid_con
 
   // ===== consumers =====
   const float* volb = vol + (size_t)b * w.src_batch_stride;
-  float* outb = out + (size_t)b * w.out_vox * Ctot;
+  float* outb = out + (size_t)b * w.out_bstride;
   const int c_base = chunk * CCH;
   const int oy = y0 - HALO, ox = x0 - Cfg::HX;
   const int lo_y = max(oy, 0), hi_y = min(oy + BY - 1, H - 1);
@@ -244,16 +245,16 @@ static int launch_march(const float* vol, const float* flow, float* out, MarchGe
   if (Cfg::VEC) {
     const uint64_t vd[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)mg.g.src_n0, (uint64_t)mg.B};
     const uint32_t vb[5] = {(uint32_t)CCH, (uint32_t)Cfg::BX, (uint32_t)Cfg::BY, 1, 1};
-    rc = encode_f32_tiled(&tmv, vol, 5, vd, vb);
+    rc = encode_f32_tiled(&tmv, vol, 5, vd, vb, (uint64_t)mg.src_batch_stride);
   } else {
     const uint64_t vd[4] = {(uint64_t)W * C, (uint64_t)H, (uint64_t)mg.g.src_n0, (uint64_t)mg.B};
     const uint32_t vb[4] = {(uint32_t)(Cfg::BX * CCH), (uint32_t)Cfg::BY, 1, 1};
-    rc = encode_f32_tiled(&tmv, vol, 4, vd, vb);
+    rc = encode_f32_tiled(&tmv, vol, 4, vd, vb, (uint64_t)mg.src_batch_stride);
   }
   if (rc != NRT_OK) return rc;
   const uint64_t fd[4] = {(uint64_t)W * 3, (uint64_t)H, (uint64_t)mg.out_n0, (uint64_t)mg.B};
   const uint32_t fb[4] = {(uint32_t)TX * 3, (uint32_t)TY, 1, 1};
-  rc = encode_f32_tiled(&tmf, flow, 4, fd, fb);
+  rc = encode_f32_tiled(&tmf, flow, 4, fd, fb, (uint64_t)mg.flow_bstride);
   if (rc != NRT_OK) return rc;
   auto kern = warp3d_march_kernel<CCH, TY, TX, HALO, AHEAD, NW, METHOD>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM) != cudaSuccess)
@@ -267,7 +268,7 @@ static int launch_march(const float* vol, const float* flow, float* out, MarchGe
 // covered: the caller then takes the box-tile or the generic gather path.
 int warp3d_march(const float* vol, const float* flow, float* out, int B, const int32_t* shape, int C, int method,
                  int has_fill, float fill, int src_z0, int src_n0, int out_z0, int out_n0, int halo,
-                 int32_t* err_flag, cudaStream_t st, bool* used) {
+                 int32_t* err_flag, int64_t vbs, int64_t fbs, int64_t obs, cudaStream_t st, bool* used) {
   *used = false;
   const int H = shape[1], W = shape[2];
   if (env_int("NRT_WARP_MARCH", 1) == 0) return NRT_OK;
@@ -279,8 +280,11 @@ int warp3d_march(const float* vol, const float* flow, float* out, int B, const i
   mg.g.has_fill = has_fill; mg.g.fill = fill; mg.g.err = err_flag;
   mg.out_z0 = out_z0; mg.out_n0 = out_n0; mg.B = B;
   mg.nchunk = mg.nseg = mg.seg_len = 1;
-  mg.src_batch_stride = (int64_t)src_n0 * H * W * C;
   mg.out_vox = (int64_t)out_n0 * H * W;
+  mg.src_batch_stride = vbs ? vbs : (int64_t)src_n0 * H * W * C;
+  mg.flow_bstride = fbs ? fbs : mg.out_vox * 3;
+  mg.out_bstride = obs ? obs : mg.out_vox * C;
+  if ((mg.src_batch_stride | mg.flow_bstride | mg.out_bstride) & 3) return NRT_OK;   // TMA strides: multiples of 16 bytes
   int rc = 1;
   const int nw16 = env_int("NRT_MARCH_NW", 16);
 #define NRT_MARCH(cch, ty, tx, ahead, nw)                                                                      \

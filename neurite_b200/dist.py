@@ -10,10 +10,12 @@ keras multi_gpu_model wrapper, neurite/tf/utils/model.py:298-321).
                              (metrics.Dice(group=...)); 768 B at cfg 3.
   * warp of ONE volume    -- output + flow split into contiguous z-slabs (axis 0, contiguous
                              in channels-last memory).  A rank needs source planes
-                             [z0 - h, z1 + h) with h = ceil(max |flow_z| over its slab) + 1:
-                               'halo'   neighbour send/recv of h planes (h <= neighbour slab)
-                               'gather' all-gather of the source slabs (27.5 MB at cfg 2),
-                                        used when h exceeds a neighbour's slab
+                             [z0 - h, z1 + h) with h = ceil(max |flow_z|) + 1 (`SlabWarper`):
+                               halo     neighbour send/recv of h planes on NCCL's stream WHILE the interior
+                                        planes are warped from the rank's own planes; the two boundary
+                                        strips follow; no host sync in the step
+                               gather   all-gather of the source slabs (27.5 MB at cfg 2),
+                                        used when h exceeds a slab (same decision on every rank)
   * Resize                -- output slabs against a replicated (small) source.
   * LocallyConnected3D    -- output positions AND their private weights sharded together
                              (model-parallel by construction); input replicated.
@@ -70,81 +72,208 @@ def gather_source(vol_slab, full_s0, group=None):
     return torch.cat([parts[r][:, :bounds[r][1]] for r in range(world)], dim=1)
 
 
+def halo_fits(full_s0, world_size, halo):
+    """True if every rank's slab can serve a `halo`-plane neighbour exchange.  Computed from the slab table, so
+    every rank reaches the same answer WITHOUT communicating: either all ranks exchange or all fall back /
+    raise -- never a rank that throws while its peers block in the collective."""
+    return all(halo <= c for _, c in all_slab_bounds(full_s0, world_size))
+
+
+def _stage_on_host(t, group):
+    """gloo cannot send / receive CUDA tensors: stage them through the host (two ranks sharing one GPU in the
+    single-GPU test variant).  NCCL moves device memory directly."""
+    return t.is_cuda and dist.get_backend(group) == 'gloo'
+
+
+def _post_exchange(sends, recvs, group):
+    """Post all (tensor, peer) sends and receives as ONE batch (ncclGroupStart/End under NCCL).  Returns a
+    function that makes the current stream wait for them (and finishes the host staging under gloo)."""
+    ops, fix = [], []
+    for t, peer in sends:
+        buf = t.contiguous()
+        if _stage_on_host(buf, group):
+            buf = buf.cpu()
+        ops.append(dist.P2POp(dist.isend, buf, _peer(peer, group), group))
+    for t, peer in recvs:
+        direct = t.is_contiguous() and not _stage_on_host(t, group)
+        buf = t if direct else torch.empty(t.shape, dtype=t.dtype, device='cpu' if _stage_on_host(t, group) else t.device)
+        if not direct:
+            fix.append((t, buf))
+        ops.append(dist.P2POp(dist.irecv, buf, _peer(peer, group), group))
+    works = dist.batch_isend_irecv(ops) if ops else []
+
+    def wait():
+        for w in works:
+            w.wait()                       # NCCL: a stream dependency, the host does not block
+        for t, buf in fix:
+            t.copy_(buf, non_blocking=True)
+    return wait
+
+
 def exchange_halo(vol_slab, halo, full_s0, group=None):
     """Neighbour exchange: returns (extended_slab, src_z0) where extended_slab holds source
-    planes [src_z0, src_z0 + n).  Requires halo <= the neighbours' slab sizes."""
+    planes [src_z0, src_z0 + n).  Raises ValueError -- on EVERY rank, before anything is posted -- if `halo`
+    exceeds some rank's slab (use gather_source then)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    bounds = all_slab_bounds(full_s0, world)
-    z0, nz = bounds[rank]
-    lo, hi = source_window(z0, nz, halo, full_s0)
-    need_lo, need_hi = z0 - lo, hi - (z0 + nz)
-    if (rank > 0 and need_lo > bounds[rank - 1][1]) or (rank < world - 1 and need_hi > bounds[rank + 1][1]):
-        raise ValueError('halo %d exceeds a neighbour slab; use gather_source' % halo)
-    B = vol_slab.shape[0]
-    rest = tuple(vol_slab.shape[2:])
-    ops, recv_lo, recv_hi = [], None, None
-    # every rank uses the same halo, so what a neighbour needs from me is known locally:
-    #   the lower neighbour's window ends at min(z0 + halo, full)  -> my first planes
-    #   the upper neighbour's window starts at max(z0 + nz - halo, 0) -> my last planes
+    if not halo_fits(full_s0, world, halo):
+        raise ValueError('halo %d exceeds a slab of the %d-way split of %d planes; use gather_source'
+                         % (halo, world, full_s0))
+    z0, nz = slab_bounds(full_s0, world, rank)
+    lo_pad = halo if rank > 0 else 0
+    hi_pad = halo if rank < world - 1 else 0
+    ext = vol_slab.new_empty((vol_slab.shape[0], lo_pad + nz + hi_pad) + tuple(vol_slab.shape[2:]))
+    ext[:, lo_pad:lo_pad + nz] = vol_slab
+    sends, recvs = [], []
     if rank > 0:
-        send_n = min(halo, full_s0 - z0)
-        if send_n > nz:
-            raise ValueError('halo %d exceeds a neighbour slab; use gather_source' % halo)
-        if send_n:
-            ops.append(dist.P2POp(dist.isend, vol_slab[:, :send_n].contiguous(), _peer(rank - 1, group), group))
-        if need_lo:
-            recv_lo = vol_slab.new_empty((B, need_lo) + rest)
-            ops.append(dist.P2POp(dist.irecv, recv_lo, _peer(rank - 1, group), group))
+        sends.append((vol_slab[:, :halo], rank - 1))
+        recvs.append((ext[:, :lo_pad], rank - 1))
     if rank < world - 1:
-        send_n = min(halo, z0 + nz)
-        if send_n > nz:
-            raise ValueError('halo %d exceeds a neighbour slab; use gather_source' % halo)
-        if send_n:
-            ops.append(dist.P2POp(dist.isend, vol_slab[:, nz - send_n:].contiguous(), _peer(rank + 1, group), group))
-        if need_hi:
-            recv_hi = vol_slab.new_empty((B, need_hi) + rest)
-            ops.append(dist.P2POp(dist.irecv, recv_hi, _peer(rank + 1, group), group))
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-    parts = [t for t in (recv_lo, vol_slab, recv_hi) if t is not None]
-    return torch.cat(parts, dim=1) if len(parts) > 1 else vol_slab, lo
+        sends.append((vol_slab[:, nz - halo:], rank + 1))
+        recvs.append((ext[:, lo_pad + nz:], rank + 1))
+    _post_exchange(sends, recvs, group)()
+    return ext, z0 - lo_pad
 
 
 def _peer(group_rank, group):
     return group_rank if group is None else dist.get_global_rank(group, group_rank)
 
 
+class SlabWarper:
+    """Warp ONE volume that is sharded in z-slabs over the ranks of `group`, repeatedly, with the halo exchange
+    OVERLAPPED with the interior of the slab and NO host synchronisation in the step (the
+    reference's call sites are neurite/tf/models.py:806-807, 1157-1159 -- it has no distributed path itself).
+
+    Per call, on rank r holding planes [z0, z0 + nz):
+      1. the rank's planes are placed in the middle of a persistent buffer [B, halo + nz + halo, ...];
+      2. the first / last `halo` planes go to the lower / upper neighbour and theirs are received straight into
+         the two ends of that buffer -- one ncclGroup of <= 4 send/recv on NCCL's stream;
+      3. meanwhile the INTERIOR output planes [z0 + halo, z0 + nz - halo), whose source window lies inside the
+         rank's own planes, are produced on the compute stream (resident planes = own slab only, so a flow that
+         exceeds `halo` raises the device flag instead of reading planes that have not arrived);
+      4. the compute stream then waits for the exchange (a stream dependency, the host does not block) and
+         produces the two boundary strips against the extended buffer.
+    `halo` = ceil(max |flow along axis 0|) + 1 is a property of the plan, not measured per step: get it once
+    with `required_halo` (one host sync, e.g. from the registration model's maximum displacement) and reuse
+    it.  A flow that exceeds it is never silently wrong: the kernels raise a device flag, read by `check()`.
+    If `halo` exceeds a slab the source is all-gathered instead (no overlap); every rank takes the same branch."""
+
+    def __init__(self, full_s0, halo, group=None, interp_method='linear', fill_value=None, tile_halo=0, warp_fn=None):
+        self.full_s0, self.halo, self.group = int(full_s0), int(halo), group
+        self.method = utils.method_id(interp_method)
+        self.fill_value, self.tile_halo = fill_value, int(tile_halo)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.z0, self.nz = slab_bounds(self.full_s0, self.world, self.rank)
+        self.fits = halo_fits(self.full_s0, self.world, self.halo)
+        self.lo_pad = self.halo if (self.fits and self.rank > 0) else 0
+        self.hi_pad = self.halo if (self.fits and self.rank < self.world - 1) else 0
+        self._ext, self._err = None, None
+        self._warp_fn = warp_fn or self._kernel
+
+    # -- the arithmetic: one launch of the warp kernels on plane sub-ranges (injectable for the CPU tests)
+    def _kernel(self, vol_v, flow_v, out_v, src_z0, out_z0):
+        utils._warp_views(vol_v, flow_v, out_v, self.full_s0, self.method, self.fill_value, src_z0, out_z0,
+                          halo=self.tile_halo, err_flag=self._err)
+
+    def _buffers(self, vol_slab):
+        shape = (vol_slab.shape[0], self.lo_pad + self.nz + self.hi_pad) + tuple(vol_slab.shape[2:])
+        if self._ext is None or tuple(self._ext.shape) != shape or self._ext.device != vol_slab.device:
+            self._ext = torch.empty(shape, dtype=torch.float32, device=vol_slab.device)
+            self._err = torch.zeros(1, dtype=torch.int32, device=vol_slab.device) if vol_slab.is_cuda else None
+        return self._ext
+
+    def source_view(self, like):
+        """The [B, nz, ...] view of the persistent buffer a producer can write the rank's planes into directly
+        (then pass that view as `vol_slab`: no copy)."""
+        ext = self._buffers(like)
+        return ext[:, self.lo_pad:self.lo_pad + self.nz]
+
+    def __call__(self, vol_slab, flow_slab, out=None):
+        nz, halo = self.nz, self.halo
+        if vol_slab.shape[1] != nz or flow_slab.shape[1] != nz:
+            raise ValueError('rank %d owns %d planes, got vol %s / flow %s' % (self.rank, nz, tuple(vol_slab.shape), tuple(flow_slab.shape)))
+        if out is None:
+            out = torch.empty(tuple(flow_slab.shape[:-1]) + (vol_slab.shape[-1],), dtype=torch.float32, device=vol_slab.device)
+        if not self.fits:
+            # halo wider than a slab: replicate the source (all-gather), one launch, nothing to overlap
+            self._buffers(vol_slab)
+            src = gather_source(vol_slab, self.full_s0, self.group)
+            self._warp_fn(src, flow_slab, out, 0, self.z0)
+            return out
+        ext = self._buffers(vol_slab)
+        mid = ext[:, self.lo_pad:self.lo_pad + nz]
+        if vol_slab.data_ptr() != mid.data_ptr():
+            mid.copy_(vol_slab)
+        sends, recvs = [], []
+        if self.rank > 0:
+            sends.append((mid[:, :halo], self.rank - 1))
+            recvs.append((ext[:, :self.lo_pad], self.rank - 1))
+        if self.rank < self.world - 1:
+            sends.append((mid[:, nz - halo:], self.rank + 1))
+            recvs.append((ext[:, self.lo_pad + nz:], self.rank + 1))
+        wait = _post_exchange(sends, recvs, self.group)
+        i_lo, i_hi = self.lo_pad, nz - self.hi_pad            # interior output planes (slab-local)
+        if i_hi > i_lo:
+            self._warp_fn(mid, flow_slab[:, i_lo:i_hi], out[:, i_lo:i_hi], self.z0, self.z0 + i_lo)
+            wait()
+            src_z0 = self.z0 - self.lo_pad
+            if i_lo > 0:
+                self._warp_fn(ext, flow_slab[:, :i_lo], out[:, :i_lo], src_z0, self.z0)
+            if i_hi < nz:
+                self._warp_fn(ext, flow_slab[:, i_hi:], out[:, i_hi:], src_z0, self.z0 + i_hi)
+        else:                                                 # slab thinner than two halos: no interior
+            wait()
+            self._warp_fn(ext, flow_slab, out, self.z0 - self.lo_pad, self.z0)
+        return out
+
+    def check(self):
+        """Host-synchronising: raises if any sample since the last check fell outside the resident planes."""
+        if self._err is not None and int(self._err.item()) != 0:
+            self._err.zero_()
+            raise RuntimeError('SlabWarper: a sample fell outside the resident source planes '
+                               '(halo %d too small for this flow)' % self.halo)
+
+
+def agreed_halo(flow_slab, group=None):
+    """ceil(max |shift along axis 0|) + 1 over ALL ranks (one all-reduce + one host sync): the `halo` of a plan."""
+    h = torch.tensor([required_halo(flow_slab)], dtype=torch.int64, device=flow_slab.device)
+    dist.all_reduce(h, op=dist.ReduceOp.MAX, group=group)
+    return int(h.item())
+
+
 def warp_slab(vol_slab, flow_slab, full_s0, interp_method='linear', fill_value=None, group=None,
               mode='auto', halo=None, tile_halo=0):
-    """Warp ONE z-slab-sharded volume.  vol_slab/flow_slab: this rank's planes
-    [B, nz_r, *S_rest, C] / [B, nz_r, *S_rest, D] of a volume with full_s0 planes.
-    Returns this rank's output slab.  Raises if the source window turned out too small
-    (device error flag), which cannot happen when `halo` is computed from the flow."""
+    """Warp ONE z-slab-sharded volume, one-shot convenience form of `SlabWarper` (it measures the halo and checks
+    the device flag, i.e. it synchronises; a training / inference loop keeps a SlabWarper instead).
+    vol_slab/flow_slab: this rank's planes [B, nz_r, *S_rest, C] / [B, nz_r, *S_rest, D] of a volume with
+    full_s0 planes.  mode: 'auto' / 'halo' = overlapped neighbour exchange ('auto' falls back to the all-gather
+    when the halo exceeds a slab, 'halo' raises then -- on every rank), 'gather' = all-gather of the source,
+    'serial' = exchange, then ONE launch (the round-1 path, kept as the timing baseline)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    bounds = all_slab_bounds(full_s0, world)
-    z0, nz = bounds[rank]
+    z0, nz = slab_bounds(full_s0, world, rank)
     if halo is None:
-        h = torch.tensor([required_halo(flow_slab)], dtype=torch.int64, device=flow_slab.device)
-        dist.all_reduce(h, op=dist.ReduceOp.MAX, group=group)       # same window rule on every rank
-        halo = int(h.item())
-    fits = all(halo <= c for _, c in bounds)
-    if mode == 'auto':
-        mode = 'halo' if fits else 'gather'
-    if mode == 'halo':
-        src, src_z0 = exchange_halo(vol_slab, halo, full_s0, group)
-    elif mode == 'gather':
-        src, src_z0 = gather_source(vol_slab, full_s0, group), 0
-    else:
-        raise ValueError("mode must be 'auto', 'halo' or 'gather'")
-    err = torch.zeros(1, dtype=torch.int32, device=vol_slab.device)
-    out = utils._warp_batched(src, flow_slab, interp_method, fill_value, halo=tile_halo,
-                              src_z0=src_z0, full_s0=full_s0, out_z0=z0, err_flag=err)
-    if int(err.item()) != 0:
-        raise RuntimeError('warp_slab: a sample fell outside the resident source planes '
-                           '(halo %d too small for this flow)' % halo)
+        halo = agreed_halo(flow_slab, group)
+    if mode not in ('auto', 'halo', 'gather', 'serial'):
+        raise ValueError("mode must be 'auto', 'halo', 'gather' or 'serial'")
+    fits = halo_fits(full_s0, world, halo)
+    if mode in ('halo', 'serial') and not fits:
+        raise ValueError('halo %d exceeds a slab of the %d-way split of %d planes; use mode=\'gather\'' % (halo, world, full_s0))
+    if mode == 'serial' or mode == 'gather':
+        if mode == 'serial':
+            src, src_z0 = exchange_halo(vol_slab, halo, full_s0, group)
+        else:
+            src, src_z0 = gather_source(vol_slab, full_s0, group), 0
+        err = torch.zeros(1, dtype=torch.int32, device=vol_slab.device)
+        out = utils._warp_batched(src, flow_slab, interp_method, fill_value, halo=tile_halo,
+                                  src_z0=src_z0, full_s0=full_s0, out_z0=z0, err_flag=err)
+        if int(err.item()) != 0:
+            raise RuntimeError('warp_slab: a sample fell outside the resident source planes '
+                               '(halo %d too small for this flow)' % halo)
+        return out
+    plan = SlabWarper(full_s0, halo, group, interp_method, fill_value, tile_halo)
+    out = plan(utils._as_f32(vol_slab).contiguous(), utils._as_f32(flow_slab).contiguous())
+    plan.check()
     return out
 
 
@@ -182,6 +311,9 @@ def blur_slab(x_slab, sigma, full_s0, group=None, blur_fn=None):
         return blur_fn(x_slab, sig)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     z0, nz = slab_bounds(full_s0, world, rank)
-    ext, src_z0 = exchange_halo(x_slab, halo, full_s0, group)
+    if halo_fits(full_s0, world, halo):
+        ext, src_z0 = exchange_halo(x_slab, halo, full_s0, group)
+    else:                                                  # same branch on every rank (decided from the slab table)
+        ext, src_z0 = gather_source(x_slab, full_s0, group), 0
     out = blur_fn(ext, sig)
     return out[:, z0 - src_z0:z0 - src_z0 + nz].contiguous()

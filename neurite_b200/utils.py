@@ -236,6 +236,37 @@ def _warp_raw(vol32, flow32, shape, method, fill_value, slab, halo, err_flag):
     return out
 
 
+def _inner_contiguous(t):
+    """True if every batch item of t [B, ...] is a dense block (only the batch stride may be larger)."""
+    exp = 1
+    for size, stride in zip(reversed(t.shape[1:]), reversed(t.stride()[1:])):
+        if size != 1 and stride != exp:
+            return False
+        exp *= size
+    return t.shape[0] <= 1 or t.stride(0) >= exp
+
+
+def _warp_views(vol_v, flow_v, out_v, full_s0, method, fill_value, src_z0, out_z0, halo=0, err_flag=None):
+    """Warp into a caller-owned output: vol_v [B, src_n0, H, W, C], flow_v [B, out_n0, H, W, 3], out_v
+    [B, out_n0, H, W, C] may be PLANE SUB-RANGES of larger [B, planes, ...] buffers (dense inside a batch item,
+    strided across the batch) -- nrt_warp_strided_f32.  No allocation, no synchronisation."""
+    require_cuda(vol_v, flow_v, out_v)
+    for v in (vol_v, flow_v, out_v):
+        if v.dtype != torch.float32 or not _inner_contiguous(v):
+            raise ValueError('_warp_views needs fp32 views that are dense inside each batch item')
+    B, C, D = vol_v.shape[0], vol_v.shape[-1], flow_v.shape[-1]
+    if out_v.numel() == 0:
+        return out_v
+    shape = [int(full_s0)] + [int(s) for s in vol_v.shape[2:-1]]
+    bs = lambda v: int(v.stride(0)) if v.shape[0] > 1 else 0          # noqa: E731
+    with torch.cuda.device(vol_v.device):
+        check(lib.nrt_warp_strided_f32(ptr(vol_v), ptr(flow_v), ptr(out_v), B, i32_array(shape), D, C, method,
+                                       0 if fill_value is None else 1, 0.0 if fill_value is None else float(fill_value),
+                                       int(src_z0), int(vol_v.shape[1]), int(out_z0), int(out_v.shape[1]), int(halo),
+                                       ptr(err_flag), bs(vol_v), bs(flow_v), bs(out_v), stream_ptr(vol_v.device)))
+    return out_v
+
+
 class _WarpFn(torch.autograd.Function):
     """autograd shell around nrt_warp_f32 / nrt_warp_bwd_f32."""
 

@@ -124,22 +124,58 @@ void oracle_warp_f32(const float* vol, const float* flow, float* out, int B, con
   }
 }
 
-/* sums[b][l][3] = {sum t*p, sum t*t, sum p*p}; double accumulation, one rounding */
+/* Parallel copy with the static schedule of the compute loops: a buffer filled by this function is
+ * first-touched by the threads that will later read it (NUMA placement of the CPU baseline's inputs). */
+void oracle_first_touch_copy_f32(float* dst, const float* src, int64_t n) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) dst[i] = src[i];
+}
+
+/* sums[b][l][3] = {sum t*p, sum t*t, sum p*p}; double accumulation, one rounding.  Voxel-parallel: every thread
+ * streams a contiguous voxel range once (all labels of a voxel are adjacent in channels-last memory) into
+ * private double partials, combined in thread order -- deterministic for a fixed thread count. */
+#define ORACLE_MAX_LABELS 1024
 void oracle_dice_sums_f32(const float* t, const float* p, int B, int64_t V, int L, float* sums) {
-#pragma omp parallel for collapse(2) schedule(static)
-  for (int b = 0; b < B; ++b)
-    for (int l = 0; l < L; ++l) {
-      double tp = 0, tt = 0, pp = 0;
-      const float* tb = t + (size_t)b * V * L + l;
-      const float* pb = p + (size_t)b * V * L + l;
-      for (int64_t v = 0; v < V; ++v) {
-        const float a = tb[v * L], c = pb[v * L];
-        tp += (double)(a * c); tt += (double)(a * a); pp += (double)(c * c);
+  for (int b = 0; b < B; ++b) {
+    const float* tb = t + (size_t)b * V * L;
+    const float* pb = p + (size_t)b * V * L;
+    double tot[ORACLE_MAX_LABELS * 3];
+    const int Lc = L <= ORACLE_MAX_LABELS ? L : ORACLE_MAX_LABELS;
+    for (int i = 0; i < Lc * 3; ++i) tot[i] = 0.0;
+    if (L > ORACLE_MAX_LABELS) {                      /* not used by the tests / bench: plain serial fallback */
+      for (int l = 0; l < L; ++l) {
+        double tp = 0, tt = 0, pp = 0;
+        for (int64_t v = 0; v < V; ++v) {
+          const float a = tb[v * L + l], c = pb[v * L + l];
+          tp += (double)(a * c); tt += (double)(a * a); pp += (double)(c * c);
+        }
+        sums[((size_t)b * L + l) * 3 + 0] = (float)tp;
+        sums[((size_t)b * L + l) * 3 + 1] = (float)tt;
+        sums[((size_t)b * L + l) * 3 + 2] = (float)pp;
       }
-      sums[((size_t)b * L + l) * 3 + 0] = (float)tp;
-      sums[((size_t)b * L + l) * 3 + 1] = (float)tt;
-      sums[((size_t)b * L + l) * 3 + 2] = (float)pp;
+      continue;
     }
+#pragma omp parallel
+    {
+      double acc[ORACLE_MAX_LABELS * 3];
+      for (int i = 0; i < L * 3; ++i) acc[i] = 0.0;
+#pragma omp for schedule(static) nowait
+      for (int64_t v = 0; v < V; ++v) {
+        const float* tv = tb + v * L;
+        const float* pv = pb + v * L;
+        for (int l = 0; l < L; ++l) {
+          const float a = tv[l], c = pv[l];
+          acc[l * 3 + 0] += (double)(a * c); acc[l * 3 + 1] += (double)(a * a); acc[l * 3 + 2] += (double)(c * c);
+        }
+      }
+#pragma omp for ordered schedule(static, 1)
+      for (int th = 0; th < omp_get_num_threads(); ++th) {
+#pragma omp ordered
+        for (int i = 0; i < L * 3; ++i) tot[i] += acc[i];
+      }
+    }
+    for (int i = 0; i < L * 3; ++i) sums[(size_t)b * L * 3 + i] = (float)tot[i];
+  }
 }
 
 /* returns sum over rows of -sum_c (w_c t_c) log(clip(p_c / sum p)) as double */

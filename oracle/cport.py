@@ -61,6 +61,15 @@ def use_all_cores():
     return set_num_threads(n)
 
 
+def first_touch(a):
+    """Copy of `a` whose pages are first touched by the OpenMP threads with the static schedule of the compute
+    loops (np.empty does not touch; the parallel copy does): NUMA-local inputs for the CPU baseline."""
+    a = np.ascontiguousarray(a, dtype=F32)
+    out = np.empty(a.shape, dtype=F32)
+    lib().oracle_first_touch_copy_f32(_p(out), _p(a), ctypes.c_int64(a.size))
+    return out
+
+
 def warp(vol, flow, interp_method='linear', fill_value=None, out=None):
     """vol [B,*S,C], flow [B,*S,D] -> [B,*S,C] (written into `out` if given)"""
     vol = np.ascontiguousarray(vol, dtype=F32)

@@ -108,3 +108,99 @@ def test_blur_slab_exchange_and_crop_gloo(world, full_s0, sigma):
     for p in procs:
         p.join(30)
     assert all(ok for _, ok in res), res
+
+
+def _oracle_warp_fn(full_s0):
+    """SlabWarper's kernel hook on CPU tensors: the numpy oracle warps the FULL volume (planes outside the
+    resident window are poisoned with NaN, so a read outside the window cannot go unnoticed) and the requested
+    output planes are written into the caller's view."""
+    import numpy as np
+    from oracle import interp as ointerp
+
+    def fn(vol_v, flow_v, out_v, src_z0, out_z0):
+        B, n_src = vol_v.shape[0], vol_v.shape[1]
+        rest, C = tuple(vol_v.shape[2:-1]), vol_v.shape[-1]
+        src = np.full((B, full_s0) + rest + (C,), np.nan, dtype=np.float32)
+        src[:, src_z0:src_z0 + n_src] = vol_v.numpy()
+        flow = np.zeros((B, full_s0) + rest + (3,), dtype=np.float32)
+        n_out = flow_v.shape[1]
+        flow[:, out_z0:out_z0 + n_out] = flow_v.numpy()
+        res = ointerp.spatial_transformer(src, flow)
+        out_v.copy_(torch.from_numpy(np.ascontiguousarray(res[:, out_z0:out_z0 + n_out])))
+    return fn
+
+
+def _slab_warper_worker(rank, world, port, full_s0, amp, B, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from oracle import interp as ointerp
+        g = torch.Generator().manual_seed(3)
+        S = (full_s0, 6, 8)
+        vol = torch.randn((B,) + S + (2,), generator=g)
+        flow = (torch.rand((B,) + S + (3,), generator=g) * 2 - 1) * amp
+        whole = torch.from_numpy(ointerp.spatial_transformer(vol.numpy(), flow.numpy()))
+        z0, nz = nd.slab_bounds(full_s0, world, rank)
+        halo = nd.agreed_halo(flow[:, z0:z0 + nz])
+        plan = nd.SlabWarper(full_s0, halo, warp_fn=_oracle_warp_fn(full_s0))
+        ok = plan.fits == nd.halo_fits(full_s0, world, halo)
+        for step in range(2):                                   # the plan is reused: second call hits the cached buffers
+            part = plan(vol[:, z0:z0 + nz].contiguous(), flow[:, z0:z0 + nz].contiguous())
+            ok = ok and bool(torch.equal(part, whole[:, z0:z0 + nz])) and not bool(torch.isnan(part).any())
+        # a producer may write its planes straight into the plan's buffer (no copy inside the call)
+        view = plan.source_view(vol[:, z0:z0 + nz])
+        view.copy_(vol[:, z0:z0 + nz])
+        part = plan(view, flow[:, z0:z0 + nz].contiguous())
+        ok = ok and bool(torch.equal(part, whole[:, z0:z0 + nz]))
+        q.put((rank, bool(ok), plan.fits))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,full_s0,amp,B', [(2, 16, 2.5, 1), (3, 20, 1.5, 2), (2, 9, 2.0, 2), (3, 9, 4.5, 1)])
+def test_slab_warper_overlapped_exchange_gloo(world, full_s0, amp, B):
+    """SlabWarper on CPU tensors: interior launch from the rank's own planes, boundary launches after the
+    neighbour exchange, thin slabs without an interior, and the all-gather branch when the halo exceeds a slab
+    (last case) -- all ranks take the same branch and the pieces equal the whole-volume warp bit for bit."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slab_warper_worker, args=(r, world, port, full_s0, amp, B, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(30)
+    assert all(ok for _, ok, _ in res), res
+    assert len({fits for _, _, fits in res}) == 1
+
+
+def _halo_raise_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        z0, nz = nd.slab_bounds(10, world, rank)                # slabs of 4, 3, 3 planes
+        slab = torch.zeros(1, nz, 2, 2, 1)
+        try:
+            nd.exchange_halo(slab, 4, 10)                       # fits rank 0's slab only
+            q.put((rank, 'no error'))
+        except ValueError:
+            q.put((rank, 'raised'))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_that_does_not_fit_raises_on_every_rank():
+    """the fit decision comes from the slab table, so no rank is left blocking in a collective."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_halo_raise_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(3)]
+    for p in procs:
+        p.join(30)
+    assert sorted(res) == [(0, 'raised'), (1, 'raised'), (2, 'raised')]

@@ -39,9 +39,11 @@ def _worker(rank, world, port, q):
             flow = ((torch.rand((2,) + S + (3,), generator=g) * 2 - 1) * amp).to(dev)
             whole = utils._warp_batched(vol, flow)
             z0, nz = nd.slab_bounds(S[0], world, rank)
-            for mode in ('auto', 'gather'):
+            fits = nd.halo_fits(S[0], world, nd.agreed_halo(flow[:, z0:z0 + nz]))
+            for mode in ('auto', 'gather') + (('serial',) if fits else ()):
                 part = nd.warp_slab(vol[:, z0:z0 + nz].contiguous(), flow[:, z0:z0 + nz].contiguous(), S[0], mode=mode)
                 ok = ok and torch.equal(part, whole[:, z0:z0 + nz])
+        ok = ok and _slab_warper_reuse(nd, utils, dev, g, world, rank)
         # Dice / CCE: voxel-range sharding + all-reduce of the partial sums
         L = 16
         lab = torch.randint(0, L, (2,) + S, generator=g)
@@ -64,6 +66,38 @@ def _worker(rank, world, port, q):
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
+
+
+def _slab_warper_reuse(nd, utils, dev, g, world, rank, C=16, S=(48, 24, 32)):
+    """A persistent SlabWarper (overlapped halo exchange, no host sync in the step) on a 16-channel volume, called
+    repeatedly with new data and through its zero-copy source view; then a flow beyond the plan's halo must raise
+    the device flag instead of returning wrong voxels silently."""
+    vol = torch.randn((2,) + S + (C,), generator=g).to(dev)
+    z0, nz = nd.slab_bounds(S[0], world, rank)
+    plan = nd.SlabWarper(S[0], halo=4)
+    ok = True
+    for it in range(3):
+        flow = ((torch.rand((2,) + S + (3,), generator=g) * 2 - 1) * 3.0).to(dev)
+        whole = utils._warp_batched(vol, flow)
+        if it == 2:
+            src = plan.source_view(vol[:, z0:z0 + nz])
+            src.copy_(vol[:, z0:z0 + nz])
+        else:
+            src = vol[:, z0:z0 + nz].contiguous()
+        part = plan(src, flow[:, z0:z0 + nz].contiguous())
+        ok = ok and torch.equal(part, whole[:, z0:z0 + nz])
+    plan.check()
+    if plan.fits:
+        big = torch.zeros((2,) + S + (3,), device=dev)
+        big[..., 0] = 9.0                                    # 9 planes up: beyond halo 4 for every rank but the last
+        plan(vol[:, z0:z0 + nz].contiguous(), big[:, z0:z0 + nz].contiguous())
+        raised = False
+        try:
+            plan.check()
+        except RuntimeError:
+            raised = True
+        ok = ok and (raised or rank == world - 1)
+    return bool(ok)
 
 
 def _mi_and_blur_sharded(ne, nd, dist, dev, S, g, world, rank, with_blur=True):
@@ -120,6 +154,10 @@ def _one_gpu_worker(rank, world, port, q):
         g = torch.Generator().manual_seed(0)
         S = (24, 16, 32)
         ok = _mi_and_blur_sharded(ne, nd, dist, dev, S, g, world, rank, with_blur=False)
+        # z-slab warp with the overlapped exchange (gloo moves the halo planes through the host here)
+        from neurite_b200 import utils
+        ok = ok and _slab_warper_reuse(nd, utils, dev, g, world, rank)
+        ok = ok and _slab_warper_reuse(nd, utils, dev, g, world, rank, C=1, S=(24, 16, 64))
         L = 16
         lab = torch.randint(0, L, (2,) + S, generator=g)
         t = torch.nn.functional.one_hot(lab, L).float().to(dev)
