@@ -15,7 +15,7 @@
 //       4-wide output-channel quads so no weight is read twice.
 //   lc3d_generic_kernel: one thread per (b, p, f) -- any Cout / F, used when the fast
 //       path's divisibility requirements do not hold.
-#include "nrt_common.cuh"
+#include "nrt_interp.cuh"   // CUtensorMap + encode_f32_tiled
 
 namespace nrt {
 
@@ -214,6 +214,128 @@ lc3d_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel
 }
 
 // ---------------------------------------------------------------------------------------
+// patch kernel (batch > 1).  lc3d_stream_kernel gathers a position's input patch lane by lane from L2: at
+// batch 8 that is 216 scalar loads per lane and ~6 integer instructions of addressing each -- 7100 warp
+// instructions per position, ALU pipe 62 % busy, 0.42 of the HBM roofline (profiles/r01_ncu_full_lc3d_b8.txt).
+// Here the producer thread fetches the patch with ONE TMA tensor load per position -- the box
+// (Cin, K2, K1, K0, NB) of the channels-last input [B, I0, I1, I2, Cin] lands in shared memory as [b][j] with
+// exactly the reference's feature order j = ((i0*K1 + i1)*K2 + i2)*Cin + c (layers.py:1173-1188) -- on the same
+// mbarrier as the weight block, and a lane reads its input values with conflict-free broadcast LDS.
+// ---------------------------------------------------------------------------------------
+template <int BB, int WPP>
+__global__ void __launch_bounds__((kLcMaxWarps * WPP + 1) * 32, 1)
+lc3d_patch_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ kernel,
+                  const float* __restrict__ bias, float* __restrict__ out, LcGeo g, int b_base,
+                  int stages, int cq_log2) {
+  constexpr int NB = BB * WPP;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int CQ = 1 << cq_log2;
+  const uint32_t blk_bytes = (uint32_t)g.F * g.Cout * sizeof(float);
+  const uint32_t patch_bytes = (uint32_t)g.F * NB * sizeof(float);
+  const uint32_t patch_off = (blk_bytes + 127u) & ~127u;
+  const uint32_t slot_stride = (patch_off + patch_bytes + 127u) & ~127u;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * slot_stride);
+  uint64_t* empty = full + stages;
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int groups = ((int)(blockDim.x >> 5) - 1) / WPP;
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, WPP); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (wid == groups * WPP) {
+    if (lane == 0) {
+      int k = 0;
+      for (int64_t n = blockIdx.x; n < g.pn; n += gridDim.x, ++k) {
+        const int slot = k % stages, round = k / stages;
+        if (round >= 1) mbar_wait(empty + slot, (uint32_t)((round - 1) & 1));
+        unsigned char* dst = smem_raw + (size_t)slot * slot_stride;
+        mbar_expect_tx(full + slot, blk_bytes + patch_bytes);
+        bulk_load_1d(dst, kernel + n * (int64_t)g.F * g.Cout, blk_bytes, full + slot);
+        int64_t p = g.p0 + n;
+        const int o2 = (int)(p % g.O[2]); p /= g.O[2];
+        const int o1 = (int)(p % g.O[1]);
+        const int o0 = (int)(p / g.O[1]);
+        tma_load_5d(dst + patch_off, &tm_x, full + slot, 0, o2 * g.St[2], o1 * g.St[1], o0 * g.St[0], b_base);
+      }
+    }
+    return;
+  }
+  const int n4 = g.F * CQ;                      // float4s per weight block
+  const int fq = lane & (CQ - 1);
+  const int grp = wid / WPP, sub = wid - grp * WPP;
+  const int b0 = b_base + sub * BB;
+  int k = grp;
+  for (int64_t n = (int64_t)blockIdx.x + (int64_t)grp * gridDim.x; n < g.pn; n += (int64_t)groups * gridDim.x, k += groups) {
+    const int slot = k % stages;
+    const uint32_t ph = (uint32_t)((k / stages) & 1);
+    const unsigned char* base = smem_raw + (size_t)slot * slot_stride;
+    const float4* w4 = reinterpret_cast<const float4*>(base);
+    const float* sx = reinterpret_cast<const float*>(base + patch_off) + (size_t)sub * BB * g.F;
+    unsigned long long acc2[BB][2];
+#pragma unroll
+    for (int b = 0; b < BB; ++b) acc2[b][0] = acc2[b][1] = 0ull;
+    mbar_wait(full + slot, ph);
+    // lane l reads float4 l, l+32, ... of the weight block: patch feature j = i / CQ advances by 32 / CQ per step
+    const float4* wp = w4 + lane;
+    const float* xp = sx + (lane >> cq_log2);
+    const int xstep = 32 >> cq_log2;
+#define NRT_LC_STEP(WV, XP)                                                                              \
+    do {                                                                                                 \
+      unsigned long long w01, w23;                                                                       \
+      asm("mov.b64 %0, {%1, %2};" : "=l"(w01) : "f"((WV).x), "f"((WV).y));                               \
+      asm("mov.b64 %0, {%1, %2};" : "=l"(w23) : "f"((WV).z), "f"((WV).w));                               \
+      _Pragma("unroll") for (int b = 0; b < BB; ++b) {                                                   \
+        const float xv = (XP)[b * g.F];                                                                  \
+        unsigned long long xx;                                                                           \
+        asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(xv));                                               \
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[b][0]) : "l"(xx), "l"(w01));                      \
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[b][1]) : "l"(xx), "l"(w23));                      \
+      }                                                                                                  \
+    } while (0)
+    const int full_iters = n4 >> 5;
+#pragma unroll 6
+    for (int c = 0; c < full_iters; ++c, wp += 32, xp += xstep) {
+      const float4 wv = *wp;
+      NRT_LC_STEP(wv, xp);
+    }
+    if ((n4 & 31) && lane + (full_iters << 5) < n4) {            // ragged tail of the block
+      const float4 wv = *wp;
+      NRT_LC_STEP(wv, xp);
+    }
+#undef NRT_LC_STEP
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + slot);      // slot free: every lane has read its share
+    float acc[BB][4];
+#pragma unroll
+    for (int b = 0; b < BB; ++b) {
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[b][0]), "=f"(acc[b][1]) : "l"(acc2[b][0]));
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[b][2]), "=f"(acc[b][3]) : "l"(acc2[b][1]));
+    }
+    // fold the 32/CQ lanes that share an output quad
+#pragma unroll
+    for (int b = 0; b < BB; ++b)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        for (int o = 16; o >= CQ; o >>= 1) acc[b][q] += __shfl_xor_sync(0xffffffffu, acc[b][q], o);
+    if (lane < CQ) {
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + n * g.Cout) + fq);
+#pragma unroll
+      for (int b = 0; b < BB; ++b) {
+        float4 r;
+        r.x = activate(acc[b][0] + bv.x, g.activation);
+        r.y = activate(acc[b][1] + bv.y, g.activation);
+        r.z = activate(acc[b][2] + bv.z, g.activation);
+        r.w = activate(acc[b][3] + bv.w, g.activation);
+        reinterpret_cast<float4*>(out + ((int64_t)(b0 + b) * g.pn + n) * g.Cout)[fq] = r;
+      }
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------
 // generic kernel: one thread per (b, position, filter)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -315,6 +437,41 @@ static int launch_stream(const float* x, const float* kernel, const float* bias,
   return check_launch("lc3d_stream_kernel");
 }
 
+// batch > 1: weights by bulk copy + the position's input patch by one TMA tensor load (lc3d_patch_kernel).
+// Returns 1 when the geometry is not covered (caller takes lc3d_stream_kernel).
+template <int BB, int WPP>
+static int launch_patch(const float* x, const float* kernel, const float* bias, float* out, const LcGeo& g,
+                        int b_base, int cq_log2, cudaStream_t st) {
+  constexpr int NB = BB * WPP;
+  if (g.feature_order != 0 || g.Cin % 4 != 0 || g.Cin > 256 || g.K[0] > 256 || g.K[1] > 256 || g.K[2] > 256 || !aligned16(x))
+    return 1;
+  const uint32_t blk_bytes = (uint32_t)g.F * g.Cout * sizeof(float);
+  const uint32_t patch_bytes = (uint32_t)g.F * NB * sizeof(float);
+  const uint32_t patch_off = (blk_bytes + 127u) & ~127u;
+  const uint32_t slot_stride = (patch_off + patch_bytes + 127u) & ~127u;
+  int stages = (int)((220 * 1024 - 2 * kLcMaxStages * sizeof(uint64_t) - 128) / (size_t)slot_stride);
+  if (stages < 3) return 1;
+  if (stages > kLcMaxStages) stages = kLcMaxStages;
+  const size_t smem = (size_t)stages * slot_stride + (size_t)stages * 16 + 16;
+  CUtensorMap tmx;
+  const uint64_t xd[5] = {(uint64_t)g.Cin, (uint64_t)g.I[2], (uint64_t)g.I[1], (uint64_t)g.I[0], (uint64_t)g.B};
+  const uint32_t xb[5] = {(uint32_t)g.Cin, (uint32_t)g.K[2], (uint32_t)g.K[1], (uint32_t)g.K[0], (uint32_t)NB};
+  int rc = encode_f32_tiled(&tmx, x, 5, xd, xb);
+  if (rc != NRT_OK) return rc;
+  auto kern = lc3d_patch_kernel<BB, WPP>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return check_launch("cudaFuncSetAttribute(lc3d_patch)");
+  int grid = sm_count();
+  if (g.pn < grid) grid = (int)g.pn;
+  int nw = kLcMaxWarps;
+  if (const char* e = getenv("NRT_LC3D_WARPS")) nw = atoi(e);
+  if (nw < 1) nw = 1;
+  if (nw > kLcMaxWarps) nw = kLcMaxWarps;
+  if (nw > stages - 1) nw = stages - 1;
+  kern<<<grid, (nw * WPP + 1) * 32, smem, st>>>(tmx, kernel, bias, out, g, b_base, stages, cq_log2);
+  return check_launch("lc3d_patch_kernel");
+}
+
 }  // namespace nrt
 
 using namespace nrt;
@@ -356,8 +513,16 @@ extern "C" int nrt_lc3d_fwd_f32(const float* x, const float* kernel, const float
     int b = 0, rc = NRT_OK;
     const char* pe = getenv("NRT_LC3D_FFMA2");
     const bool p2 = !(pe && atoi(pe) == 0);
+    const bool patch = env_int("NRT_LC3D_PATCH", 1) != 0;
     while (b < B && rc == NRT_OK) {              // batch items per pass = BB * WPP (weights streamed once per pass)
       const int left = B - b;
+      if (patch && left >= 2) {
+        // batch > 1: the position's input patch arrives by TMA next to its weight block (lc3d_patch_kernel)
+        int prc;
+        if (left >= 8) { prc = launch_patch<4, 2>(x, kernel, bias, out, g, b, cq_log2, st); if (prc <= 0) { rc = prc; b += 8; continue; } }
+        else if (left >= 4) { prc = launch_patch<2, 2>(x, kernel, bias, out, g, b, cq_log2, st); if (prc <= 0) { rc = prc; b += 4; continue; } }
+        else { prc = launch_patch<2, 1>(x, kernel, bias, out, g, b, cq_log2, st); if (prc <= 0) { rc = prc; b += 2; continue; } }
+      }
       // batch > 1 is FMA-issue bound: packed fp32x2 FMAs (NRT_LC3D_FFMA2=0 restores the scalar chain)
       if (left >= 8) { rc = p2 ? launch_stream<4, 2, true>(x, kernel, bias, out, g, b, cq_log2, st) : launch_stream<4, 2>(x, kernel, bias, out, g, b, cq_log2, st); b += 8; }
       else if (left >= 4) { rc = p2 ? launch_stream<2, 2, true>(x, kernel, bias, out, g, b, cq_log2, st) : launch_stream<2, 2>(x, kernel, bias, out, g, b, cq_log2, st); b += 4; }

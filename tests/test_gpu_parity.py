@@ -339,12 +339,13 @@ def test_lc3d_golden(ne, monkeypatch, name, generic):
     np.testing.assert_allclose(out, g['out'], rtol=1e-5, atol=2e-5)
 
 
-@pytest.mark.parametrize('ffma2', ['1', '0'])
-def test_lc3d_vs_oracle_batches_activations_and_sharding(ne, monkeypatch, ffma2):
-    """batch 11 = passes of 8 + 2 + 1 items: the packed-FMA (fp32x2) and the scalar accumulation chains are
-    bit-identical, both within 1e-5 of the oracle."""
+@pytest.mark.parametrize('ffma2,patch', [('1', '1'), ('1', '0'), ('0', '0')])
+def test_lc3d_vs_oracle_batches_activations_and_sharding(ne, monkeypatch, ffma2, patch):
+    """batch 11 = passes of 8 + 2 + 1 items: the TMA-patch kernel (batch > 1), the register-gather kernel with
+    packed (fp32x2) and with scalar accumulation chains are bit-identical, all within 1e-5 of the oracle."""
     from neurite_b200.layers import local_conv3d
     monkeypatch.setenv('NRT_LC3D_FFMA2', ffma2)
+    monkeypatch.setenv('NRT_LC3D_PATCH', patch)
     rng = np.random.default_rng(13)
     x = rng.standard_normal((11, 8, 9, 10, 16)).astype(F32)
     O = (6, 7, 8)
@@ -356,9 +357,18 @@ def test_lc3d_vs_oracle_batches_activations_and_sharding(ne, monkeypatch, ffma2)
         np.testing.assert_allclose(out, ref, rtol=1e-5, atol=2e-5)
     if ffma2 == '1':
         monkeypatch.setenv('NRT_LC3D_FFMA2', '0')
+        monkeypatch.setenv('NRT_LC3D_PATCH', '0')
         scalar = local_conv3d(dev(x), dev(kernel), dev(bias), (3, 3, 3), (1, 1, 1), O, activation='sigmoid').cpu().numpy()
         np.testing.assert_array_equal(out, scalar)
         monkeypatch.setenv('NRT_LC3D_FFMA2', '1')
+        monkeypatch.setenv('NRT_LC3D_PATCH', patch)
+        # strides > 1 and a ragged weight block (F * Cout / 4 not a multiple of 32): patch origin = position * stride
+        xs = rng.standard_normal((4, 9, 8, 11, 4)).astype(F32)
+        Os = (4, 3, 5)
+        ks = (rng.standard_normal((int(np.prod(Os)), 2 * 3 * 2 * 4, 4)) * 0.1).astype(F32)
+        refs = olc3d.locally_connected_3d(xs, ks, None, (2, 3, 2), strides=(2, 2, 2), literal=False)
+        outs = local_conv3d(dev(xs), dev(ks), None, (2, 3, 2), (2, 2, 2), Os).cpu().numpy()
+        np.testing.assert_allclose(outs, refs, rtol=1e-5, atol=2e-5)
     # position sharding: two ranks each own half of the positions AND of the weights
     ref = olc3d.locally_connected_3d(x, kernel, bias, (3, 3, 3), literal=False).reshape(11, -1, 16)
     P = kernel.shape[0]
@@ -432,14 +442,22 @@ def test_vxm_adjacent_transforms_vs_oracle(ne):
 
 
 @pytest.mark.parametrize('shape,C,zoom', [((7, 9, 33), 1, 2), ((6, 5, 40), 2, 3), ((5, 6, 35), 3, 2.5), ((4, 7, 34), 4, 4),
-                                          ((9, 8, 32), 3, [1.5, 2, 3.7]), ((3, 2, 2), 1, 2), ((10, 12, 70), 3, 1.6)])
+                                          ((9, 8, 32), 3, [1.5, 2, 3.7]), ((3, 2, 2), 1, 2), ((10, 12, 70), 3, 1.6),
+                                          ((40, 9, 21), 3, [2, 2, 3]), ((5, 33, 17), 2, 2), ((6, 7, 9), 1, [2, 2, 0.6]),
+                                          ((33, 18, 20), 4, [0.5, 1.3, 2.1])])
 def test_resize_upsampling_vs_oracle(ne, monkeypatch, shape, C, zoom):
-    """up-sampling shapes through the separable-table kernel and the generic kernel"""
+    """up-sampling (and mixed) shapes through the packed two-voxels-per-thread kernel (even and odd output widths),
+    the one-voxel separable-table kernel and the generic kernel: -0.0 / rounding identical (array_equal + signbit)"""
     rng = np.random.default_rng(51)
     x = rng.standard_normal((2,) + shape + (C,)).astype(F32)
+    x[0, 0, 0, :2] = 0.0                                     # exact zeros: the packed a*b = fma(a, b, -0) must keep their sign
+    x[1, -1, -1, -3:] = -0.0
     ref = ointerp.resize_layer(x, zoom)
     out = ne.layers.Resize(zoom)(dev(x))
     np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    np.testing.assert_array_equal(np.signbit(out.cpu().numpy()), np.signbit(ref))
+    monkeypatch.setenv('NRT_RESIZE_X2', '0')
+    np.testing.assert_array_equal(ne.layers.Resize(zoom)(dev(x)).cpu().numpy(), ref)
     monkeypatch.setenv('NRT_RESIZE_GENERIC', '1')
     np.testing.assert_array_equal(ne.layers.Resize(zoom)(dev(x)).cpu().numpy(), ref)
 
