@@ -168,20 +168,20 @@ class SpatialTransformer(_Layer):
         assert len(inputs) == 2, 'inputs has to be len 2, found: %d' % len(inputs)
         vol, trf = inputs
         nd = vol.dim() - 2
-        if trf.dim() == 3 and tuple(trf.shape[1:]) == (nd, nd + 1):            # affine [B, N, N+1]
-            trf = self._affine_to_dense(trf, tuple(vol.shape[1:-1]) if self.shape is None else tuple(self.shape))
+        if trf.dim() == 3 and tuple(trf.shape[1:]) in ((nd, nd + 1), (nd + 1, nd + 1)):
+            # affine [B, N, N+1] or the square homogeneous form [B, N+1, N+1] (vxm accepts both; the last row is dropped)
+            trf = self._affine_to_dense(trf[:, :nd, :], tuple(vol.shape[1:-1]) if self.shape is None else tuple(self.shape))
         if self.indexing == 'xy':                                              # swap the first two shift channels
             trf = torch.cat([trf[..., 1:2], trf[..., 0:1], trf[..., 2:]], -1)
-        if self.single_transform and trf.shape[0] == 1 and vol.shape[0] > 1:
-            trf = trf.expand((vol.shape[0],) + tuple(trf.shape[1:]))
+        if self.single_transform:
+            # vxm: the FIRST transform of the batch is applied to every volume, whatever the transform batch size
+            trf = trf[:1].expand((vol.shape[0],) + tuple(trf.shape[1:]))
         if tuple(trf.shape[1:-1]) != tuple(vol.shape[1:-1]):
-            # output grid differs from the volume grid: go through interpn per batch item
-            outs = []
-            for b in range(vol.shape[0]):
-                mesh = utils.volshape_to_ndgrid(trf.shape[1:-1], device=trf.device)
-                loc = torch.stack([mesh[d].to(torch.float32) + trf[b, ..., d] for d in range(nd)], -1)
-                outs.append(utils.interpn(vol[b], loc, self.interp_method, self.fill_value))
-            return torch.stack(outs, 0)
+            # output grid differs from the volume grid: go through interpn per batch item (one grid for all of them)
+            mesh = utils.volshape_to_ndgrid(trf.shape[1:-1], device=trf.device)
+            grid = torch.stack([m.to(torch.float32) for m in mesh], -1)
+            return torch.stack([utils.interpn(vol[b], grid + trf[b], self.interp_method, self.fill_value)
+                                for b in range(vol.shape[0])], 0)
         return utils._warp_batched(vol, trf, self.interp_method, self.fill_value, halo=self.halo)
 
 
@@ -317,9 +317,11 @@ class LocallyConnected3D(_Layer):
         self.bias_constraint = bias_constraint
         if implementation not in (1, 2, 3):
             raise ValueError('Unrecognized implementation mode: %d.' % implementation)            # :1030-1032
-        if implementation != 1:
-            raise NotImplementedError('neurite_b200 builds implementation 1 (the reference default); '
-                                      'implementations 2/3 are storage variants of the same map')
+        if implementation != 1 and self.padding != 'valid':
+            # implementations 2 / 3 also allow 'same' in the reference (masks / index lists over the padded
+            # geometry, layers.py:986-1028); here they are weight-LAYOUT variants feeding the implementation-1
+            # kernel, which is 'valid' only
+            raise NotImplementedError("LocallyConnected3D implementations 2 / 3 are built for padding='valid'")
         self.implementation = implementation
         self.kernel = None
         self.bias = None
@@ -341,12 +343,34 @@ class LocallyConnected3D(_Layer):
         self.output_col = conv_output_length(input_col, self.kernel_size[1], self.padding, self.strides[1])
         self.output_z = conv_output_length(input_z, self.kernel_size[2], self.padding, self.strides[2])
         self.input_filter = input_filter
-        self.kernel_shape = (self.output_row * self.output_col * self.output_z,
-                             self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2] * input_filter,
-                             self.filters)                                                        # :974-977
+        self.input_spatial = (input_row, input_col, input_z)
+        P = self.output_row * self.output_col * self.output_z
+        F = self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2] * input_filter
+        self.impl1_kernel_shape = (P, F, self.filters)
+        if self.implementation == 1:
+            self.kernel_shape = self.impl1_kernel_shape                                          # :974-977
+        elif self.implementation == 2:
+            # dense input x output weight, masked to the local connectivity (:986-1006)
+            if self.data_format == 'channels_first':
+                self.kernel_shape = (input_filter, input_row, input_col, input_z,
+                                     self.filters, self.output_row, self.output_col, self.output_z)
+            else:
+                self.kernel_shape = (input_row, input_col, input_z, input_filter,
+                                     self.output_row, self.output_col, self.output_z, self.filters)
+            if int(np.prod(self.kernel_shape)) > 2 ** 31:
+                raise ValueError('implementation 2 stores a dense %s weight: too large' % (self.kernel_shape,))
+        else:
+            # one weight per connected (output, input) pair, ordered by the sorted index pairs (:1008-1028)
+            self.kernel_shape = (P * F * self.filters,)
         if self.kernel is None:
             kernel = torch.empty(self.kernel_shape, dtype=torch.float32)
-            self._init(kernel, self.kernel_initializer, fan_in=self.kernel_shape[1], fan_out=self.kernel_shape[2])
+            if self.implementation == 1:
+                self._init(kernel, self.kernel_initializer, fan_in=F, fan_out=self.filters)
+            else:
+                k1 = torch.empty(self.impl1_kernel_shape, dtype=torch.float32)
+                self._init(k1, self.kernel_initializer, fan_in=F, fan_out=self.filters)
+                kernel = lc3d_kernel_to_impl(k1, self.implementation, self.input_spatial, input_filter, self.kernel_size,
+                                             self.strides, self.data_format)
             self.kernel = torch.nn.Parameter(kernel)
         if self.use_bias and self.bias is None:
             bias = torch.empty((self.output_row, self.output_col, self.output_z, self.filters), dtype=torch.float32)
@@ -384,7 +408,15 @@ class LocallyConnected3D(_Layer):
         return (input_shape[0], rows, cols, z, self.filters)
 
     def call(self, inputs):
-        return local_conv3d(inputs, self.kernel, self.bias if self.use_bias else None, self.kernel_size,
+        kernel = self.kernel
+        if self.implementation != 1:
+            # implementations 2 / 3 (layers.py:1080-1091): the same unshared map stored as a masked dense matrix /
+            # as the values of a sparse matrix.  Re-indexed (torch gather: differentiable, so the parameter keeps
+            # the reference's shape and ordering and trained weights load as they are) into the [P, F, Cout] blocks
+            # the streaming kernel consumes.
+            kernel = lc3d_kernel_from_impl(kernel, self.implementation, self.input_spatial, self.input_filter,
+                                           self.filters, self.kernel_size, self.strides, self.data_format)
+        return local_conv3d(inputs, kernel, self.bias if self.use_bias else None, self.kernel_size,
                             self.strides, (self.output_row, self.output_col, self.output_z),
                             self.data_format, self.activation)
 
@@ -403,6 +435,80 @@ class LocallyConnected3D(_Layer):
 
 
 _TORCH_ACT = {None: None, 'linear': None, 'relu': torch.relu, 'sigmoid': torch.sigmoid, 'tanh': torch.tanh}
+
+
+def _lc3d_impl2_index(input_spatial, Cin, Cout, kernel_size, strides, data_format, device):
+    """Flat indices into the implementation-2 weight (dense input x output, layers.py:986-992) of the entries that
+    form the implementation-1 kernel [P, F, Cout] ('valid' padding: patch voxel = position * stride + tap)."""
+    I, K, St = list(input_spatial), list(kernel_size), list(strides)
+    O = [(I[d] - K[d]) // St[d] + 1 for d in range(3)]
+    ar = lambda n: torch.arange(n, device=device)      # noqa: E731
+    p = torch.stack(torch.meshgrid(ar(O[0]), ar(O[1]), ar(O[2]), indexing='ij'), -1).reshape(-1, 1, 1, 3)      # [P,1,1,3]
+    if data_format == 'channels_first':               # feature j = ((c*k0+i0)*k1+i1)*k2+i2
+        c, i0, i1, i2 = torch.meshgrid(ar(Cin), ar(K[0]), ar(K[1]), ar(K[2]), indexing='ij')
+    else:                                             # feature j = ((i0*k1+i1)*k2+i2)*Cin + c
+        i0, i1, i2, c = torch.meshgrid(ar(K[0]), ar(K[1]), ar(K[2]), ar(Cin), indexing='ij')
+    tap = torch.stack([i0, i1, i2], -1).reshape(1, -1, 1, 3)
+    c = c.reshape(1, -1, 1)
+    f = ar(Cout).reshape(1, 1, -1)
+    q = p * torch.tensor(St, device=device) + tap                                                            # [P,F,1,3]
+    if data_format == 'channels_first':
+        dims = (Cin, I[0], I[1], I[2], Cout, O[0], O[1], O[2])
+        sub = (c, q[..., 0], q[..., 1], q[..., 2], f, p[..., 0], p[..., 1], p[..., 2])
+    else:
+        dims = (I[0], I[1], I[2], Cin, O[0], O[1], O[2], Cout)
+        sub = (q[..., 0], q[..., 1], q[..., 2], c, p[..., 0], p[..., 1], p[..., 2], f)
+    flat = torch.zeros((), dtype=torch.int64, device=device)
+    for s, n in zip(sub, dims):
+        flat = flat * n + s
+    return flat                                                                                              # [P,F,Cout]
+
+
+def lc3d_kernel_from_impl(kernel, implementation, input_spatial, Cin, Cout, kernel_size, strides,
+                          data_format='channels_last'):
+    """Weights stored the way LocallyConnected3D implementation 2 or 3 stores them (reference layers.py:986-1028)
+    -> the implementation-1 kernel [P, k0*k1*k2*Cin, Cout] (layers.py:974-984).  padding 'valid'.
+
+    impl 2: dense (input..., output...) tensor, channels placed like the data; only the connected entries are used
+            (the reference multiplies by a 0/1 mask, :1260-1304).
+    impl 3: 1-D vector of the connected entries in the order of sorted (out_flat, in_flat) index pairs
+            (conv_kernel_idxs :1346-1434): for channels_last out_flat = ravel(p, f), in_flat = ravel(q, c), which is
+            [P, Cout, F] row-major with F in implementation-1 feature order; channels_first: [Cout, P, F]."""
+    K, St = list(kernel_size), list(strides)
+    O = [(int(input_spatial[d]) - K[d]) // St[d] + 1 for d in range(3)]
+    P, F = O[0] * O[1] * O[2], K[0] * K[1] * K[2] * Cin
+    if implementation == 1:
+        return kernel
+    if implementation == 3:
+        if kernel.numel() != P * F * Cout:
+            raise ValueError('implementation-3 kernel has %d weights, expected %d' % (kernel.numel(), P * F * Cout))
+        if data_format == 'channels_first':
+            return kernel.reshape(Cout, P, F).permute(1, 2, 0).contiguous()
+        return kernel.reshape(P, Cout, F).permute(0, 2, 1).contiguous()
+    if implementation == 2:
+        idx = _lc3d_impl2_index(input_spatial, Cin, Cout, K, St, data_format, kernel.device)
+        return kernel.reshape(-1)[idx]
+    raise ValueError('Unrecognized implementation mode: %d.' % implementation)
+
+
+def lc3d_kernel_to_impl(kernel1, implementation, input_spatial, Cin, kernel_size, strides, data_format='channels_last'):
+    """Inverse of lc3d_kernel_from_impl: an implementation-1 kernel [P, F, Cout] in the layout of implementation 2
+    (dense, zeros at unconnected entries) or 3 (sorted sparse values)."""
+    K, St = list(kernel_size), list(strides)
+    O = [(int(input_spatial[d]) - K[d]) // St[d] + 1 for d in range(3)]
+    P, F, Cout = kernel1.shape
+    if implementation == 1:
+        return kernel1
+    if implementation == 3:
+        if data_format == 'channels_first':
+            return kernel1.permute(2, 0, 1).reshape(-1).contiguous()
+        return kernel1.permute(0, 2, 1).reshape(-1).contiguous()
+    I = [int(s) for s in input_spatial]
+    shape = (Cin, I[0], I[1], I[2], Cout, O[0], O[1], O[2]) if data_format == 'channels_first' \
+        else (I[0], I[1], I[2], Cin, O[0], O[1], O[2], Cout)
+    dense = torch.zeros(int(np.prod(shape)), dtype=kernel1.dtype, device=kernel1.device)
+    dense[_lc3d_impl2_index(input_spatial, Cin, Cout, K, St, data_format, kernel1.device).reshape(-1)] = kernel1.reshape(-1)
+    return dense.reshape(shape)
 
 
 def _lc3d_raw(x, k, b, kernel_size, strides, feature_order, act_id, p0, p_count):
@@ -462,6 +568,12 @@ def local_conv3d(inputs, kernel, bias, kernel_size, strides, output_shape, data_
     if p_count is None:
         p_count = P - p0
     b = None if bias is None else bias.to(torch.float32).contiguous().reshape(-1, Cout)
+    if b is not None and data_format == 'channels_first':
+        # K.bias_add(..., 'channels_first') adds reshape(bias, (1, C, o0, o1, o2)): a RAW reshape of the
+        # [o0,o1,o2,C] weight (layers.py:1098-1099 + keras/backend.py), so output[b, f, p] gets bias.flat[f*P + p]
+        if p_count != P:
+            raise NotImplementedError('channels_first bias under position sharding: the raw-reshape rule needs the whole bias')
+        b = b.reshape(Cout, P).t().contiguous()
     feature_order = 1 if data_format == 'channels_first' else 0
     needs_grad = torch.is_grad_enabled() and (x.requires_grad or k.requires_grad or (b is not None and b.requires_grad))
     if needs_grad:

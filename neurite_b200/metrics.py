@@ -15,6 +15,7 @@ import warnings
 import numpy as np
 import torch
 
+from . import utils
 from ._lib import lib, check, ptr, stream_ptr, require_cuda
 
 
@@ -23,17 +24,15 @@ class InvalidArgumentError(ValueError):
 
 
 _WS = {}
+_WS_MAX_STREAMS = 8
 
 
 def _workspace(device, nbytes):
     """Per (device, stream) scratch for the block partials of the reductions (1.6 MB at
-    cfg 3): launches on the same stream are ordered, so one buffer per stream is race free."""
-    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
-    buf = _WS.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
-        _WS[key] = buf
-    return buf
+    cfg 3): launches on the same stream are ordered, so one buffer per stream is race free.
+    The cache is bounded: beyond _WS_MAX_STREAMS streams the oldest entry is dropped (the caching allocator keeps
+    its memory alive for the kernels already queued on that stream), so short-lived streams do not leak buffers."""
+    return utils._stream_scratch(_WS, _WS_MAX_STREAMS, device, nbytes)
 
 
 def dice_sums(y_true, y_pred, normalize=False, check_input_limits=True, group=None):
@@ -296,6 +295,11 @@ class CategoricalCrossentropy:
         if sample_weight is not None:
             sw = torch.as_tensor(sample_weight, dtype=torch.float32, device=p.device)
             sw = sw.expand(p.shape[:-1]).contiguous() if sw.dim() > 0 else sw.expand(p.shape[:-1]).contiguous()
+        if torch.is_grad_enabled() and y_true.requires_grad:
+            # TF autodiff would return dL/dy_true (soft / learned targets); that gradient is not built here and must
+            # not be dropped silently
+            raise NotImplementedError('CategoricalCrossentropy: gradients w.r.t. y_true are not implemented '
+                                      '(detach the target, or use a differentiable torch expression for it)')
         if torch.is_grad_enabled() and y_pred.requires_grad:
             if self.group is not None:
                 raise NotImplementedError('CCE gradients are built for one device')

@@ -429,13 +429,20 @@ flatten_batch_channel = batch_channel_flatten
 _SCRATCH = {}
 
 
-def _scratch(device, nbytes):
+def _stream_scratch(cache, max_streams, device, nbytes):
+    """Scratch buffer per (device, stream), LRU-bounded to `max_streams` entries (dicts keep insertion order)."""
     key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
-    buf = _SCRATCH.get(key)
+    buf = cache.pop(key, None)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
-        _SCRATCH[key] = buf
+    cache[key] = buf                                   # most recently used last
+    while len(cache) > max_streams:
+        cache.pop(next(iter(cache)))
     return buf
+
+
+def _scratch(device, nbytes):
+    return _stream_scratch(_SCRATCH, 8, device, nbytes)
 
 
 def minmax(x, group=None):

@@ -120,7 +120,8 @@ def locally_connected_3d(inputs, kernel, bias, kernel_size, strides=(1, 1, 1), p
     if bias is not None:
         bias = np.asarray(bias, dtype=F32)
         if data_format == 'channels_first':
-            out = out + np.moveaxis(bias, -1, 0)[None]
+            # K.bias_add(channels_first) with a [o0,o1,o2,C] bias: raw reshape to (1, C, o0, o1, o2), not a transpose
+            out = out + bias.reshape((bias.shape[-1],) + bias.shape[:-1])[None]
         else:
             out = out + bias[None]
     return _ACTIVATIONS[activation](out).astype(F32)

@@ -480,3 +480,52 @@ def test_interpn_on_the_volume_grid_uses_tiles_and_stays_exact(ne, monkeypatch):
                 np.testing.assert_array_equal(out, ref)
     monkeypatch.setenv('NRT_WARP_TILE', '0')
     np.testing.assert_array_equal(ne.utils.interpn(dev(vol), dev(loc)).cpu().numpy(), ointerp.interpn(vol, loc))
+
+
+def test_lc3d_implementations_2_and_3_equal_implementation_1(ne):
+    """the layer with the reference's implementation-2 / -3 parameter layouts (converted on the fly) == implementation 1"""
+    from neurite_b200 import layers
+    rng = np.random.default_rng(77)
+    for fmt, xshape in (('channels_last', (3, 6, 5, 7, 4)), ('channels_first', (3, 4, 6, 5, 7))):
+        x = dev(rng.standard_normal(xshape).astype(F32))
+        l1 = layers.LocallyConnected3D(8, (3, 2, 3), strides=(1, 2, 1), data_format=fmt, activation='relu')
+        l1.build(xshape)
+        l1 = l1.cuda()
+        with torch.no_grad():
+            l1.bias.normal_()
+            y1 = l1(x)
+        for impl in (2, 3):
+            li = layers.LocallyConnected3D(8, (3, 2, 3), strides=(1, 2, 1), data_format=fmt, activation='relu', implementation=impl)
+            li.build(xshape)
+            li = li.cuda()
+            with torch.no_grad():
+                li.kernel.copy_(layers.lc3d_kernel_to_impl(l1.kernel, impl, l1.input_spatial, l1.input_filter, l1.kernel_size,
+                                                           l1.strides, fmt))
+                li.bias.copy_(l1.bias)
+                assert torch.equal(li(x), y1)
+    # gradients reach the implementation-3 weight vector through the re-indexing
+    li.kernel.grad = None
+    li(x).sum().backward()
+    assert li.kernel.grad is not None and tuple(li.kernel.grad.shape) == tuple(li.kernel.shape)
+
+
+def test_spatial_transformer_single_transform_and_square_affine(ne):
+    """single_transform applies trf[0] to every volume whatever the transform batch size; affines may come
+    as [B, N+1, N+1]; a transform on another grid shares one mesh across the batch."""
+    rng = np.random.default_rng(31)
+    vol = rng.standard_normal((3, 8, 9, 12, 2)).astype(F32)
+    flow = rng.uniform(-2, 2, (3, 8, 9, 12, 3)).astype(F32)
+    out = ne.layers.SpatialTransformer(single_transform=True)([dev(vol), dev(flow)]).cpu().numpy()
+    ref = ointerp.spatial_transformer(vol, np.repeat(flow[:1], 3, 0))
+    np.testing.assert_array_equal(out, ref)
+    aff = np.tile(np.eye(4, dtype=F32)[None], (3, 1, 1))
+    aff[:, :3, 3] = [[0.5, -1.25, 2.0]] * 3
+    aff[:, 0, 1] = 0.03
+    a = ne.layers.SpatialTransformer()([dev(vol), dev(aff[:, :3, :])])
+    b = ne.layers.SpatialTransformer()([dev(vol), dev(aff)])
+    assert torch.equal(a, b)
+    small = rng.uniform(-1, 1, (3, 4, 5, 6, 3)).astype(F32)                    # output grid != volume grid
+    out = ne.layers.SpatialTransformer()([dev(vol), dev(small)]).cpu().numpy()
+    for bi in range(3):
+        mesh = np.stack(np.meshgrid(*[np.arange(s, dtype=F32) for s in small.shape[1:-1]], indexing='ij'), -1)
+        np.testing.assert_array_equal(out[bi], ointerp.interpn(vol[bi], mesh + small[bi]))

@@ -261,6 +261,23 @@ def gen_lc3d():
              data_format=np.array(fmt), filters=np.array(filters))
 
 
+def gen_lc3d_impl():
+    """Weight orderings of LocallyConnected3D implementations 2 / 3: the reference's own index generator
+    (conv_kernel_idxs, layers.py:1346-1434; build() sorts it, :1012-1021) executed on small geometries.  The fixture
+    holds the sorted (out_flat, in_flat) pairs -- the order of the implementation-3 weight vector and the support of the
+    implementation-2 mask."""
+    ref = 'reference neurite/tf/layers.py:1346-1434 LocallyConnected3D.conv_kernel_idxs (sorted as in build(), :1012-1021)'
+    cases = [('lc3d_impl_idx_cl', (4, 5, 3), 2, 3, (2, 3, 2), (1, 1, 1), 'channels_last'),
+             ('lc3d_impl_idx_cl_s2', (5, 4, 6), 3, 2, (3, 2, 2), (2, 1, 2), 'channels_last'),
+             ('lc3d_impl_idx_cf', (3, 4, 4), 2, 2, (2, 2, 3), (1, 2, 1), 'channels_first')]
+    for name, ishape, cin, cout, ks, st, fmt in cases:
+        idxs = sorted(ne.layers.LocallyConnected3D.conv_kernel_idxs(input_shape=ishape, kernel_shape=ks, strides=st,
+                                                                    padding='valid', filters_in=cin, filters_out=cout,
+                                                                    data_format=fmt))
+        save(name, ref, idxs=np.asarray(idxs, dtype=np.int64), input_shape=np.asarray(ishape), filters_in=np.array(cin),
+             filters_out=np.array(cout), kernel_size=np.asarray(ks), strides=np.asarray(st), data_format=np.array(fmt))
+
+
 # ---------------------------------------------------------------------------------------
 # MutualInformation / soft_quantize  (SURVEY.md 8f-3)
 # ---------------------------------------------------------------------------------------
@@ -381,7 +398,7 @@ def gen_blur():
 
 if __name__ == '__main__':
     only = sys.argv[1:]
-    for fn in (gen_interpn, gen_resize, gen_spatial_transformer, gen_dice, gen_lc3d, gen_mi, gen_blur):
+    for fn in (gen_interpn, gen_resize, gen_spatial_transformer, gen_dice, gen_lc3d, gen_lc3d_impl, gen_mi, gen_blur):
         if not only or fn.__name__[4:] in only:
             fn()
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))

@@ -429,9 +429,12 @@ def _install_tf():
     K.permute_dimensions = lambda x, perm: Tensor(np.transpose(A(x), perm))
 
     def bias_add(x, bias, data_format=None):
+        # tf.keras.backend.bias_add with an N-D bias (ndim(x) - 1 dims): channels_last adds reshape(bias, (1,) + shape);
+        # channels_first adds reshape(bias, (1, shape[-1]) + shape[:-1]) -- a RAW reshape of the [..., C] weight, not a
+        # transpose (keras/backend.py).  Weights trained by Keras carry that layout, so it is the contract.
         b = A(bias)
         if data_format == 'channels_first':
-            b = np.moveaxis(b, -1, 0)
+            b = b.reshape((b.shape[-1],) + b.shape[:-1])
         return Tensor(A(x) + b[None])
     K.bias_add = bias_add
     K.image_data_format = lambda: 'channels_last'
