@@ -700,6 +700,7 @@ warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
   float* s_flow = reinterpret_cast<float*>(smem_raw);                       // [TZ][TY][TX][3]
   float* s_box = s_flow + Cfg::FLOW_ELEMS;                                  // [BZ][BY][BX]
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_box + Cfg::BOX_ELEMS);
+  int* s_org = reinterpret_cast<int*>(bar + 1);                             // mean shift of the tile (box re-staging)
   const int b = blockIdx.z / w.ntz;
   const int x0 = blockIdx.x * Cfg::TX, y0 = blockIdx.y * TY, z0l = (blockIdx.z - b * w.ntz) * TZ;
   if (threadIdx.x == 0) {
@@ -713,33 +714,43 @@ warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
   }
   __syncthreads();                                   // the barrier is initialised
   mbar_wait(bar, 0);
-  // Where does the tile land ON AVERAGE?  Every warp computes the mean shift over the same 3x3x3 lattice of
-  // the STAGED flow tile (27 lanes, one LDS each: no global latency, no block-wide hand-off; all warps get the
-  // same numbers, so the decision is block-uniform).  A large coherent displacement means the speculative box is
-  // useless; the box is then re-staged around the displaced position, so that the halo only has to cover the
-  // variation of the flow inside the tile.  An incoherent flow averages out and keeps the speculative box.
+  // Where does the tile land ON AVERAGE?  ONE warp looks at a 3x3x3 lattice of the STAGED flow tile (27 lanes, one
+  // LDS per component: no global latency) and sums the shifts in 1/64-voxel fixed point with the warp-reduce
+  // instruction (three REDUX instead of fifteen shuffle + add steps).  A large coherent displacement means the
+  // speculative box is useless; the box is then re-staged around the displaced position, so that the halo only has
+  // to cover the variation of the flow inside the tile.  An incoherent flow averages out and keeps the box.
+  // (Measured, profiles/: every warp doing this redundantly costs 12 % on the BASELINE workload -- 8 x 60
+  // instructions per tile are ~9 % of the tile's instruction count -- one warp + one block barrier costs ~1 %.)
   int sz = 0, sy = 0, sx = 0;
-  if (follow) {
-    float mz = 0.f, my = 0.f, mx = 0.f;
-    const int l = threadIdx.x & 31;
-    if (l < 27) {
-      const int jz = l / 9, jy = (l / 3) % 3, jx = l % 3;
-      const int cz = min(z0l + (jz * (TZ - 1)) / 2, w.out_n0 - 1);
-      const int cy = min(y0 + (jy * (TY - 1)) / 2, w.g.S[1] - 1);
-      const int cx = min(x0 + (jx * (Cfg::TX - 1)) / 2, w.g.S[2] - 1);
-      const float* f = s_flow + (((cz - z0l) * TY + (cy - y0)) * Cfg::TX + (cx - x0)) * 3;
-      const float lim = 1048576.f;
-      const float gz_ = ABS ? (float)(w.out_z0 + cz) : 0.f, gy_ = ABS ? (float)cy : 0.f, gx_ = ABS ? (float)cx : 0.f;
-      mz = fminf(fmaxf(f[0] - gz_, -lim), lim);
-      my = fminf(fmaxf(f[1] - gy_, -lim), lim);
-      mx = fminf(fmaxf(f[2] - gx_, -lim), lim);
+  if (follow) {                                      // launch-uniform
+    if (threadIdx.x < 32) {
+      int mz = 0, my = 0, mx = 0;
+      const int l = threadIdx.x;
+      if (l < 27) {
+        const int jz = l / 9, jy = (l / 3) % 3, jx = l % 3;
+        const int cz = min(z0l + (jz * (TZ - 1)) / 2, w.out_n0 - 1);
+        const int cy = min(y0 + (jy * (TY - 1)) / 2, w.g.S[1] - 1);
+        const int cx = min(x0 + (jx * (Cfg::TX - 1)) / 2, w.g.S[2] - 1);
+        const float* f = s_flow + (((cz - z0l) * TY + (cy - y0)) * Cfg::TX + (cx - x0)) * 3;
+        const float lim = 16384.f;                   // |shift| beyond this is clamped: 27 * 64 * 16384 < 2^31
+        const float gz_ = ABS ? (float)(w.out_z0 + cz) : 0.f, gy_ = ABS ? (float)cy : 0.f, gx_ = ABS ? (float)cx : 0.f;
+        mz = __float2int_rn(fminf(fmaxf(f[0] - gz_, -lim), lim) * 64.f);
+        my = __float2int_rn(fminf(fmaxf(f[1] - gy_, -lim), lim) * 64.f);
+        mx = __float2int_rn(fminf(fmaxf(f[2] - gx_, -lim), lim) * 64.f);
+      }
+      mz = __reduce_add_sync(0xffffffffu, mz); my = __reduce_add_sync(0xffffffffu, my); mx = __reduce_add_sync(0xffffffffu, mx);
+      // dead band: 2 voxels in z/y, 4 in x (the TMA needs the x start 16-byte aligned and the x halo is already
+      // rounded up to 4); thresholds in units of 1/64 voxel summed over 27 samples
+      int3 s = make_int3(0, 0, 0);
+      if (abs(mz) >= 2 * 64 * 27 || abs(my) >= 2 * 64 * 27 || abs(mx) >= 4 * 64 * 27) {
+        s.z = __float2int_rn((float)mz * (1.f / (64.f * 27.f)));
+        s.y = __float2int_rn((float)my * (1.f / (64.f * 27.f)));
+        s.x = __float2int_rn((float)mx * (1.f / (64.f * 27.f * 4.f))) * 4;
+      }
+      if (threadIdx.x == 0) { s_org[0] = s.z; s_org[1] = s.y; s_org[2] = s.x; }
     }
-    mz = warp_sum(mz) * (1.f / 27.f); my = warp_sum(my) * (1.f / 27.f); mx = warp_sum(mx) * (1.f / 27.f);
-    // dead band: 2 voxels in z/y, 4 in x (the TMA needs the x start 16-byte aligned and
-    // the x halo is already rounded up to 4)
-    if (fabsf(mz) >= 2.f || fabsf(my) >= 2.f || fabsf(mx) >= 4.f) {
-      sz = __float2int_rn(mz); sy = __float2int_rn(my); sx = __float2int_rn(mx * 0.25f) * 4;
-    }
+    __syncthreads();
+    sz = s_org[0]; sy = s_org[1]; sx = s_org[2];
   }
   const int oz = w.out_z0 + z0l - HALO + sz, oy = y0 - HALO + sy, ox = x0 - Cfg::HX + sx;
   if ((sz | sy | sx) != 0) {                         // block-uniform

@@ -31,13 +31,19 @@ struct MarchGeo {
   int64_t flow_bstride, out_bstride;   // elements between batch items of flow / out
 };
 
-// CCH = channels staged per voxel (a chunk of the volume's C); VEC: lanes own 4-channel quads, else all CCH channels
-template <int CCH, int TY_, int TX_, int HALO_, int AHEAD_>
+// CCH = channels staged per voxel (a chunk of the volume's C); VEC: lanes own 4-channel quads, else all CCH channels.
+// QPT = quads per thread (VEC only): the per-voxel corner setup (~60 instructions) and the 8 corner weights are
+// shared by the QPT quads a thread owns -- with one quad per thread they are 2/3 of all instructions
+// (profiles/r02_ncu_march16.txt: 227 per voxel-quad, issue-bound at 76 %).
+template <int CCH, int TY_, int TX_, int HALO_, int AHEAD_, int QPT_ = 1>
 struct MarchCfg {
   static constexpr int TY = TY_, TX = TX_, HALO = HALO_, AHEAD = AHEAD_;
   static constexpr bool VEC = (CCH % 4 == 0);
-  static constexpr int LPV = VEC ? CCH / 4 : 1;                 // lanes per voxel
-  static constexpr int CPL = CCH / LPV;                         // channels per lane
+  static constexpr int QPT = VEC ? QPT_ : 1;
+  static constexpr int Q = VEC ? CCH / 4 : 1;                   // quads per voxel
+  static constexpr int LPV = VEC ? Q / QPT : 1;                 // lanes per voxel
+  static constexpr int CPL = VEC ? 4 : CCH;                     // channels per lane and pass
+  static_assert(!VEC || Q % QPT == 0, "quads per thread must divide the quads per voxel");
   // the TMA needs a 16-byte aligned start address: (x0 - HX) * C * 4 bytes
   static constexpr int HX = VEC ? HALO : ((CCH % 2 == 0) ? ((HALO + 1) & ~1) : ((HALO + 3) & ~3));
   static constexpr int BY = TY + 2 * HALO, BX = TX + 2 * HX;
@@ -64,12 +70,12 @@ __device__ __forceinline__ void lds_channels(const float* p, float (&v)[CPL]) {
   }
 }
 
-template <int CCH, int TY, int TX, int HALO, int AHEAD, int NW, int METHOD>
+template <int CCH, int TY, int TX, int HALO, int AHEAD, int NW, int METHOD, int QPT = 1>
 __global__ void __launch_bounds__((NW + 1) * 32, 1)
 warp3d_march_kernel(const __grid_constant__ CUtensorMap tm_vol, const __grid_constant__ CUtensorMap tm_flow,
                     const float* __restrict__ vol, float* __restrict__ out, MarchGeo w) {
-  using Cfg = MarchCfg<CCH, TY, TX, HALO, AHEAD>;
-  constexpr int R = Cfg::R, WIN = Cfg::WIN, BX = Cfg::BX, BY = Cfg::BY, LPV = Cfg::LPV, CPL = Cfg::CPL;
+  using Cfg = MarchCfg<CCH, TY, TX, HALO, AHEAD, QPT>;
+  constexpr int R = Cfg::R, WIN = Cfg::WIN, BX = Cfg::BX, BY = Cfg::BY, LPV = Cfg::LPV, CPL = Cfg::CPL, Q = Cfg::Q;
   constexpr int NTC = NW * 32;
   static_assert(Cfg::ITEMS % NTC == 0, "the plane tile must be a whole number of passes of the consumer threads");
   constexpr int ITER = Cfg::ITEMS / NTC;
@@ -150,7 +156,11 @@ warp3d_march_kernel(const __grid_constant__ CUtensorMap tm_vol, const __grid_con
       const float lz = __fadd_rn(fz, fl[0]);
       const float ly = __fadd_rn((float)gy, fl[1]);
       const float lx = __fadd_rn((float)gx, fl[2]);
-      float res[CPL];
+      // Quads of this thread: [q * QPT, (q + 1) * QPT), visited in a rotated order so that the lanes of a quarter
+      // warp -- consecutive voxels when the flow is smooth -- hit distinct 16-byte bank groups: a voxel is Q quads
+      // wide, 8 / Q voxels share a 128-byte bank cycle, so voxel v starts at rotation v * Q / 8.
+      const int rot = (Cfg::VEC && QPT > 1) ? (((vy * TX + vx) * Q) >> 3) : 0;
+      float res[Cfg::QPT][CPL];
       bool ok;
       if (METHOD == NRT_LINEAR) {
         AxisBox<true, WIN> az; AxisBox<true, BY> ay; AxisBox<true, BX> ax;
@@ -160,23 +170,27 @@ warp3d_march_kernel(const __grid_constant__ CUtensorMap tm_vol, const __grid_con
         ok = az.ok & ay.ok & ax.ok;
         int s0 = wbase + az.c0; s0 -= (s0 >= R) ? R : 0;
         int s1 = s0 + az.d;     s1 -= (s1 >= R) ? R : 0;
-        const int inplane = (ay.c0 * BX + ax.c0) * CCH + q * CPL;
+        const int inplane = (ay.c0 * BX + ax.c0) * CCH + q * Cfg::QPT * CPL;
         const float* p0 = reinterpret_cast<const float*>(smem_raw + (size_t)s0 * Cfg::SLOT_BYTES) + inplane;
         const float* p1 = reinterpret_cast<const float*>(smem_raw + (size_t)s1 * Cfg::SLOT_BYTES) + inplane;
         const int dy = ay.d * BX * CCH, dx = ax.d * CCH;
-        float v[8][CPL];
-        lds_channels<CPL>(p0, v[0]);           lds_channels<CPL>(p0 + dx, v[1]);
-        lds_channels<CPL>(p0 + dy, v[2]);      lds_channels<CPL>(p0 + dy + dx, v[3]);
-        lds_channels<CPL>(p1, v[4]);           lds_channels<CPL>(p1 + dx, v[5]);
-        lds_channels<CPL>(p1 + dy, v[6]);      lds_channels<CPL>(p1 + dy + dx, v[7]);
         float k[8];
         corner_weights(az.wlo, az.whi, ay.wlo, ay.whi, ax.wlo, ax.whi, k);
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-          float r = __fadd_rn(0.f, __fmul_rn(k[0], v[0][c]));
+        for (int qi = 0; qi < Cfg::QPT; ++qi) {
+          const int qo = (Cfg::QPT > 1 ? ((qi + rot) % Cfg::QPT) : 0) * CPL;        // offset of this pass's quad
+          float v[8][CPL];
+          lds_channels<CPL>(p0 + qo, v[0]);           lds_channels<CPL>(p0 + qo + dx, v[1]);
+          lds_channels<CPL>(p0 + qo + dy, v[2]);      lds_channels<CPL>(p0 + qo + dy + dx, v[3]);
+          lds_channels<CPL>(p1 + qo, v[4]);           lds_channels<CPL>(p1 + qo + dx, v[5]);
+          lds_channels<CPL>(p1 + qo + dy, v[6]);      lds_channels<CPL>(p1 + qo + dy + dx, v[7]);
 #pragma unroll
-          for (int n = 1; n < 8; ++n) r = __fadd_rn(r, __fmul_rn(k[n], v[n][c]));
-          res[c] = r;
+          for (int c = 0; c < CPL; ++c) {
+            float r = __fadd_rn(0.f, __fmul_rn(k[0], v[0][c]));
+#pragma unroll
+            for (int n = 1; n < 8; ++n) r = __fadd_rn(r, __fmul_rn(k[n], v[n][c]));
+            res[qi][c] = r;
+          }
         }
       } else {
         ok = true;
@@ -184,10 +198,14 @@ warp3d_march_kernel(const __grid_constant__ CUtensorMap tm_vol, const __grid_con
         const int cy = nearest_box<true, BY>(ly, oy, lo_y, hi_y, H - 1, ok);
         const int cx = nearest_box<true, BX>(lx, ox, lo_x, hi_x, W - 1, ok);
         int s0 = wbase + cz; s0 -= (s0 >= R) ? R : 0;
-        lds_channels<CPL>(reinterpret_cast<const float*>(smem_raw + (size_t)s0 * Cfg::SLOT_BYTES) +
-                              (cy * BX + cx) * CCH + q * CPL, res);
+        const float* p0 = reinterpret_cast<const float*>(smem_raw + (size_t)s0 * Cfg::SLOT_BYTES) +
+                          (cy * BX + cx) * CCH + q * Cfg::QPT * CPL;
+#pragma unroll
+        for (int qi = 0; qi < Cfg::QPT; ++qi)
+          lds_channels<CPL>(p0 + (Cfg::QPT > 1 ? ((qi + rot) % Cfg::QPT) : 0) * CPL, res[qi]);
       }
       if (gx >= W || gy >= H) continue;                         // lanes of a partial tile (after the loads: no divergence above)
+      float* op = outb + (((size_t)zl * H + gy) * W + gx) * Ctot + c_base + q * Cfg::QPT * CPL;
       if (!ok) {
         // rare: a corner outside the staged window -> the generic global gather (identical semantics, incl. the
         // fill rule and the resident-plane check that raises the device error flag)
@@ -196,25 +214,37 @@ warp3d_march_kernel(const __grid_constant__ CUtensorMap tm_vol, const __grid_con
         setup_point<3, METHOD>(g, loc, kc);
         const bool oob = g.has_fill ? out_of_bounds<3>(g, loc) : false;
         if (CPL == 4) {
-          gather_point<3, 4, METHOD>(volb, g, kc, oob, c_base + q * 4, *reinterpret_cast<float (*)[4]>(res));
+#pragma unroll
+          for (int qi = 0; qi < Cfg::QPT; ++qi) {
+            float r4[4];
+            gather_point<3, 4, METHOD>(volb, g, kc, oob, c_base + (q * Cfg::QPT + qi) * 4, r4);
+            *reinterpret_cast<float4*>(op + qi * 4) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+          }
         } else {
 #pragma unroll
           for (int c = 0; c < CPL; ++c) {
             float r1[1];
             gather_point<3, 1, METHOD>(volb, g, kc, oob, c_base + c, r1);
-            res[c] = r1[0];
+            op[c] = r1[0];
           }
         }
-      } else if (g.has_fill) {
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) res[c] = fill_if_oob(g, res[c], lz, ly, lx);
+        continue;
       }
-      float* op = outb + (((size_t)zl * H + gy) * W + gx) * Ctot + c_base + q * CPL;
+      if (g.has_fill) {
+#pragma unroll
+        for (int qi = 0; qi < Cfg::QPT; ++qi)
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) res[qi][c] = fill_if_oob(g, res[qi][c], lz, ly, lx);
+      }
       if (CPL == 4) {
-        *reinterpret_cast<float4*>(op) = make_float4(res[0], res[1 % CPL], res[2 % CPL], res[3 % CPL]);
+#pragma unroll
+        for (int qi = 0; qi < Cfg::QPT; ++qi) {
+          const int qo = (Cfg::QPT > 1 ? ((qi + rot) % Cfg::QPT) : 0) * 4;
+          *reinterpret_cast<float4*>(op + qo) = make_float4(res[qi][0], res[qi][1 % CPL], res[qi][2 % CPL], res[qi][3 % CPL]);
+        }
       } else {
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) op[c] = res[c];
+        for (int c = 0; c < CPL; ++c) op[c] = res[0][c];
       }
     }
     // this warp is done with the oldest plane of the window (and with everything older)
@@ -223,9 +253,9 @@ warp3d_march_kernel(const __grid_constant__ CUtensorMap tm_vol, const __grid_con
   }
 }
 
-template <int CCH, int TY, int TX, int HALO, int AHEAD, int NW, int METHOD>
+template <int CCH, int TY, int TX, int HALO, int AHEAD, int NW, int METHOD, int QPT = 1>
 static int launch_march(const float* vol, const float* flow, float* out, MarchGeo mg, cudaStream_t st) {
-  using Cfg = MarchCfg<CCH, TY, TX, HALO, AHEAD>;
+  using Cfg = MarchCfg<CCH, TY, TX, HALO, AHEAD, QPT>;
   static_assert(Cfg::SMEM <= 227 * 1024, "ring does not fit shared memory");
   const int H = mg.g.S[1], W = mg.g.S[2], C = mg.g.C;
   const int ntx = (W + TX - 1) / TX, nty = (H + TY - 1) / TY;
@@ -256,7 +286,7 @@ static int launch_march(const float* vol, const float* flow, float* out, MarchGe
   const uint32_t fb[4] = {(uint32_t)TX * 3, (uint32_t)TY, 1, 1};
   rc = encode_f32_tiled(&tmf, flow, 4, fd, fb, (uint64_t)mg.flow_bstride);
   if (rc != NRT_OK) return rc;
-  auto kern = warp3d_march_kernel<CCH, TY, TX, HALO, AHEAD, NW, METHOD>;
+  auto kern = warp3d_march_kernel<CCH, TY, TX, HALO, AHEAD, NW, METHOD, QPT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM) != cudaSuccess)
     return check_launch("cudaFuncSetAttribute(warp3d_march)");
   const dim3 grid(ntx, nty, (unsigned)gz);
@@ -287,13 +317,21 @@ int warp3d_march(const float* vol, const float* flow, float* out, int B, const i
   if ((mg.src_batch_stride | mg.flow_bstride | mg.out_bstride) & 3) return NRT_OK;   // TMA strides: multiples of 16 bytes
   int rc = 1;
   const int nw16 = env_int("NRT_MARCH_NW", 16);
+  const int qpt = env_int("NRT_MARCH_QPT", 1);
 #define NRT_MARCH(cch, ty, tx, ahead, nw)                                                                      \
   rc = method == NRT_LINEAR ? launch_march<cch, ty, tx, 3, ahead, nw, NRT_LINEAR>(vol, flow, out, mg, st)      \
                             : launch_march<cch, ty, tx, 3, ahead, nw, NRT_NEAREST>(vol, flow, out, mg, st)
+#define NRT_MARCH_Q(cch, ty, tx, ahead, nw, qq)                                                                \
+  rc = method == NRT_LINEAR ? launch_march<cch, ty, tx, 3, ahead, nw, NRT_LINEAR, qq>(vol, flow, out, mg, st)  \
+                            : launch_march<cch, ty, tx, 3, ahead, nw, NRT_NEAREST, qq>(vol, flow, out, mg, st)
   if (C % 16 == 0) {
-    if (nw16 == 8) NRT_MARCH(16, 8, 16, 3, 8); else NRT_MARCH(16, 8, 16, 3, 16);
+    // QPT 2 / 4: a thread owns 8 / 16 channels of its voxel and shares the corner setup between them
+    if (qpt == 4) NRT_MARCH_Q(16, 8, 16, 3, 4, 4);
+    else if (qpt == 2) NRT_MARCH_Q(16, 8, 16, 3, 8, 2);
+    else if (nw16 == 8) NRT_MARCH(16, 8, 16, 3, 8); else NRT_MARCH(16, 8, 16, 3, 16);
   } else if (C % 8 == 0) {
-    if (nw16 == 8) NRT_MARCH(8, 8, 32, 3, 8); else NRT_MARCH(8, 8, 32, 3, 16);
+    if (qpt >= 2) NRT_MARCH_Q(8, 8, 32, 3, 8, 2);
+    else if (nw16 == 8) NRT_MARCH(8, 8, 32, 3, 8); else NRT_MARCH(8, 8, 32, 3, 16);
   } else if (C % 4 == 0) {
     if (nw16 == 8) NRT_MARCH(4, 16, 32, 3, 8); else NRT_MARCH(4, 16, 32, 3, 16);
   } else if (C == 3 && env_int("NRT_MARCH_C3", 1)) {
@@ -301,6 +339,7 @@ int warp3d_march(const float* vol, const float* flow, float* out, int B, const i
   } else if (C == 2 && env_int("NRT_MARCH_C2", 1)) {
     NRT_MARCH(2, 16, 32, 3, 16);
   }
+#undef NRT_MARCH_Q
 #undef NRT_MARCH
   if (rc == 1) return NRT_OK;
   *used = true;

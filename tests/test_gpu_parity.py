@@ -318,7 +318,7 @@ def test_cce_variants_vs_oracle(ne):
 
 # ------------------------------------------------------------------ LocallyConnected3D
 @pytest.mark.parametrize('generic', [False, True])
-@pytest.mark.parametrize('name', golden_names('lc3d_'))
+@pytest.mark.parametrize('name', [n for n in golden_names('lc3d_') if 'impl_idx' not in n])
 def test_lc3d_golden(ne, monkeypatch, name, generic):
     if generic:
         monkeypatch.setenv('NRT_LC3D_GENERIC', '1')

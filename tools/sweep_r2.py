@@ -38,7 +38,7 @@ def timeit(fn, iters=20):
 
 def setenv(env):
     for k in ('NRT_WARP_TILE', 'NRT_WARP_MARCH', 'NRT_MARCH_SMALLC', 'NRT_MARCH_NW', 'NRT_WARP_FOLLOW', 'NRT_MARCH_NSEG',
-              'NRT_WARP_TILE_CFG'):
+              'NRT_WARP_TILE_CFG', 'NRT_MARCH_QPT'):
         os.environ.pop(k, None)
     os.environ.update(env)
 
@@ -55,7 +55,7 @@ def main():
     dev = torch.device('cuda')
     g = torch.Generator(device=dev).manual_seed(0)
     only = os.environ.get('SWEEP_ONLY', '')
-    if only in ('', 'c1'):
+    if only in ('', 'c1', 'quick'):
         B = 8
         vol = torch.randn((B,) + S + (1,), device=dev, generator=g)
         fl = flows_for(B, dev, g)
@@ -65,16 +65,15 @@ def main():
         fl['smooth8'] = (sm / sm.abs().amax() * 8).permute(0, 2, 3, 4, 1).contiguous()
         for fname, flow in fl.items():
             for method in ('linear', 'nearest'):
-                for label, env in (('tile follow', {}), ('tile nofollow', {'NRT_WARP_FOLLOW': '0'}),
-                                   ('tile 4x8x32', {'NRT_WARP_TILE_CFG': '3'})):
+                for label, env in (('tile follow', {}), ('tile nofollow', {'NRT_WARP_FOLLOW': '0'})):
                     setenv(env)
                     ms = timeit(lambda: utils._warp_batched(vol, flow, method, None), 50)
                     gbs = 20.0 * B * V / ms / 1e6
                     print('C=1  B=%d %-8s %-7s %-14s: %.4f ms  %.3e vox/s  frac %.3f' %
                           (B, fname, method, label, ms, B * V / ms * 1e3, gbs / PEAK), flush=True)
         del vol, fl
-    for C in (16, 8, 4, 3, 2, 32):
-        if only not in ('', 'multi', 'c%d' % C):
+    for C in (16, 8, 4, 3, 2, 32) if only != 'quick' else (16, 8):
+        if only not in ('', 'multi', 'quick', 'c%d' % C):
             continue
         B = max(1, min(8, 32 // C))
         vol = torch.randn((B,) + S + (C,), device=dev, generator=g)
@@ -83,6 +82,10 @@ def main():
             if C <= 4:
                 variants.append(('box-tile', {'NRT_WARP_MARCH': '0'}))
             variants += [('march nw16', {'NRT_MARCH_SMALLC': '1'}), ('march nw8', {'NRT_MARCH_SMALLC': '1', 'NRT_MARCH_NW': '8'})]
+            if C % 8 == 0:
+                variants.append(('march qpt2 nw8', {'NRT_MARCH_QPT': '2'}))
+            if C % 16 == 0:
+                variants.append(('march qpt4 nw4', {'NRT_MARCH_QPT': '4'}))
             ref = None
             for method in ('linear',) if fname != 'iid3' else ('linear', 'nearest'):
                 for label, env in variants:
