@@ -185,7 +185,10 @@ def dist_setup(n_gpus):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        import datetime
+        # a short collective timeout: a rank that fails must not leave the others (and the driver) hanging for the
+        # default 10 minutes
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local), timeout=datetime.timedelta(seconds=180))
     return world, rank, local
 
 
@@ -195,10 +198,16 @@ def timed_region(fn, steps, warmup, world, min_preheat_s=0.3):
     sampler something to see."""
     import torch
     import torch.distributed as dist
-    t0 = time.time()
-    while time.time() - t0 < min_preheat_s:
-        fn()
+    if world > 1:
+        # a FIXED number of pre-heat calls: `fn` may contain collectives, so every rank must call it equally often
+        for _ in range(10 if min_preheat_s > 0 else 0):
+            fn()
         torch.cuda.synchronize()
+    else:
+        t0 = time.time()
+        while time.time() - t0 < min_preheat_s:
+            fn()
+            torch.cuda.synchronize()
     for _ in range(max(warmup, 3)):
         fn()
     torch.cuda.synchronize()

@@ -128,13 +128,19 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = global_timer_ns();
   while (!mbar_try_wait(bar, parity)) {
     if (global_timer_ns() - t0 > 4000000000ull) {      // 4 s: a transaction was lost
-      printf("nrt: mbarrier timeout (block %d)\n", blockIdx.x);
+      if ((threadIdx.x & 31) == 0)
+        printf("nrt: mbarrier timeout (block %d thread %d tag %d parity %u smem offset %u)\n", blockIdx.x, threadIdx.x, tag,
+               parity, smem_u32(bar));
+#ifdef NRT_DEBUG_NO_TRAP
+      return;
+#else
       __trap();
+#endif
     }
   }
 }

@@ -1243,8 +1243,11 @@ static int warp_impl(const float* vol, const float* flow, float* out, int B, con
               (obs == 0 || obs >= plane * out_n0 * C), NRT_E_ARG, "batch stride smaller than one batch item");
   if (B == 0 || out_n0 == 0) return NRT_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (D == 3 && C >= 2 && (C > 4 || env_int("NRT_MARCH_SMALLC", 0))) {
-    // many channels: z-marching ring kernel (all channels of a voxel side by side in shared memory)
+  // 3 or more channels: z-marching ring kernel (all channels of a voxel side by side in shared memory).  Measured on
+  // B200 (profiles/r02_sweep_visit1.txt, i.i.d. / smooth flows): C = 3: 0.48 / 0.59 vs 0.39 / 0.42 for the box-tile
+  // kernel, C = 4: 0.56 / 0.68 vs 0.47 / 0.53; C = 2 stays on the box tiles (0.54 / 0.65 vs 0.50 / 0.53).
+  const int march_min_c = env_int("NRT_MARCH_SMALLC", 0) ? 2 : env_int("NRT_MARCH_MINC", 3);
+  if (D == 3 && C >= 2 && C >= march_min_c) {
     bool used = false;
     rc = warp3d_march(vol, flow, out, B, shape, C, method, has_fill, fill, src_z0, src_n0, out_z0, out_n0,
                       halo, err_flag, vbs, fbs, obs, st, &used);

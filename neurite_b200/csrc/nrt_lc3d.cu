@@ -150,7 +150,11 @@ lc3d_stream_kernel(const float* __restrict__ x, const float* __restrict__ kernel
 #pragma unroll
         for (int b = 0; b < BB; ++b) xv[c][b] = __ldg(xp + (int64_t)b * g.x_batch + off);
       }
-      if (i0 == 0) mbar_wait(full + slot, ph);
+      if (i0 == 0) {
+        // parity aliasing guard (see lc3d_patch_kernel): the previous round of this slot must have been consumed
+        if (k >= stages) mbar_wait(empty + slot, ph ^ 1u);
+        mbar_wait(full + slot, ph);
+      }
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         const int i = lane + ((i0 + c) << 5);
@@ -248,7 +252,7 @@ lc3d_patch_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restr
       int k = 0;
       for (int64_t n = blockIdx.x; n < g.pn; n += gridDim.x, ++k) {
         const int slot = k % stages, round = k / stages;
-        if (round >= 1) mbar_wait(empty + slot, (uint32_t)((round - 1) & 1));
+        if (round >= 1) mbar_wait(empty + slot, (uint32_t)((round - 1) & 1), 1000000 + k);
         unsigned char* dst = smem_raw + (size_t)slot * slot_stride;
         mbar_expect_tx(full + slot, blk_bytes + patch_bytes);
         bulk_load_1d(dst, kernel + n * (int64_t)g.F * g.Cout, blk_bytes, full + slot);
@@ -275,7 +279,15 @@ lc3d_patch_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restr
     unsigned long long acc2[BB][2];
 #pragma unroll
     for (int b = 0; b < BB; ++b) acc2[b][0] = acc2[b][1] = 0ull;
-    mbar_wait(full + slot, ph);
+    // Parity aliasing guard.  A group visits only every `groups`-th step, so it may reach for step k while the PREVIOUS
+    // use of this slot (step k - stages, another group's) is still in flight: copies of different steps can complete
+    // out of order (the patch comes through the tensor path, the weights through the bulk path), the barrier would
+    // still be one phase behind and try_wait on the next parity would return at once -- on a half-filled slot.
+    // First make sure the previous round of the slot has been CONSUMED (which implies it had landed); the `empty`
+    // barrier cannot be more than one phase away from what this warp expects, so that wait cannot alias.
+    // (Found on B200 as a 4 s mbarrier timeout at full size, batch 2 -- never with the sanitizer's slower timing.)
+    if (k >= stages) mbar_wait(empty + slot, ph ^ 1u, 2000000 + k);
+    mbar_wait(full + slot, ph, k);
     // lane l reads float4 l, l+32, ... of the weight block: patch feature j = i / CQ advances by 32 / CQ per step
     const float4* wp = w4 + lane;
     const float* xp = sx + (lane >> cq_log2);
@@ -452,6 +464,7 @@ static int launch_patch(const float* x, const float* kernel, const float* bias, 
   int stages = (int)((220 * 1024 - 2 * kLcMaxStages * sizeof(uint64_t) - 128) / (size_t)slot_stride);
   if (stages < 3) return 1;
   if (stages > kLcMaxStages) stages = kLcMaxStages;
+  if (const char* e = getenv("NRT_LC3D_STAGES")) { const int s = atoi(e); if (s >= 3 && s < stages) stages = s; }
   const size_t smem = (size_t)stages * slot_stride + (size_t)stages * 16 + 16;
   CUtensorMap tmx;
   const uint64_t xd[5] = {(uint64_t)g.Cin, (uint64_t)g.I[2], (uint64_t)g.I[1], (uint64_t)g.I[0], (uint64_t)g.B};
@@ -521,7 +534,12 @@ extern "C" int nrt_lc3d_fwd_f32(const float* x, const float* kernel, const float
         int prc;
         if (left >= 8) { prc = launch_patch<4, 2>(x, kernel, bias, out, g, b, cq_log2, st); if (prc <= 0) { rc = prc; b += 8; continue; } }
         else if (left >= 4) { prc = launch_patch<2, 2>(x, kernel, bias, out, g, b, cq_log2, st); if (prc <= 0) { rc = prc; b += 4; continue; } }
-        else { prc = launch_patch<2, 1>(x, kernel, bias, out, g, b, cq_log2, st); if (prc <= 0) { rc = prc; b += 2; continue; } }
+        else {
+          // two batch items: <2,1> = one warp per position doing both, <1,2> = two warps per position, one item each
+          prc = env_int("NRT_LC3D_B2", 12) == 21 ? launch_patch<2, 1>(x, kernel, bias, out, g, b, cq_log2, st)
+                                                  : launch_patch<1, 2>(x, kernel, bias, out, g, b, cq_log2, st);
+          if (prc <= 0) { rc = prc; b += 2; continue; }
+        }
       }
       // batch > 1 is FMA-issue bound: packed fp32x2 FMAs (NRT_LC3D_FFMA2=0 restores the scalar chain)
       if (left >= 8) { rc = p2 ? launch_stream<4, 2, true>(x, kernel, bias, out, g, b, cq_log2, st) : launch_stream<4, 2>(x, kernel, bias, out, g, b, cq_log2, st); b += 8; }

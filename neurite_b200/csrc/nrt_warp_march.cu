@@ -317,7 +317,9 @@ int warp3d_march(const float* vol, const float* flow, float* out, int B, const i
   if ((mg.src_batch_stride | mg.flow_bstride | mg.out_bstride) & 3) return NRT_OK;   // TMA strides: multiples of 16 bytes
   int rc = 1;
   const int nw16 = env_int("NRT_MARCH_NW", 16);
-  const int qpt = env_int("NRT_MARCH_QPT", 1);
+  // quads per thread: 2 by default for 8 / 16-channel chunks (measured, profiles/r02_sweep_visit2.txt: smooth flows
+  // 0.63 vs 0.59 of the roofline at C = 16, i.i.d. flows 0.55 vs 0.56 -- those are bank-conflict bound either way)
+  const int qpt = env_int("NRT_MARCH_QPT", 2);
 #define NRT_MARCH(cch, ty, tx, ahead, nw)                                                                      \
   rc = method == NRT_LINEAR ? launch_march<cch, ty, tx, 3, ahead, nw, NRT_LINEAR>(vol, flow, out, mg, st)      \
                             : launch_march<cch, ty, tx, 3, ahead, nw, NRT_NEAREST>(vol, flow, out, mg, st)
