@@ -529,10 +529,19 @@ extern "C" int nrt_lc3d_fwd_f32(const float* x, const float* kernel, const float
     const bool patch = env_int("NRT_LC3D_PATCH", 1) != 0;
     while (b < B && rc == NRT_OK) {              // batch items per pass = BB * WPP (weights streamed once per pass)
       const int left = B - b;
+      if (patch && left == 1 && env_int("NRT_LC3D_PATCH1", 0)) {
+        const int prc = launch_patch<1, 1>(x, kernel, bias, out, g, b, cq_log2, st);
+        if (prc <= 0) { rc = prc; b += 1; continue; }
+      }
       if (patch && left >= 2) {
         // batch > 1: the position's input patch arrives by TMA next to its weight block (lc3d_patch_kernel)
         int prc;
-        if (left >= 8) { prc = launch_patch<4, 2>(x, kernel, bias, out, g, b, cq_log2, st); if (prc <= 0) { rc = prc; b += 8; continue; } }
+        if (left >= 8) {
+          // <4,2>: two warps per position, four batch items each; <2,4>: four warps, two items each (more warps in flight)
+          prc = env_int("NRT_LC3D_B8", 42) == 24 ? launch_patch<2, 4>(x, kernel, bias, out, g, b, cq_log2, st)
+                                                  : launch_patch<4, 2>(x, kernel, bias, out, g, b, cq_log2, st);
+          if (prc <= 0) { rc = prc; b += 8; continue; }
+        }
         else if (left >= 4) { prc = launch_patch<2, 2>(x, kernel, bias, out, g, b, cq_log2, st); if (prc <= 0) { rc = prc; b += 4; continue; } }
         else {
           // two batch items: <2,1> = one warp per position doing both, <1,2> = two warps per position, one item each
