@@ -292,6 +292,177 @@ resize3d_kernel(const float* __restrict__ vol, float* __restrict__ out, ResizeGe
 }
 
 // ---------------------------------------------------------------------------------------
+// resize3d_tile_kernel: the linear z-marching kernel with its SOURCE staged in shared memory.  resize3d_kernel issues
+// its corner loads to L1/L2 when an output plane enters a new source cell and then waits ~600 cycles for them with
+// 3 CTAs per SM: it is latency-bound (74 % issue-active, 0.43 of the roofline; a packed two-voxel variant that
+// halves the arithmetic is no faster).  An up-sampling zoom reads a SMALL source box per output tile -- 32 x 8 x 32
+// outputs of a x2 zoom touch 18 x 6 x 18 source voxels -- so the CTA fetches that box with ONE TMA tensor load
+// (coordinates from the tile's own table entries, extents = the largest box any tile needs, computed on the host
+// with the same fp32 linspace arithmetic) and every corner read becomes a ~30-cycle LDS.
+// A tile whose box would not fit the staged extents (cannot happen when host and device agree) or a zoom whose
+// boxes are larger than the budget (down-sampling) takes resize3d_kernel.
+// ---------------------------------------------------------------------------------------
+struct ResizeBox { int bz, by, bx; };            // staged source extents (bx already padded for the TMA alignment)
+
+template <int CT, int TZ>
+__global__ void __launch_bounds__(256)
+resize3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol, const float* __restrict__ vol, float* __restrict__ out,
+                     ResizeGeo w, ResizeBox bxs, int ntz, int nty, int ntx, int xalign) {
+  constexpr int TY = 8, TX = 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* s_box = reinterpret_cast<float*>(smem_raw);                                     // [bz][by][bx][CT]
+  const int box_elems = bxs.bz * bxs.by * bxs.bx * CT;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)box_elems * 4 + 15) & ~(size_t)15));
+  int* s_lo = reinterpret_cast<int*>(bar + 1);                                           // box origin (source voxels)
+  __shared__ AxisEntry s_ax[TZ + TY + TX];
+  __shared__ int s_i[2][TZ + TY + TX];                                                   // i0 / i1 per table entry
+  const Geo& g = w.g;
+  int tile = blockIdx.x;
+  const int tx = tile % ntx; tile /= ntx;
+  const int ty = tile % nty; tile /= nty;
+  const int tz = tile % ntz;
+  const int b = tile / ntz;
+  const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;            // z0 relative to the produced slab
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (threadIdx.x < TZ + TY + TX) {
+    const int t = threadIdx.x;
+    const int d = t < TZ ? 0 : (t < TZ + TY ? 1 : 2);
+    const int i = d == 0 ? w.out_z0 + z0 + t : (d == 1 ? y0 + (t - TZ) : x0 + (t - TZ - TY));
+    AxisEntry e;
+    int i0 = -1, i1 = -1;
+    if (i < w.M[d] && (d != 0 || z0 + t < w.out_n0)) {
+      // tf.linspace(0, S-1, M): endpoints exact, interior 0 + delta*i  (utils.py:259)
+      const float loc = (i == w.M[d] - 1 && w.M[d] > 1) ? (float)(g.S[d] - 1) : __fmul_rn(w.delta[d], (float)i);
+      const Axis a = axis_linear(loc, (float)(g.S[d] - 1), g.S[d] - 1);
+      i0 = a.i0; i1 = a.i1; e.wlo = a.wlo; e.whi = a.whi;
+    } else {
+      e.wlo = e.whi = 0.f;
+    }
+    e.o0 = e.o1 = 0;
+    s_ax[t] = e; s_i[0][t] = i0; s_i[1][t] = i1;
+  }
+  __syncthreads();
+  // box origin = first corner of the tile's first output per axis (linspace is monotonic); x aligned for the TMA
+  if (threadIdx.x == 0) {
+    int lo[3], ok = 1;
+    const int first[3] = {0, TZ, TZ + TY}, count[3] = {TZ, TY, TX}, ext[3] = {bxs.bz, bxs.by, bxs.bx};
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = s_i[0][first[d]];
+      if (d == 2) lo[d] -= lo[d] % xalign;
+      int hi = lo[d];
+      for (int k = 0; k < count[d]; ++k) hi = max(hi, s_i[1][first[d] + k]);
+      ok &= (hi - lo[d] + 1 <= ext[d]);
+    }
+    s_lo[0] = lo[0]; s_lo[1] = lo[1]; s_lo[2] = lo[2]; s_lo[3] = ok;
+    if (ok) {
+      mbar_expect_tx(bar, (uint32_t)(box_elems * sizeof(float)));
+      tma_load_4d(s_box, &tm_vol, bar, lo[2] * CT, lo[1], lo[0], b);
+    }
+  }
+  __syncthreads();
+  const bool staged = s_lo[3] != 0;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int ox = x0 + lane, oy = y0 + wid;
+  // offsets of this thread's table entries: box-relative when staged, else into the global volume
+  const int sz_ = staged ? bxs.by * bxs.bx * CT : g.S[1] * g.S[2] * CT;
+  const int sy_ = staged ? bxs.bx * CT : g.S[2] * CT;
+  const int lz = staged ? s_lo[0] : 0, ly = staged ? s_lo[1] : 0, lx = staged ? s_lo[2] : 0;
+  if (staged) mbar_wait(bar, 0);
+  if (oy >= w.M[1] || ox >= w.M[2]) return;
+  const AxisEntry ey = s_ax[TZ + wid], ex = s_ax[TZ + TY + lane];
+  const int y_o0 = (s_i[0][TZ + wid] - ly) * sy_, y_o1 = (s_i[1][TZ + wid] - ly) * sy_;
+  const int x_o0 = (s_i[0][TZ + TY + lane] - lx) * CT, x_o1 = (s_i[1][TZ + TY + lane] - lx) * CT;
+  const float* src = staged ? s_box : vol + (size_t)b * w.src_batch_stride;
+  float* outb = out + ((size_t)b * w.out_vox + ((size_t)z0 * w.M[1] + oy) * w.M[2] + ox) * CT;
+  const size_t plane = (size_t)w.M[1] * w.M[2] * CT;
+  const float* q00 = src + y_o0 + x_o0; const float* q01 = src + y_o0 + x_o1;
+  const float* q10 = src + y_o1 + x_o0; const float* q11 = src + y_o1 + x_o1;
+  float lo[4][CT], hi[4][CT];
+  int cur0 = -1, cur1 = -1;
+#pragma unroll 1
+  for (int z = 0; z < TZ; ++z, outb += plane) {
+    if (z0 + z >= w.out_n0) break;
+    const AxisEntry ez = s_ax[z];
+    const int z_o0 = (s_i[0][z] - lz) * sz_, z_o1 = (s_i[1][z] - lz) * sz_;
+    if (z_o0 != cur0) {
+      if (z_o0 == cur1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int c = 0; c < CT; ++c) lo[q][c] = hi[q][c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+          lo[0][c] = q00[z_o0 + c]; lo[1][c] = q01[z_o0 + c];
+          lo[2][c] = q10[z_o0 + c]; lo[3][c] = q11[z_o0 + c];
+        }
+      }
+      cur0 = z_o0;
+    }
+    if (z_o1 != cur1) {
+      if (z_o1 == cur0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int c = 0; c < CT; ++c) hi[q][c] = lo[q][c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+          hi[0][c] = q00[z_o1 + c]; hi[1][c] = q01[z_o1 + c];
+          hi[2][c] = q10[z_o1 + c]; hi[3][c] = q11[z_o1 + c];
+        }
+      }
+      cur1 = z_o1;
+    }
+    const float w00 = __fmul_rn(ez.wlo, ey.wlo), w01 = __fmul_rn(ez.wlo, ey.whi);
+    const float w10 = __fmul_rn(ez.whi, ey.wlo), w11 = __fmul_rn(ez.whi, ey.whi);
+    const float k0 = __fmul_rn(w00, ex.wlo), k1 = __fmul_rn(w00, ex.whi), k2 = __fmul_rn(w01, ex.wlo), k3 = __fmul_rn(w01, ex.whi);
+    const float k4 = __fmul_rn(w10, ex.wlo), k5 = __fmul_rn(w10, ex.whi), k6 = __fmul_rn(w11, ex.wlo), k7 = __fmul_rn(w11, ex.whi);
+    float res[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      float r = __fadd_rn(0.f, __fmul_rn(k0, lo[0][c]));
+      r = __fadd_rn(r, __fmul_rn(k1, lo[1][c]));
+      r = __fadd_rn(r, __fmul_rn(k2, lo[2][c]));
+      r = __fadd_rn(r, __fmul_rn(k3, lo[3][c]));
+      r = __fadd_rn(r, __fmul_rn(k4, hi[0][c]));
+      r = __fadd_rn(r, __fmul_rn(k5, hi[1][c]));
+      r = __fadd_rn(r, __fmul_rn(k6, hi[2][c]));
+      r = __fadd_rn(r, __fmul_rn(k7, hi[3][c]));
+      res[c] = r;
+    }
+    if (CT == 4) {
+      *reinterpret_cast<float4*>(outb) = make_float4(res[0], res[1 % CT], res[2 % CT], res[3 % CT]);
+    } else if (CT == 2) {
+      *reinterpret_cast<float2*>(outb) = make_float2(res[0], res[1 % CT]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < CT; ++c) outb[c] = res[c];
+    }
+  }
+}
+
+// largest source extent any tile of T outputs needs along one axis, with the device's fp32 linspace arithmetic
+static int resize_axis_extent(int S, int M, float delta, int first, int count, int T, int align) {
+  int ext = 1;
+  for (int t0 = first; t0 < first + count; t0 += T) {
+    const int t1 = (t0 + T - 1 < first + count - 1) ? t0 + T - 1 : first + count - 1;
+    auto cell = [&](int i, int& i0, int& i1) {
+      const float loc = (i == M - 1 && M > 1) ? (float)(S - 1) : delta * (float)i;
+      float f0 = floorf(loc); f0 = f0 < 0.f ? 0.f : (f0 > (float)(S - 1) ? (float)(S - 1) : f0);
+      float f1 = f0 + 1.0f; f1 = f1 > (float)(S - 1) ? (float)(S - 1) : f1;
+      i0 = (int)f0; i1 = (int)f1;
+    };
+    int a0, a1, b0, b1;
+    cell(t0, a0, a1); cell(t1, b0, b1);
+    int lo = a0 - a0 % align;
+    int hi = b1 > a1 ? b1 : a1;
+    if (hi - lo + 1 > ext) ext = hi - lo + 1;
+  }
+  return ext;
+}
+
+// ---------------------------------------------------------------------------------------
 // resize3d_x2_kernel: the linear z-marching kernel above with TWO x positions per thread.  resize3d_kernel is
 // issue-bound (~115 instructions per output voxel at C = 3, 60 of them the reference's separately rounded
 // multiplies and adds); here the two voxels of a thread form the halves of packed fp32x2 registers, so every one of
@@ -1318,8 +1489,48 @@ int nrt_resize_f32(const float* vol, float* out, int B, const int32_t* in_shape,
     int TZ = tze ? atoi(tze) : (out_n0 >= 64 ? 32 : (out_n0 >= 24 ? 16 : 8));
     if (TZ != 16 && TZ != 32 && TZ != 64) TZ = 8;
     if (method != NRT_LINEAR || C < 1 || C > 4) TZ = 8;          // the marching path is linear, C = 1..4
+    // up-sampling: source box of every output tile staged by TMA (resize3d_tile_kernel)
+    if (method == NRT_LINEAR && C >= 1 && C <= 4 && env_int("NRT_RESIZE_TILE", 1) && aligned16(vol) &&
+        (rg.g.S[2] * C) % 4 == 0 && ((C != 2 && C != 4) || (reinterpret_cast<uintptr_t>(out) & (C == 4 ? 15u : 7u)) == 0)) {
+      const int tzt = (TZ == 64) ? 32 : TZ;
+      const int xalign = (C == 4) ? 1 : (C == 2 ? 2 : 4);
+      ResizeBox bxs;
+      bxs.bz = resize_axis_extent(rg.g.S[0], rg.M[0], rg.delta[0], out_z0, out_n0, tzt, 1);
+      bxs.by = resize_axis_extent(rg.g.S[1], rg.M[1], rg.delta[1], 0, rg.M[1], 8, 1);
+      bxs.bx = resize_axis_extent(rg.g.S[2], rg.M[2], rg.delta[2], 0, rg.M[2], 32, xalign);
+      bxs.bx = (bxs.bx + xalign - 1) / xalign * xalign;
+      const size_t box_bytes = (size_t)bxs.bz * bxs.by * bxs.bx * C * 4;
+      const int ntz3 = (out_n0 + tzt - 1) / tzt, nty3 = (rg.M[1] + 7) / 8, ntx3 = (rg.M[2] + 31) / 32;
+      const int64_t grid3 = (int64_t)B * ntz3 * nty3 * ntx3;
+      if (box_bytes <= 48 * 1024 && bxs.bx * C <= 256 && bxs.by <= 256 && bxs.bz <= 256 && grid3 <= 0x7fffffffLL) {
+        CUtensorMap tmv;
+        const uint64_t vd[4] = {(uint64_t)rg.g.S[2] * C, (uint64_t)rg.g.S[1], (uint64_t)rg.g.S[0], (uint64_t)B};
+        const uint32_t vb[4] = {(uint32_t)(bxs.bx * C), (uint32_t)bxs.by, (uint32_t)bxs.bz, 1};
+        int erc = encode_f32_4d(&tmv, vol, vd, vb);
+        if (erc != NRT_OK) return erc;
+        const size_t smem = ((box_bytes + 15) & ~(size_t)15) + 32;
+#define NRT_RESIZE_TILE(CT, TZZ)                                                                                          \
+        do {                                                                                                              \
+          auto kern = resize3d_tile_kernel<CT, TZZ>;                                                                      \
+          if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)          \
+            return check_launch("cudaFuncSetAttribute(resize3d_tile)");                                                   \
+          kern<<<(int)grid3, 256, smem, st>>>(tmv, vol, out, rg, bxs, ntz3, nty3, ntx3, xalign);                          \
+        } while (0)
+#define NRT_RESIZE_TILE_C(CT)                                                                                             \
+        do { if (tzt == 8) NRT_RESIZE_TILE(CT, 8); else if (tzt == 16) NRT_RESIZE_TILE(CT, 16); else NRT_RESIZE_TILE(CT, 32); } while (0)
+        switch (C) {
+          case 1: NRT_RESIZE_TILE_C(1); break;
+          case 2: NRT_RESIZE_TILE_C(2); break;
+          case 3: NRT_RESIZE_TILE_C(3); break;
+          default: NRT_RESIZE_TILE_C(4); break;
+        }
+#undef NRT_RESIZE_TILE_C
+#undef NRT_RESIZE_TILE
+        return check_launch("resize3d_tile_kernel");
+      }
+    }
     // two x positions per thread on packed fp32x2 arithmetic (linear, C = 1..4, even row pitch for the vector stores)
-    if (method == NRT_LINEAR && C >= 1 && C <= 4 && env_int("NRT_RESIZE_X2", 1) && (rg.M[2] * C) % (C == 2 ? 4 : 2) == 0 &&
+    if (method == NRT_LINEAR && C >= 1 && C <= 4 && env_int("NRT_RESIZE_X2", 0) && (rg.M[2] * C) % (C == 2 ? 4 : 2) == 0 &&
         (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && (rg.out_vox * C) % 4 == 0) {
       const int tz2 = (TZ == 64) ? 32 : TZ;
       const int ntz2 = (out_n0 + tz2 - 1) / tz2, nty2 = (rg.M[1] + 15) / 16, ntx2 = (rg.M[2] + 31) / 32;

@@ -85,21 +85,36 @@ def _stage_on_host(t, group):
     return t.is_cuda and dist.get_backend(group) == 'gloo'
 
 
+def _dense_pieces(t):
+    """A [B, planes, ...] view that is dense inside every batch item -> pieces that are contiguous as they are
+    (the whole view, or one per batch item), so that NCCL can send / receive them in place, without staging copies."""
+    if t.is_contiguous():
+        return [t]
+    if t.dim() >= 2 and all(t[b].is_contiguous() for b in range(t.shape[0])):
+        return [t[b] for b in range(t.shape[0])]
+    return None
+
+
 def _post_exchange(sends, recvs, group):
-    """Post all (tensor, peer) sends and receives as ONE batch (ncclGroupStart/End under NCCL).  Returns a
-    function that makes the current stream wait for them (and finishes the host staging under gloo)."""
+    """Post all (tensor, peer) sends and receives as ONE batch (ncclGroupStart/End under NCCL).  Plane ranges of a
+    batched slab are strided across the batch: they travel as one op per batch item, in place.  Returns a function
+    that makes the current stream wait for them (and finishes the host staging under gloo)."""
     ops, fix = [], []
     for t, peer in sends:
-        buf = t.contiguous()
-        if _stage_on_host(buf, group):
-            buf = buf.cpu()
-        ops.append(dist.P2POp(dist.isend, buf, _peer(peer, group), group))
+        pieces = None if _stage_on_host(t, group) else _dense_pieces(t)
+        if pieces is None:
+            buf = t.contiguous()
+            pieces = [buf.cpu() if _stage_on_host(buf, group) else buf]
+        for piece in pieces:
+            ops.append(dist.P2POp(dist.isend, piece, _peer(peer, group), group))
     for t, peer in recvs:
-        direct = t.is_contiguous() and not _stage_on_host(t, group)
-        buf = t if direct else torch.empty(t.shape, dtype=t.dtype, device='cpu' if _stage_on_host(t, group) else t.device)
-        if not direct:
+        pieces = None if _stage_on_host(t, group) else _dense_pieces(t)
+        if pieces is None:
+            buf = torch.empty(t.shape, dtype=t.dtype, device='cpu' if _stage_on_host(t, group) else t.device)
             fix.append((t, buf))
-        ops.append(dist.P2POp(dist.irecv, buf, _peer(peer, group), group))
+            pieces = [buf]
+        for piece in pieces:
+            ops.append(dist.P2POp(dist.irecv, piece, _peer(peer, group), group))
     works = dist.batch_isend_irecv(ops) if ops else []
 
     def wait():
