@@ -85,43 +85,34 @@ def _stage_on_host(t, group):
     return t.is_cuda and dist.get_backend(group) == 'gloo'
 
 
-def _dense_pieces(t):
-    """A [B, planes, ...] view that is dense inside every batch item -> pieces that are contiguous as they are
-    (the whole view, or one per batch item), so that NCCL can send / receive them in place, without staging copies."""
-    if t.is_contiguous():
-        return [t]
-    if t.dim() >= 2 and all(t[b].is_contiguous() for b in range(t.shape[0])):
-        return [t[b] for b in range(t.shape[0])]
-    return None
-
-
 def _post_exchange(sends, recvs, group):
-    """Post all (tensor, peer) sends and receives as ONE batch (ncclGroupStart/End under NCCL).  Plane ranges of a
-    batched slab are strided across the batch: they travel as one op per batch item, in place.  Returns a function
-    that makes the current stream wait for them (and finishes the host staging under gloo)."""
+    """Post all (tensor, peer) sends and receives as ONE batch (ncclGroupStart/End under NCCL).  Wire protocol: a
+    [B, planes, ...] tensor always travels as B messages, one per batch item -- plane ranges of a batched slab are
+    strided across the batch but dense inside an item, so they are sent and received IN PLACE, and both ends agree
+    on the message count whatever the memory layout on either side.  Returns a function that makes the current
+    stream wait for them (and finishes the host staging under gloo, which cannot move CUDA memory)."""
     ops, fix = [], []
     for t, peer in sends:
-        pieces = None if _stage_on_host(t, group) else _dense_pieces(t)
-        if pieces is None:
-            buf = t.contiguous()
-            pieces = [buf.cpu() if _stage_on_host(buf, group) else buf]
-        for piece in pieces:
+        for b in range(t.shape[0]):
+            piece = t[b] if t[b].is_contiguous() else t[b].contiguous()
+            if _stage_on_host(piece, group):
+                piece = piece.cpu()
             ops.append(dist.P2POp(dist.isend, piece, _peer(peer, group), group))
     for t, peer in recvs:
-        pieces = None if _stage_on_host(t, group) else _dense_pieces(t)
-        if pieces is None:
-            buf = torch.empty(t.shape, dtype=t.dtype, device='cpu' if _stage_on_host(t, group) else t.device)
-            fix.append((t, buf))
-            pieces = [buf]
-        for piece in pieces:
+        for b in range(t.shape[0]):
+            piece = t[b]
+            if not piece.is_contiguous() or _stage_on_host(piece, group):
+                buf = torch.empty(piece.shape, dtype=piece.dtype, device='cpu' if _stage_on_host(piece, group) else piece.device)
+                fix.append((piece, buf))
+                piece = buf
             ops.append(dist.P2POp(dist.irecv, piece, _peer(peer, group), group))
     works = dist.batch_isend_irecv(ops) if ops else []
 
     def wait():
         for w in works:
             w.wait()                       # NCCL: a stream dependency, the host does not block
-        for t, buf in fix:
-            t.copy_(buf, non_blocking=True)
+        for dst, buf in fix:
+            dst.copy_(buf, non_blocking=True)
     return wait
 
 
