@@ -20,10 +20,12 @@ except Exception as e:
     print(name, 'unreadable', e)
 PY
 }
-run slab_c1 "--op warp_slab --slab-channels 1 --steps 200"
-run slab_c16 "--op warp_slab --slab-channels 16 --steps 100"
+if [ "$N" != "8" ]; then
+  run slab_c1 "--op warp_slab --slab-channels 1 --steps 200"
+  run slab_c16 "--op warp_slab --slab-channels 16 --steps 100"
+  run cfg5 "--op cfg5 --cfg5-steps 5"
+fi
 run slab_c16_b8 "--op warp_slab --slab-channels 16 --slab-batch 8 --steps 50"
-run cfg5 "--op cfg5 --cfg5-steps 5"
 run dice "--op dice"
 run default "--steps 20 --warmup 5"
 tail -5 gpurun_out/r2m${N}.err
