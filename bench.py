@@ -664,51 +664,55 @@ def slab_record(args, world, rank, dev, channels=1, batch=1):
         ms = timed_region(lambda: utils._warp_views(vol, flow, out, SHAPE[0], 0, None, 0, 0), steps, 3, world)
         rec['overlap'] = {'ms_per_step': ms / steps, 'value': B * V * steps / (ms * 1e-3), 'unit': 'voxels/s'}
         return rec
-    plan = nd.SlabWarper(SHAPE[0], halo)
     out = torch.empty(tuple(flow.shape[:-1]) + (C,), dtype=torch.float32, device=dev)
-    # the producer of the volume writes its planes straight into the plan's buffer (zero-copy hand-over): the step is
-    # exchange + kernels only
-    src = plan.source_view(vol)
-    src.copy_(vol)
-    ms_ov = timed_region(lambda: plan(src, flow, out), steps, 3, world, min_preheat_s=0.1)
-    plan.check()
+    peak, _ = measured_peak()
+
+    def measure(transport):
+        plan = nd.SlabWarper(SHAPE[0], halo, transport=transport)
+        # the producer of the volume writes its planes straight into the plan's buffer (zero-copy hand-over): the
+        # step is exchange + kernels only
+        src = plan.source_view(vol)
+        src.copy_(vol)
+        ms_ov = timed_region(lambda: plan(src, flow, out), steps, 3, world, min_preheat_s=0.1)
+        plan.check()
+        # the two ingredients on their own: the halo exchange (no kernels) and the three launches (no exchange)
+        ext, pad = plan._buffers(vol), plan._pad
+        mid = ext[:, pad:pad + nz]
+        ms_ex = timed_region(lambda: plan._exchange(ext, mid)(), steps, 3, world, min_preheat_s=0.0)
+
+        def kernels_only():
+            i_lo, i_hi = plan.lo_pad, nz - plan.hi_pad
+            srcx = ext[:, pad - plan.lo_pad:pad + nz + plan.hi_pad]
+            plan._kernel(mid, flow[:, i_lo:i_hi], out[:, i_lo:i_hi], z0, z0 + i_lo)
+            if i_lo > 0:
+                plan._kernel(srcx, flow[:, :i_lo], out[:, :i_lo], z0 - plan.lo_pad, z0)
+            if i_hi < nz:
+                plan._kernel(srcx, flow[:, i_hi:], out[:, i_hi:], z0 - plan.lo_pad, z0 + i_hi)
+        ms_k = timed_region(kernels_only, steps, 3, world, min_preheat_s=0.0)
+        plan._err.zero_()
+        return {'transport': plan.active_transport, 'ms_per_step': ms_ov / steps, 'value': B * V * steps / (ms_ov * 1e-3),
+                'unit': 'voxels/s', 'exchange_only_us': ms_ex / steps * 1e3, 'kernels_only_us': ms_k / steps * 1e3,
+                'roofline_frac_aggregate': model_bytes / (ms_ov / steps * 1e-3) / 1e9 / (peak * world),
+                'limiter': 'the halo exchange' if ms_ex > ms_k else 'the three kernel launches'}
+    rec['overlap'] = measure('auto')
+    rec['overlap']['what'] = ('SlabWarper: interior planes warped while the halo planes travel; no host sync in the step; '
+                              'transport peer = halos pulled out of the neighbours\' symmetric-memory buffers over NVLink, '
+                              'nccl = one ncclGroup of send/recv')
+    if rec['overlap']['transport'] == 'peer':
+        rec['overlap_nccl'] = measure('nccl')
     ser_steps = max(20, steps // 4)
     ms_ser = timed_region(lambda: nd.warp_slab(vol, flow, SHAPE[0], mode='serial', halo=halo), ser_steps, 3, world, min_preheat_s=0.0)
-    # the two ingredients on their own: the neighbour exchange (one ncclGroup of <= 4 send/recv, no kernels) and the
-    # three launches (no exchange): which one bounds the step
-    ext = plan._buffers(vol)
-    mid = ext[:, plan.lo_pad:plan.lo_pad + nz]
-
-    def exchange_only():
-        sends, recvs = [], []
-        if rank > 0:
-            sends.append((mid[:, :halo], rank - 1))
-            recvs.append((ext[:, :plan.lo_pad], rank - 1))
-        if rank < world - 1:
-            sends.append((mid[:, nz - halo:], rank + 1))
-            recvs.append((ext[:, plan.lo_pad + nz:], rank + 1))
-        nd._post_exchange(sends, recvs, None)()
-    ms_ex = timed_region(exchange_only, steps, 3, world, min_preheat_s=0.0)
-
-    def kernels_only():
-        i_lo, i_hi = plan.lo_pad, nz - plan.hi_pad
-        plan._kernel(mid, flow[:, i_lo:i_hi], out[:, i_lo:i_hi], z0, z0 + i_lo)
-        if i_lo > 0:
-            plan._kernel(ext, flow[:, :i_lo], out[:, :i_lo], z0 - plan.lo_pad, z0)
-        if i_hi < nz:
-            plan._kernel(ext, flow[:, i_hi:], out[:, i_hi:], z0 - plan.lo_pad, z0 + i_hi)
-    ms_k = timed_region(kernels_only, steps, 3, world, min_preheat_s=0.0)
-    plan._err.zero_()
-    peak, _ = measured_peak()
-    rec.update({
-        'overlap': {'ms_per_step': ms_ov / steps, 'value': B * V * steps / (ms_ov * 1e-3), 'unit': 'voxels/s',
-                    'what': 'SlabWarper: interior planes warped while the halo planes travel; no host sync in the step'},
-        'serial': {'ms_per_step': ms_ser / ser_steps, 'value': B * V * ser_steps / (ms_ser * 1e-3), 'unit': 'voxels/s',
-                   'what': 'round-1 path: exchange, then one launch, err.item() every step'},
-        'exchange_only_us': ms_ex / steps * 1e3, 'kernels_only_us': ms_k / steps * 1e3,
-        'roofline_frac_aggregate': model_bytes / (ms_ov / steps * 1e-3) / 1e9 / (peak * world),
-        'limiter': 'the neighbour ncclSend/Recv group' if ms_ex > ms_k else 'the three kernel launches',
-    })
+    rec['serial'] = {'ms_per_step': ms_ser / ser_steps, 'value': B * V * ser_steps / (ms_ser * 1e-3), 'unit': 'voxels/s',
+                     'what': 'round-1 path: NCCL exchange, then one launch, err.item() every step'}
+    # strong-scaling reference: the same batch on ONE GPU (no exchange), timed on rank 0's device
+    g1 = torch.Generator(device=dev).manual_seed(78)
+    vol1 = torch.randn((B,) + SHAPE + (C,), device=dev, generator=g1)
+    flow1 = torch.rand((B,) + SHAPE + (3,), device=dev, generator=g1) * 6 - 3
+    out1 = torch.empty_like(vol1)
+    ms_one = timed_region(lambda: utils._warp_views(vol1, flow1, out1, SHAPE[0], 0, None, 0, 0), max(20, steps // 4), 3, world,
+                          min_preheat_s=0.0)
+    rec['one_gpu_whole_volume'] = {'ms_per_step': ms_one / max(20, steps // 4),
+                                   'speedup_of_the_slab_plan': (ms_one / max(20, steps // 4)) / rec['overlap']['ms_per_step']}
     return rec
 
 
@@ -756,9 +760,19 @@ def cfg5_record(args, world, rank, dev):
         if job.plan is not None:
             job.plan.check()
         nvox_rank = B * job.nz * SHAPE[1] * SHAPE[2]
+        # per-stage times: in slab mode the ranks at the ends of the volume have smaller UNet windows and then WAIT in
+        # the halo exchange for their neighbours, so rank 0's 'warp' would mostly be that wait; report the largest
+        # UNet time and the SMALLEST warp / Dice times over the ranks (the rank that arrives last does not wait)
+        st_t = torch.tensor(stage_ms, dtype=torch.float64, device=dev)
+        st_max, st_min = st_t.clone(), st_t.clone()
+        if world > 1:
+            torch.distributed.all_reduce(st_max, op=torch.distributed.ReduceOp.MAX)
+            torch.distributed.all_reduce(st_min, op=torch.distributed.ReduceOp.MIN)
+        stage_ms = [float(st_max[0]), float(st_min[1]), float(st_min[2])]
         rec[mode] = {
             'ms_per_step': ms / steps, 'value': gb * steps / (ms * 1e-3), 'unit': 'volumes/s',
-            'stage_ms_rank0': {'unet': stage_ms[0], 'warp': stage_ms[1], 'dice': stage_ms[2]},
+            'stage_ms': {'unet_max_over_ranks': stage_ms[0], 'warp_min_over_ranks': stage_ms[1], 'dice_min_over_ranks': stage_ms[2]},
+            'transport': job.plan.active_transport if job.plan is not None else None,
             'warp_roofline_frac': 140.0 * nvox_rank / (stage_ms[1] * 1e-3) / 1e9 / peak if stage_ms[1] > 0 else None,
             'dice_roofline_frac': 128.0 * nvox_rank / (stage_ms[2] * 1e-3) / 1e9 / peak if stage_ms[2] > 0 else None,
             'mean_dice_loss': float(loss),

@@ -151,29 +151,40 @@ class SlabWarper:
     reference's call sites are neurite/tf/models.py:806-807, 1157-1159 -- it has no distributed path itself).
 
     Per call, on rank r holding planes [z0, z0 + nz):
-      1. the rank's planes are placed in the middle of a persistent buffer [B, halo + nz + halo, ...];
-      2. the first / last `halo` planes go to the lower / upper neighbour and theirs are received straight into
-         the two ends of that buffer -- one ncclGroup of <= 4 send/recv on NCCL's stream;
+      1. the rank's planes sit in the middle of a persistent buffer [B, halo + nz_max + halo, ...] (`source_view`
+         hands that middle to the producer, so there is no copy in the step);
+      2. the `halo` planes next to each slab boundary travel to the neighbour's buffer ends:
+           transport 'peer' (NCCL groups on NVLink, the default when torch's symmetric memory can be set up):
+             the buffers are SYMMETRIC MEMORY, i.e. mapped into every rank's address space.  After one on-stream
+             barrier a rank PULLS its two halos straight out of the neighbours' buffers over NVLink on a side
+             stream (plain device copies through peer pointers: no NCCL call, no send/recv matching);
+           transport 'nccl': one ncclGroup of send/recv per step on NCCL's stream (also what gloo runs on CPUs);
       3. meanwhile the INTERIOR output planes [z0 + halo, z0 + nz - halo), whose source window lies inside the
          rank's own planes, are produced on the compute stream (resident planes = own slab only, so a flow that
          exceeds `halo` raises the device flag instead of reading planes that have not arrived);
-      4. the compute stream then waits for the exchange (a stream dependency, the host does not block) and
+      4. the compute stream then waits for the halos (a stream dependency, the host does not block) and
          produces the two boundary strips against the extended buffer.
     `halo` = ceil(max |flow along axis 0|) + 1 is a property of the plan, not measured per step: get it once
-    with `required_halo` (one host sync, e.g. from the registration model's maximum displacement) and reuse
+    with `agreed_halo` (one host sync, e.g. from the registration model's maximum displacement) and reuse
     it.  A flow that exceeds it is never silently wrong: the kernels raise a device flag, read by `check()`.
     If `halo` exceeds a slab the source is all-gathered instead (no overlap); every rank takes the same branch."""
 
-    def __init__(self, full_s0, halo, group=None, interp_method='linear', fill_value=None, tile_halo=0, warp_fn=None):
+    def __init__(self, full_s0, halo, group=None, interp_method='linear', fill_value=None, tile_halo=0, warp_fn=None,
+                 transport='auto'):
         self.full_s0, self.halo, self.group = int(full_s0), int(halo), group
         self.method = utils.method_id(interp_method)
         self.fill_value, self.tile_halo = fill_value, int(tile_halo)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.z0, self.nz = slab_bounds(self.full_s0, self.world, self.rank)
+        self.nz_max = max(c for _, c in all_slab_bounds(self.full_s0, self.world))
         self.fits = halo_fits(self.full_s0, self.world, self.halo)
+        # planes of halo that exist below / above this slab (none at the ends of the volume)
         self.lo_pad = self.halo if (self.fits and self.rank > 0) else 0
         self.hi_pad = self.halo if (self.fits and self.rank < self.world - 1) else 0
-        self._ext, self._err = None, None
+        if transport not in ('auto', 'peer', 'nccl'):
+            raise ValueError("transport must be 'auto', 'peer' or 'nccl'")
+        self.transport = transport
+        self._ext, self._err, self._symm, self._peers, self._side = None, None, None, None, None
         self._warp_fn = warp_fn or self._kernel
 
     # -- the arithmetic: one launch of the warp kernels on plane sub-ranges (injectable for the CPU tests)
@@ -181,21 +192,77 @@ class SlabWarper:
         utils._warp_views(vol_v, flow_v, out_v, self.full_s0, self.method, self.fill_value, src_z0, out_z0,
                           halo=self.tile_halo, err_flag=self._err)
 
-    def _buffers(self, vol_slab):
-        shape = (vol_slab.shape[0], self.lo_pad + self.nz + self.hi_pad) + tuple(vol_slab.shape[2:])
-        if self._ext is None or tuple(self._ext.shape) != shape or self._ext.device != vol_slab.device:
-            self._ext = torch.empty(shape, dtype=torch.float32, device=vol_slab.device)
-            self._err = torch.zeros(1, dtype=torch.int32, device=vol_slab.device) if vol_slab.is_cuda else None
+    def _want_peer(self, like):
+        if self.transport == 'nccl' or not self.fits or self.world == 1 or not like.is_cuda:
+            return False
+        return dist.get_backend(self.group) == 'nccl'
+
+    def _buffers(self, like):
+        """Persistent buffer [B, halo + nz_max + halo, ...]: the same shape on every rank (symmetric memory needs
+        that), this rank's planes at [halo, halo + nz)."""
+        pad = self.halo if self.fits else 0
+        shape = (like.shape[0], pad + self.nz_max + pad) + tuple(like.shape[2:])
+        if self._ext is not None and tuple(self._ext.shape) == shape and self._ext.device == like.device:
+            return self._ext
+        self._pad = pad
+        self._symm = self._peers = None
+        if self._want_peer(like):
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                grp = self.group if self.group is not None else dist.group.WORLD
+                ext = symm_mem.empty(shape, dtype=torch.float32, device=like.device)
+                hdl = symm_mem.rendezvous(ext, grp)
+                self._peers = {r: hdl.get_buffer(r, shape, torch.float32)
+                               for r in (self.rank - 1, self.rank + 1) if 0 <= r < self.world}
+                self._symm, self._ext = hdl, ext
+                self._side = torch.cuda.Stream(device=like.device)
+            except Exception as ex:                          # noqa: BLE001 -- no symmetric memory here: NCCL send/recv
+                if self.transport == 'peer':
+                    raise RuntimeError('SlabWarper(transport=\'peer\'): symmetric memory is not available: %s' % ex)
+                self._symm = self._peers = None
+        if self._symm is None:
+            self._ext = torch.empty(shape, dtype=torch.float32, device=like.device)
+        self._err = torch.zeros(1, dtype=torch.int32, device=like.device) if like.is_cuda else None
         return self._ext
+
+    @property
+    def active_transport(self):
+        return 'peer' if self._symm is not None else ('nccl' if self.fits else 'gather')
 
     def source_view(self, like):
         """The [B, nz, ...] view of the persistent buffer a producer can write the rank's planes into directly
         (then pass that view as `vol_slab`: no copy)."""
         ext = self._buffers(like)
-        return ext[:, self.lo_pad:self.lo_pad + self.nz]
+        return ext[:, self._pad:self._pad + self.nz]
+
+    def _exchange(self, ext, mid):
+        """start moving the halo planes; returns wait() that makes the CURRENT stream depend on their arrival"""
+        nz, halo, pad = self.nz, self.halo, self._pad
+        if self._symm is not None:
+            cur = torch.cuda.current_stream(ext.device)
+            self._symm.barrier(channel=0)                    # every rank's planes are in its buffer (stream-ordered)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                if self.rank > 0:                            # pull the lower neighbour's LAST `halo` planes
+                    nz_lo = slab_bounds(self.full_s0, self.world, self.rank - 1)[1]
+                    ext[:, pad - halo:pad].copy_(self._peers[self.rank - 1][:, pad + nz_lo - halo:pad + nz_lo], non_blocking=True)
+                if self.rank < self.world - 1:               # pull the upper neighbour's FIRST `halo` planes
+                    ext[:, pad + nz:pad + nz + halo].copy_(self._peers[self.rank + 1][:, pad:pad + halo], non_blocking=True)
+                # nobody may overwrite its planes (next step's producer) before every neighbour has pulled them
+                self._symm.barrier(channel=1)
+            side = self._side
+            return lambda: cur.wait_stream(side)
+        sends, recvs = [], []
+        if self.rank > 0:
+            sends.append((mid[:, :halo], self.rank - 1))
+            recvs.append((ext[:, pad - halo:pad], self.rank - 1))
+        if self.rank < self.world - 1:
+            sends.append((mid[:, nz - halo:], self.rank + 1))
+            recvs.append((ext[:, pad + nz:pad + nz + halo], self.rank + 1))
+        return _post_exchange(sends, recvs, self.group)
 
     def __call__(self, vol_slab, flow_slab, out=None):
-        nz, halo = self.nz, self.halo
+        nz = self.nz
         if vol_slab.shape[1] != nz or flow_slab.shape[1] != nz:
             raise ValueError('rank %d owns %d planes, got vol %s / flow %s' % (self.rank, nz, tuple(vol_slab.shape), tuple(flow_slab.shape)))
         if out is None:
@@ -207,29 +274,24 @@ class SlabWarper:
             self._warp_fn(src, flow_slab, out, 0, self.z0)
             return out
         ext = self._buffers(vol_slab)
-        mid = ext[:, self.lo_pad:self.lo_pad + nz]
+        pad = self._pad
+        mid = ext[:, pad:pad + nz]
         if vol_slab.data_ptr() != mid.data_ptr():
             mid.copy_(vol_slab)
-        sends, recvs = [], []
-        if self.rank > 0:
-            sends.append((mid[:, :halo], self.rank - 1))
-            recvs.append((ext[:, :self.lo_pad], self.rank - 1))
-        if self.rank < self.world - 1:
-            sends.append((mid[:, nz - halo:], self.rank + 1))
-            recvs.append((ext[:, self.lo_pad + nz:], self.rank + 1))
-        wait = _post_exchange(sends, recvs, self.group)
+        wait = self._exchange(ext, mid)
         i_lo, i_hi = self.lo_pad, nz - self.hi_pad            # interior output planes (slab-local)
+        src = ext[:, pad - self.lo_pad:pad + nz + self.hi_pad]     # the planes that exist around this slab
+        src_z0 = self.z0 - self.lo_pad
         if i_hi > i_lo:
             self._warp_fn(mid, flow_slab[:, i_lo:i_hi], out[:, i_lo:i_hi], self.z0, self.z0 + i_lo)
             wait()
-            src_z0 = self.z0 - self.lo_pad
             if i_lo > 0:
-                self._warp_fn(ext, flow_slab[:, :i_lo], out[:, :i_lo], src_z0, self.z0)
+                self._warp_fn(src, flow_slab[:, :i_lo], out[:, :i_lo], src_z0, self.z0)
             if i_hi < nz:
-                self._warp_fn(ext, flow_slab[:, i_hi:], out[:, i_hi:], src_z0, self.z0 + i_hi)
+                self._warp_fn(src, flow_slab[:, i_hi:], out[:, i_hi:], src_z0, self.z0 + i_hi)
         else:                                                 # slab thinner than two halos: no interior
             wait()
-            self._warp_fn(ext, flow_slab, out, self.z0 - self.lo_pad, self.z0)
+            self._warp_fn(src, flow_slab, out, src_z0, self.z0)
         return out
 
     def check(self):

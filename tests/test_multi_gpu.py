@@ -44,6 +44,7 @@ def _worker(rank, world, port, q):
                 part = nd.warp_slab(vol[:, z0:z0 + nz].contiguous(), flow[:, z0:z0 + nz].contiguous(), S[0], mode=mode)
                 ok = ok and torch.equal(part, whole[:, z0:z0 + nz])
         ok = ok and _slab_warper_reuse(nd, utils, dev, g, world, rank)
+        ok = ok and _slab_warper_reuse(nd, utils, dev, g, world, rank, C=3, S=(40, 16, 64), transport='nccl')
         # Dice / CCE: voxel-range sharding + all-reduce of the partial sums
         L = 16
         lab = torch.randint(0, L, (2,) + S, generator=g)
@@ -68,13 +69,13 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def _slab_warper_reuse(nd, utils, dev, g, world, rank, C=16, S=(48, 24, 32)):
+def _slab_warper_reuse(nd, utils, dev, g, world, rank, C=16, S=(48, 24, 32), transport='auto'):
     """A persistent SlabWarper (overlapped halo exchange, no host sync in the step) on a 16-channel volume, called
     repeatedly with new data and through its zero-copy source view; then a flow beyond the plan's halo must raise
     the device flag instead of returning wrong voxels silently."""
     vol = torch.randn((2,) + S + (C,), generator=g).to(dev)
     z0, nz = nd.slab_bounds(S[0], world, rank)
-    plan = nd.SlabWarper(S[0], halo=4)
+    plan = nd.SlabWarper(S[0], halo=4, transport=transport)
     ok = True
     for it in range(3):
         flow = ((torch.rand((2,) + S + (3,), generator=g) * 2 - 1) * 3.0).to(dev)
