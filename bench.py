@@ -690,7 +690,18 @@ def slab_record(args, world, rank, dev, channels=1, batch=1):
                 plan._kernel(srcx, flow[:, i_hi:], out[:, i_hi:], z0 - plan.lo_pad, z0 + i_hi)
         ms_k = timed_region(kernels_only, steps, 3, world, min_preheat_s=0.0)
         plan._err.zero_()
-        return {'transport': plan.active_transport, 'ms_per_step': ms_ov / steps, 'value': B * V * steps / (ms_ov * 1e-3),
+        graph = None
+        if plan.active_transport == 'peer':
+            # the same step as ONE CUDA-graph replay (no python / launch overhead between its pieces)
+            try:
+                plan.capture(src, flow, out)
+                ms_g = timed_region(plan.replay, steps, 3, world, min_preheat_s=0.0)
+                plan.check()
+                graph = {'ms_per_step': ms_g / steps, 'value': B * V * steps / (ms_g * 1e-3), 'unit': 'voxels/s'}
+            except Exception as ex:                          # noqa: BLE001
+                graph = {'error': '%s: %s' % (type(ex).__name__, str(ex)[:200])}
+        return {'transport': plan.active_transport, 'cuda_graph_replay': graph,
+                'ms_per_step': ms_ov / steps, 'value': B * V * steps / (ms_ov * 1e-3),
                 'unit': 'voxels/s', 'exchange_only_us': ms_ex / steps * 1e3, 'kernels_only_us': ms_k / steps * 1e3,
                 'roofline_frac_aggregate': model_bytes / (ms_ov / steps * 1e-3) / 1e9 / (peak * world),
                 'limiter': 'the halo exchange' if ms_ex > ms_k else 'the three kernel launches'}
@@ -711,8 +722,12 @@ def slab_record(args, world, rank, dev, channels=1, batch=1):
     out1 = torch.empty_like(vol1)
     ms_one = timed_region(lambda: utils._warp_views(vol1, flow1, out1, SHAPE[0], 0, None, 0, 0), max(20, steps // 4), 3, world,
                           min_preheat_s=0.0)
+    best = rec['overlap']['ms_per_step']
+    gr = rec['overlap'].get('cuda_graph_replay') or {}
+    if 'ms_per_step' in gr:
+        best = min(best, gr['ms_per_step'])
     rec['one_gpu_whole_volume'] = {'ms_per_step': ms_one / max(20, steps // 4),
-                                   'speedup_of_the_slab_plan': (ms_one / max(20, steps // 4)) / rec['overlap']['ms_per_step']}
+                                   'speedup_of_the_slab_plan': (ms_one / max(20, steps // 4)) / best}
     return rec
 
 

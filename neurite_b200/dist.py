@@ -294,6 +294,25 @@ class SlabWarper:
             self._warp_fn(src, flow_slab, out, src_z0, self.z0)
         return out
 
+    def capture(self, vol_slab, flow_slab, out=None):
+        """Capture ONE step (barrier, halo pulls on the side stream, interior and boundary launches) into a CUDA
+        graph: at 30-250 us of GPU work per step the ~100 us of python / launch overhead of the eager step is the
+        bottleneck, a graph replay costs ~10 us.  Static buffers: `vol_slab` should be `source_view(...)`, and
+        `flow_slab` / the returned `out` are the tensors the producer / consumer keep using; call `replay()` per
+        step.  Peer transport only (the step then contains no NCCL call); every rank must capture and replay alike."""
+        out = self(vol_slab, flow_slab, out)                  # warm-up outside the capture: buffers, rendezvous, kernel attributes
+        if self._symm is None and self.world > 1:
+            raise RuntimeError('SlabWarper.capture needs the peer transport (active: %s)' % self.active_transport)
+        torch.cuda.synchronize(vol_slab.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self(vol_slab, flow_slab, out)
+        self._graph = graph
+        return out
+
+    def replay(self):
+        self._graph.replay()
+
     def check(self):
         """Host-synchronising: raises if any sample since the last check fell outside the resident planes."""
         if self._err is not None and int(self._err.item()) != 0:

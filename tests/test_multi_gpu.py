@@ -88,6 +88,18 @@ def _slab_warper_reuse(nd, utils, dev, g, world, rank, C=16, S=(48, 24, 32), tra
         part = plan(src, flow[:, z0:z0 + nz].contiguous())
         ok = ok and torch.equal(part, whole[:, z0:z0 + nz])
     plan.check()
+    if plan.active_transport == 'peer':
+        # the whole step as one CUDA-graph replay: new data written into the static buffers, same bits out
+        flow = ((torch.rand((2,) + S + (3,), generator=g) * 2 - 1) * 3.0).to(dev)
+        whole = utils._warp_batched(vol, flow)
+        src = plan.source_view(vol[:, z0:z0 + nz])
+        fl = flow[:, z0:z0 + nz].contiguous()
+        out = plan.capture(src, fl)
+        src.copy_(vol[:, z0:z0 + nz])
+        out.zero_()
+        plan.replay()
+        ok = ok and torch.equal(out, whole[:, z0:z0 + nz])
+        plan.check()
     if plan.fits:
         big = torch.zeros((2,) + S + (3,), device=dev)
         big[..., 0] = 9.0                                    # 9 planes up: beyond halo 4 for every rank but the last
