@@ -461,8 +461,8 @@ resize3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol, const float* __
 // resize3d_x2_kernel).  With the load latency gone the staged kernel is issue-bound (87 % issue-active, 134
 // instructions per voxel at C = 3, profiles/r02_ncu_full_resize_tile.txt); here the 60 separately rounded multiplies
 // / adds of a voxel are shared by a voxel pair and so are the table reads, addresses and the loop.
-template <int CT, int TZ>
-__global__ void __launch_bounds__(256)
+template <int CT, int TZ, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB)
 resize3d_tile_x2_kernel(const __grid_constant__ CUtensorMap tm_vol, const float* __restrict__ vol, float* __restrict__ out,
                         ResizeGeo w, ResizeBox bxs, int ntz, int nty, int ntx, int xalign, f32x2 negzero2, f32x2 one2) {
   constexpr int TY = 16, TX = 32;                      // a warp = two rows of 16 x-pairs
@@ -780,7 +780,7 @@ struct TileCfg {
   static constexpr int ROWS = TY / NW;                  // rows of 32 voxels per warp per plane
   static constexpr int FLOW_ELEMS = TZ * TY * TX * 3, BOX_ELEMS = BZ * BY * BX * CC;
   static_assert(BX * CC <= 256, "TMA box limit on the merged (x, channel) dimension");
-  static constexpr size_t SMEM = (size_t)(FLOW_ELEMS + BOX_ELEMS) * sizeof(float) + 32;   // + mbarrier + box origin
+  static constexpr size_t SMEM = (size_t)(FLOW_ELEMS + BOX_ELEMS) * sizeof(float) + 32;   // + 2 mbarriers + box origin
   static_assert(TY % NW == 0, "TY must be a multiple of the warp count");
   static_assert(BX <= 256 && BY <= 256 && BZ <= 256, "TMA box limit");
 };
@@ -1018,21 +1018,24 @@ warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* s_flow = reinterpret_cast<float*>(smem_raw);                       // [TZ][TY][TX][3]
   float* s_box = s_flow + Cfg::FLOW_ELEMS;                                  // [BZ][BY][BX]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(s_box + Cfg::BOX_ELEMS);
-  int* s_org = reinterpret_cast<int*>(bar + 1);                             // mean shift of the tile (box re-staging)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_box + Cfg::BOX_ELEMS);     // bar[0]: source box, bar[1]: flow tile
+  int* s_org = reinterpret_cast<int*>(bar + 2);                             // mean shift of the tile (box re-staging)
   const int b = blockIdx.z / w.ntz;
   const int x0 = blockIdx.x * Cfg::TX, y0 = blockIdx.y * TY, z0l = (blockIdx.z - b * w.ntz) * TZ;
   if (threadIdx.x == 0) {
     // speculative load: flow tile + the box centred on the tile itself (right for small or
-    // incoherent displacements), issued before anything is known about the flow
+    // incoherent displacements), issued before anything is known about the flow.  The flow tile goes first and on
+    // its own barrier: the warp that inspects it can start while the (larger) box is still landing.
     mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
     fence_mbar_init();
-    mbar_expect_tx(bar, (uint32_t)((Cfg::FLOW_ELEMS + Cfg::BOX_ELEMS) * sizeof(float)));
-    tma_load_4d(s_flow, &tm_flow, bar, x0 * 3, y0, z0l, b);
+    mbar_expect_tx(bar + 1, (uint32_t)(Cfg::FLOW_ELEMS * sizeof(float)));
+    tma_load_4d(s_flow, &tm_flow, bar + 1, x0 * 3, y0, z0l, b);
+    mbar_expect_tx(bar, (uint32_t)(Cfg::BOX_ELEMS * sizeof(float)));
     tma_load_4d(s_box, &tm_vol, bar, (x0 - Cfg::HX) * CC, y0 - HALO, w.out_z0 + z0l - HALO - w.g.src_z0, b);
   }
-  __syncthreads();                                   // the barrier is initialised
-  mbar_wait(bar, 0);
+  __syncthreads();                                   // the barriers are initialised
+  mbar_wait(bar + 1, 0);
   // Where does the tile land ON AVERAGE?  ONE warp looks at a 3x3x3 lattice of the STAGED flow tile (27 lanes, one
   // LDS per component: no global latency) and sums the shifts in 1/64-voxel fixed point with the warp-reduce
   // instruction (three REDUX instead of fifteen shuffle + add steps).  A large coherent displacement means the
@@ -1071,6 +1074,7 @@ warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
     __syncthreads();
     sz = s_org[0]; sy = s_org[1]; sx = s_org[2];
   }
+  mbar_wait(bar, 0);
   const int oz = w.out_z0 + z0l - HALO + sz, oy = y0 - HALO + sy, ox = x0 - Cfg::HX + sx;
   if ((sz | sy | sx) != 0) {                         // block-uniform
     // every thread must have observed phase 0 before phase 1 is armed: an mbarrier waiter
@@ -1665,9 +1669,15 @@ int nrt_resize_f32(const float* vol, float* out, int B, const int32_t* in_shape,
         uint32_t nzb, oneb;
         memcpy(&nzb, &nzf, 4); memcpy(&oneb, &onef, 4);
         const f32x2 negzero2 = ((f32x2)nzb << 32) | nzb, one2 = ((f32x2)oneb << 32) | oneb;
+        const bool minb3 = env_int("NRT_RESIZE_MINB", 1) == 3;        // registers capped for 3 CTAs per SM (experiment)
 #define NRT_RESIZE_TILE(CT, TZZ)                                                                                          \
         do {                                                                                                              \
-          if (x2) {                                                                                                       \
+          if (x2 && minb3) {                                                                                              \
+            auto kern = resize3d_tile_x2_kernel<CT, TZZ, 3>;                                                              \
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)        \
+              return check_launch("cudaFuncSetAttribute(resize3d_tile_x2)");                                              \
+            kern<<<(int)grid3, 256, smem, st>>>(tmv, vol, out, rg, bxs, ntz3, nty3, ntx3, xalign, negzero2, one2);        \
+          } else if (x2) {                                                                                                \
             auto kern = resize3d_tile_x2_kernel<CT, TZZ>;                                                                 \
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)        \
               return check_launch("cudaFuncSetAttribute(resize3d_tile_x2)");                                              \
