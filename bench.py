@@ -860,17 +860,15 @@ def bench_blur(args):
     sampler = ClockSampler(local).start()
     ms = timed_region(lambda: lay(x), args.steps, args.warmup, world)
     clocks = sampler.stop()
-    fused = os.environ.get('NRT_BLUR_FUSED', '0') == '1' and round(args.sigma * 3) * 2 + 1 <= 15
     if rank == 0:
         line = base_line('voxels/s, GaussianBlur(sigma=%g), 160x192x224 fp32' % args.sigma,
                          world * B * V * args.steps / (ms * 1e-3), 'voxels/s', world, args.steps, args.warmup, ms, 'weak',
-                         'GaussianBlur(sigma=%g) on [%d,160,192,224,1] (reference layers.py:251-364): %s'
-                         % (args.sigma, B, 'one fused kernel' if fused else 'three separable passes'))
-        line['roofline'] = roofline(8.0 * B * V, ms / args.steps, 'blur_fused' if fused else 'blur',
-                                    '8 B/voxel for the whole blur (read once, write once)'
-                                    + ('' if fused else '; the three-pass path moves 24 B/voxel, so 0.33 is its ceiling'),
-                                    'blur3d_fused_kernel' if fused else 'sepconv_col4_kernel x2 + sepconv_row_kernel')
-        line['gpu_launches'] = args.steps * (1 if fused else 3)
+                         'GaussianBlur(sigma=%g) on [%d,160,192,224,1] (reference layers.py:251-364): three separable passes'
+                         % (args.sigma, B))
+        line['roofline'] = roofline(8.0 * B * V, ms / args.steps, 'blur',
+                                    '8 B/voxel for the whole blur (read once, write once); the three-pass path moves '
+                                    '24 B/voxel, so 0.33 is its ceiling', 'sepconv_col4_kernel x2 + sepconv_row_kernel')
+        line['gpu_launches'] = args.steps * 3
         line['clocks'] = clocks
         if world == 1 and not args.no_cpu_baseline:
             import numpy as np

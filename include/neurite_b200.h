@@ -271,13 +271,6 @@ NRT_API int nrt_soft_quantize_f32(const float* x, int64_t n, const float* center
  * pointer ([K]).  x and out must not alias. */
 NRT_API int nrt_sepconv_axis_f32(const float* x, float* out, int64_t outer, int64_t L, int64_t inner, const float* kernel,
                          int K, int stride, int dilation, int pad_before, int64_t L_out, void* stream);
-/* The three 'SAME' passes of a 3-D single-channel blur (GaussianBlur on [B,Z,Y,X,1], layers.py:251-364)
- * fused into one kernel: 8 B of HBM traffic per voxel instead of 24.  kz / ky / kx: device pointers
- * to K taps each, K odd and <= 15 -- shorter kernels centred and zero padded by the caller
- * (K == 1 or 3 both run the 3-tap instantiation: pad a 1-tap kernel to {0, k, 0}).  x and out must
- * not alias. */
-NRT_API int nrt_blur3d_f32(const float* x, float* out, int B, int Z, int Y, int X, const float* kz, const float* ky,
-                   const float* kx, int K, void* stream);
 /* out[o, l, i] = x[o, index[l], i]: tf.gather along an axis (subsample_axis, utils.py:818-823). */
 NRT_API int nrt_gather_axis_f32(const float* x, const int32_t* index, float* out, int64_t outer, int64_t L, int64_t inner,
                         int64_t L_out, void* stream);

@@ -78,8 +78,6 @@ SIGNATURES = {
                                               ctypes.c_int, c_vp, c_vp]),
     'nrt_sepconv_axis_f32': (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_int, ctypes.c_int, c_i64, c_vp]),
-    'nrt_blur3d_f32': (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp,
-                                       ctypes.c_int, c_vp]),
     'nrt_gather_axis_f32': (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp]),
 }
 

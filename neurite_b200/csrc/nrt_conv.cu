@@ -235,119 +235,6 @@ __global__ void sepconv_generic_kernel(const ConvArgs a) {
 }
 
 
-// ---------------------------------------------------------------------------------------
-// blur3d_fused_kernel: the three passes of a 3-D single-channel blur in ONE kernel, 8 B of HBM
-// traffic per voxel instead of 24.  A CTA owns a TY x TX column of the volume and marches along
-// z: each input plane (tile + xy halo) is staged in shared memory, convolved along x, then along
-// y, and the result enters a ring of K planes; the z convolution reads the ring and writes one
-// output plane per step.  K = the longest of the three kernels (odd, <= 15); shorter kernels
-// are centred and zero padded, so all tap loops are compile-time and the weights live in
-// registers.  Zero 'SAME' padding falls out of zero-filled halo elements / planes.  The passes
-// run x, y, z instead of the reference's z, y, x: the same sums in another order (1e-5 parity,
-// like every reduction here).
-// ---------------------------------------------------------------------------------------
-constexpr int kFTX = 64, kFTY = 16;
-struct Blur3dArgs {
-  const float* x;
-  float* out;
-  const float* kz; const float* ky; const float* kx;   // device, centred and zero padded to K taps each
-  int B, Z, Y, X;
-  int zsplit, zlen;                                    // z segments per column, planes per segment
-};
-
-template <int K>
-__global__ void __launch_bounds__(256) blur3d_fused_kernel(const Blur3dArgs a) {
-  constexpr int R = K / 2;
-  constexpr int AY = kFTY + K - 1, AX = kFTX + K - 1;
-  extern __shared__ float smem[];
-  float* A = smem;                         // [AY][AX]   input plane tile with halo
-  float* Bx = A + AY * AX;                 // [AY][kFTX] after the x pass
-  float* ring = Bx + AY * kFTX;            // [K][kFTY * kFTX] after the y pass
-  const int tid = threadIdx.x;
-  float wz[K], wy[K], wx[K];
-#pragma unroll
-  for (int j = 0; j < K; ++j) { wz[j] = a.kz[j]; wy[j] = a.ky[j]; wx[j] = a.kx[j]; }
-
-  const int x0 = blockIdx.x * kFTX, y0 = blockIdx.y * kFTY;
-  const int b = blockIdx.z / a.zsplit, seg = blockIdx.z - b * a.zsplit;
-  const int zb = seg * a.zlen, ze = min(zb + a.zlen, a.Z);
-  const size_t plane = (size_t)a.Y * a.X;
-  const float* xb = a.x + (size_t)b * a.Z * plane;
-  float* ob = a.out + (size_t)b * a.Z * plane;
-
-  int slot = 0;                            // ring slot of the plane being produced
-  for (int zi = zb - R; zi < ze + R; ++zi) {
-    float* dst = ring + slot * (kFTY * kFTX);
-    if (zi >= 0 && zi < a.Z) {             // block-uniform
-      const float* xp = xb + (size_t)zi * plane;
-      for (int e = tid; e < AY * AX; e += 256) {
-        const int r = e / AX, c = e - r * AX;
-        const int gy = y0 - R + r, gx = x0 - R + c;
-        A[e] = (gy >= 0 && gy < a.Y && gx >= 0 && gx < a.X) ? ld_stream_f(xp + (size_t)gy * a.X + gx) : 0.f;
-      }
-      __syncthreads();                     // (also orders the previous step's ring reads before this step's ring write)
-      for (int e = tid; e < AY * kFTX; e += 256) {
-        const int r = e / kFTX, c = e - r * kFTX;
-        const float* ap = A + r * AX + c;
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < K; ++j) s = fmaf(wx[j], ap[j], s);
-        Bx[e] = s;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int m = 0; m < kFTY * kFTX / 256; ++m) {
-        const int e = tid + m * 256;
-        const float* bp = Bx + e;          // row e / kFTX of the output = rows .. + K - 1 of Bx
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < K; ++j) s = fmaf(wy[j], bp[j * kFTX], s);
-        dst[e] = s;
-      }
-    } else {
-      __syncthreads();
-#pragma unroll
-      for (int m = 0; m < kFTY * kFTX / 256; ++m) dst[tid + m * 256] = 0.f;
-    }
-    __syncthreads();
-    const int zo = zi - R;                 // the output plane whose K input planes are now in the ring
-    if (zo >= zb && zo < ze) {
-      // plane zo - R + j sits in slot (slot + 1 + j) mod K: the ring holds planes zi - K + 1 .. zi
-      float acc[kFTY * kFTX / 256];
-#pragma unroll
-      for (int m = 0; m < kFTY * kFTX / 256; ++m) acc[m] = 0.f;
-      int sl = slot + 1 == K ? 0 : slot + 1;
-#pragma unroll
-      for (int j = 0; j < K; ++j) {
-        const float* rp = ring + sl * (kFTY * kFTX) + tid;
-#pragma unroll
-        for (int m = 0; m < kFTY * kFTX / 256; ++m) acc[m] = fmaf(wz[j], rp[m * 256], acc[m]);
-        sl = sl + 1 == K ? 0 : sl + 1;
-      }
-#pragma unroll
-      for (int m = 0; m < kFTY * kFTX / 256; ++m) {
-        const int e = tid + m * 256;
-        const int gy = y0 + e / kFTX, gx = x0 + (e & (kFTX - 1));
-        if (gy < a.Y && gx < a.X) st_stream_f(ob + (size_t)zo * plane + (size_t)gy * a.X + gx, acc[m]);
-      }
-    }
-    slot = slot + 1 == K ? 0 : slot + 1;
-  }
-}
-
-template <int K>
-int launch_blur3d(const Blur3dArgs& a, cudaStream_t st) {
-  constexpr int AY = kFTY + K - 1, AX = kFTX + K - 1;
-  const size_t smem = (size_t)(AY * AX + AY * kFTX + K * kFTY * kFTX) * sizeof(float);
-  auto kern = blur3d_fused_kernel<K>;
-  if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return check_launch("cudaFuncSetAttribute(blur3d_fused)");
-  dim3 grid((a.X + kFTX - 1) / kFTX, (a.Y + kFTY - 1) / kFTY, a.B * a.zsplit);
-  kern<<<grid, 256, smem, st>>>(a);
-  return check_launch("blur3d_fused_kernel");
-}
-
 // out[o, l, i] = x[o, idx[l], i]   (tf.gather along an axis, utils.py:818-823)
 __global__ void gather_axis_kernel(const float* x, const int32_t* idx, float* out, int64_t outer, int64_t L,
                                    int64_t inner, int64_t L_out) {
@@ -415,36 +302,6 @@ int nrt_sepconv_axis_f32(const float* x, float* out, int64_t outer, int64_t L, i
   const int grid = (int)imin64((total + 255) / 256, (int64_t)sm_count() * 32);
   sepconv_generic_kernel<<<grid, 256, 0, st>>>(a);
   return check_launch("sepconv_generic_kernel");
-}
-
-int nrt_blur3d_f32(const float* x, float* out, int B, int Z, int Y, int X, const float* kz, const float* ky,
-                   const float* kx, int K, void* stream) {
-  NRT_REQUIRE(x && out && kz && ky && kx, NRT_E_ARG, "null pointer");
-  NRT_REQUIRE(x != out, NRT_E_ARG, "in-place blur is not supported");
-  NRT_REQUIRE(B >= 0 && Z >= 1 && Y >= 1 && X >= 1, NRT_E_ARG, "bad shape");
-  NRT_REQUIRE(K >= 1 && K <= 15 && (K & 1), NRT_E_SIZE, "K = %d: the fused blur takes odd kernels of at most 15 taps", K);
-  if (B == 0) return NRT_OK;
-  Blur3dArgs a{x, out, kz, ky, kx, B, Z, Y, X, 1, Z};
-  const int64_t cols = (int64_t)((X + kFTX - 1) / kFTX) * ((Y + kFTY - 1) / kFTY) * B;
-  NRT_REQUIRE(cols <= 65535 * 4, NRT_E_SIZE, "too many tile columns");
-  // enough CTAs for ~5 per SM; every z segment re-reads K - 1 planes, so segments stay >= 4 K planes long
-  int zsplit = (int)(((int64_t)sm_count() * 5 + cols - 1) / cols);
-  const int max_split = Z / (4 * K) > 0 ? Z / (4 * K) : 1;
-  if (zsplit > max_split) zsplit = max_split;
-  if (zsplit < 1) zsplit = 1;
-  a.zlen = (Z + zsplit - 1) / zsplit;
-  a.zsplit = (Z + a.zlen - 1) / a.zlen;
-  NRT_REQUIRE((int64_t)B * a.zsplit <= 65535, NRT_E_SIZE, "B * z segments > 65535");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (K) {
-    case 1: case 3: return launch_blur3d<3>(a, st);
-    case 5: return launch_blur3d<5>(a, st);
-    case 7: return launch_blur3d<7>(a, st);
-    case 9: return launch_blur3d<9>(a, st);
-    case 11: return launch_blur3d<11>(a, st);
-    case 13: return launch_blur3d<13>(a, st);
-    default: return launch_blur3d<15>(a, st);
-  }
 }
 
 int nrt_gather_axis_f32(const float* x, const int32_t* index, float* out, int64_t outer, int64_t L, int64_t inner,

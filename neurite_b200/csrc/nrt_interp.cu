@@ -302,6 +302,10 @@ resize3d_kernel(const float* __restrict__ vol, float* __restrict__ out, ResizeGe
 // A tile whose box would not fit the staged extents (cannot happen when host and device agree) or a zoom whose
 // boxes are larger than the budget (down-sampling) takes resize3d_kernel.
 // ---------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (FFMA2 issues at the scalar FFMA rate on sm_100: two results per issue slot).
+// Bit-exactness: ptxas fuses mul.f32x2 + add.f32x2 into one FFMA2 (single rounding) even with fmad=false, so the
+// reference's separately rounded ops are written as  a*b = fma(a, b, -0)  and  a+b = fma(a, 1, b)  with the identity
+// operands (-0,-0) and (1,1) passed as kernel PARAMETERS (visible constants are folded and re-fused).
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float a, float b) {
   f32x2 r;
@@ -457,8 +461,8 @@ resize3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol, const float* __
   }
 }
 
-// resize3d_tile_x2_kernel: staged source box (as above) + TWO x positions per thread on packed fp32x2 arithmetic (as
-// resize3d_x2_kernel).  With the load latency gone the staged kernel is issue-bound (87 % issue-active, 134
+// resize3d_tile_x2_kernel: staged source box (as above) + TWO x positions per thread: the two voxels of a thread form
+// the halves of packed fp32x2 registers.  With the load latency gone the staged kernel is issue-bound (87 % issue-active, 134
 // instructions per voxel at C = 3, profiles/r02_ncu_full_resize_tile.txt); here the 60 separately rounded multiplies
 // / adds of a voxel are shared by a voxel pair and so are the table reads, addresses and the loop.
 template <int CT, int TZ, int MINB = 1>
@@ -623,136 +627,6 @@ static int resize_axis_extent(int S, int M, float delta, int first, int count, i
     if (hi - lo + 1 > ext) ext = hi - lo + 1;
   }
   return ext;
-}
-
-// ---------------------------------------------------------------------------------------
-// resize3d_x2_kernel: the linear z-marching kernel above with TWO x positions per thread.  resize3d_kernel is
-// issue-bound (~115 instructions per output voxel at C = 3, 60 of them the reference's separately rounded
-// multiplies and adds); here the two voxels of a thread form the halves of packed fp32x2 registers, so every one of
-// those multiplies / adds covers both voxels (FFMA2 issues at the scalar FFMA rate on sm_100), and the table
-// reads, address arithmetic and loop overhead are shared by the pair.
-//
-// Bit-exactness: ptxas fuses mul.f32x2 + add.f32x2 into one FFMA2 (single rounding) even with fmad=false, so the
-// reference's separately rounded ops are written as  a*b = fma(a, b, -0)  and  a+b = fma(a, 1, b)  with the
-// identity operands (-0,-0) and (1,1) passed as kernel PARAMETERS (visible constants are folded and re-fused).
-// ---------------------------------------------------------------------------------------
-template <int CT, int TZ>
-__global__ void __launch_bounds__(256)
-resize3d_x2_kernel(const float* __restrict__ vol, float* __restrict__ out, ResizeGeo w, int ntz, int nty, int ntx,
-                   f32x2 negzero2, f32x2 one2) {
-  constexpr int TY = 16, TX = 32;                      // a warp = two rows of 16 x-pairs
-  __shared__ AxisEntry s_ax[TZ + TY + TX];
-  const Geo& g = w.g;
-  int tile = blockIdx.x;
-  const int tx = tile % ntx; tile /= ntx;
-  const int ty = tile % nty; tile /= nty;
-  const int tz = tile % ntz;
-  const int b = tile / ntz;
-  const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;            // z0 relative to the produced slab
-  if (threadIdx.x < TZ + TY + TX) {
-    const int t = threadIdx.x;
-    const int d = t < TZ ? 0 : (t < TZ + TY ? 1 : 2);
-    const int i = d == 0 ? w.out_z0 + z0 + t : (d == 1 ? y0 + (t - TZ) : x0 + (t - TZ - TY));
-    const int stride = d == 0 ? g.S[1] * g.S[2] * CT : (d == 1 ? g.S[2] * CT : CT);
-    AxisEntry e;
-    if (i < w.M[d]) {
-      // tf.linspace(0, S-1, M): endpoints exact, interior 0 + delta*i  (utils.py:259)
-      const float loc = (i == w.M[d] - 1 && w.M[d] > 1) ? (float)(g.S[d] - 1) : __fmul_rn(w.delta[d], (float)i);
-      const Axis a = axis_linear(loc, (float)(g.S[d] - 1), g.S[d] - 1);
-      e.o0 = a.i0 * stride; e.o1 = a.i1 * stride; e.wlo = a.wlo; e.whi = a.whi;
-    } else {
-      e.o0 = e.o1 = 0; e.wlo = e.whi = 0.f;
-    }
-    s_ax[t] = e;
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int row = wid * 2 + (lane >> 4), xp = lane & 15;
-  const int ox = x0 + 2 * xp, oy = y0 + row;
-  if (oy >= w.M[1] || ox >= w.M[2]) return;
-  const bool has1 = ox + 1 < w.M[2];                    // odd output width: the pair's second voxel may not exist
-  const AxisEntry ey = s_ax[TZ + row], ea = s_ax[TZ + TY + 2 * xp], eb = s_ax[TZ + TY + 2 * xp + 1];
-  const float* volb = vol + (size_t)b * w.src_batch_stride;
-  float* outb = out + ((size_t)b * w.out_vox + ((size_t)z0 * w.M[1] + oy) * w.M[2] + ox) * CT;
-  const size_t plane = (size_t)w.M[1] * w.M[2] * CT;
-  // in-plane corners q = 2*(y corner) + (x corner), for voxel a (first half) and voxel b (second half)
-  const float* qa[4] = {volb + ey.o0 + ea.o0, volb + ey.o0 + ea.o1, volb + ey.o1 + ea.o0, volb + ey.o1 + ea.o1};
-  const float* qb[4] = {volb + ey.o0 + eb.o0, volb + ey.o0 + eb.o1, volb + ey.o1 + eb.o0, volb + ey.o1 + eb.o1};
-  const f32x2 exlo = pack2(ea.wlo, eb.wlo), exhi = pack2(ea.whi, eb.whi);
-  const f32x2 zero2 = pack2(0.f, 0.f);
-  f32x2 lo[4][CT], hi[4][CT];
-  int cur0 = -1, cur1 = -1;
-#pragma unroll 1
-  for (int z = 0; z < TZ; ++z, outb += plane) {
-    if (z0 + z >= w.out_n0) break;
-    const AxisEntry ez = s_ax[z];
-    if (ez.o0 != cur0) {
-      if (ez.o0 == cur1) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int c = 0; c < CT; ++c) lo[q][c] = hi[q][c];
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int c = 0; c < CT; ++c) lo[q][c] = pack2(__ldg(qa[q] + ez.o0 + c), __ldg(qb[q] + ez.o0 + c));
-      }
-      cur0 = ez.o0;
-    }
-    if (ez.o1 != cur1) {
-      if (ez.o1 == cur0) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int c = 0; c < CT; ++c) hi[q][c] = lo[q][c];
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int c = 0; c < CT; ++c) hi[q][c] = pack2(__ldg(qa[q] + ez.o1 + c), __ldg(qb[q] + ez.o1 + c));
-      }
-      cur1 = ez.o1;
-    }
-    // corner weights in the reference's order ((wz*wy)*wx, utils.py:1085-1092); the (z, y) products are the same
-    // for both voxels, the x factor differs per half
-    const float w00 = __fmul_rn(ez.wlo, ey.wlo), w01 = __fmul_rn(ez.wlo, ey.whi);
-    const float w10 = __fmul_rn(ez.whi, ey.wlo), w11 = __fmul_rn(ez.whi, ey.whi);
-    const f32x2 p00 = pack2(w00, w00), p01 = pack2(w01, w01), p10 = pack2(w10, w10), p11 = pack2(w11, w11);
-    f32x2 k[8];
-    k[0] = fma2(p00, exlo, negzero2); k[1] = fma2(p00, exhi, negzero2);
-    k[2] = fma2(p01, exlo, negzero2); k[3] = fma2(p01, exhi, negzero2);
-    k[4] = fma2(p10, exlo, negzero2); k[5] = fma2(p10, exhi, negzero2);
-    k[6] = fma2(p11, exlo, negzero2); k[7] = fma2(p11, exhi, negzero2);
-    f32x2 res[CT];
-#pragma unroll
-    for (int c = 0; c < CT; ++c) {
-      f32x2 r = fma2(fma2(k[0], lo[0][c], negzero2), one2, zero2);          // 0 + k0*v0
-#pragma unroll
-      for (int q = 1; q < 4; ++q) r = fma2(fma2(k[q], lo[q][c], negzero2), one2, r);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) r = fma2(fma2(k[4 + q], hi[q][c], negzero2), one2, r);
-      res[c] = r;
-    }
-    float ra[CT], rb[CT];
-#pragma unroll
-    for (int c = 0; c < CT; ++c) unpack2(res[c], ra[c], rb[c]);
-    if (!has1) {
-#pragma unroll
-      for (int c = 0; c < CT; ++c) outb[c] = ra[c];
-    } else if (CT == 1) {
-      *reinterpret_cast<float2*>(outb) = make_float2(ra[0], rb[0]);
-    } else if (CT == 2) {
-      *reinterpret_cast<float4*>(outb) = make_float4(ra[0], ra[1 % CT], rb[0], rb[1 % CT]);
-    } else if (CT == 3) {
-      *reinterpret_cast<float2*>(outb) = make_float2(ra[0], ra[1 % CT]);
-      *reinterpret_cast<float2*>(outb + 2) = make_float2(ra[2 % CT], rb[0]);
-      *reinterpret_cast<float2*>(outb + 4) = make_float2(rb[1 % CT], rb[2 % CT]);
-    } else {
-      *reinterpret_cast<float4*>(outb) = make_float4(ra[0], ra[1 % CT], ra[2 % CT], ra[3 % CT]);
-      *reinterpret_cast<float4*>(outb + 4) = make_float4(rb[0], rb[1 % CT], rb[2 % CT], rb[3 % CT]);
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1700,34 +1574,6 @@ int nrt_resize_f32(const float* vol, float* out, int B, const int32_t* in_shape,
 #undef NRT_RESIZE_TILE_C
 #undef NRT_RESIZE_TILE
         return check_launch("resize3d_tile_kernel");
-      }
-    }
-    // two x positions per thread on packed fp32x2 arithmetic (linear, C = 1..4, even row pitch for the vector stores)
-    if (method == NRT_LINEAR && C >= 1 && C <= 4 && env_int("NRT_RESIZE_X2", 0) && (rg.M[2] * C) % (C == 2 ? 4 : 2) == 0 &&
-        (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && (rg.out_vox * C) % 4 == 0) {
-      const int tz2 = (TZ == 64) ? 32 : TZ;
-      const int ntz2 = (out_n0 + tz2 - 1) / tz2, nty2 = (rg.M[1] + 15) / 16, ntx2 = (rg.M[2] + 31) / 32;
-      const int64_t grid2 = (int64_t)B * ntz2 * nty2 * ntx2;
-      if (grid2 <= 0x7fffffffLL) {
-        const float nz = -0.0f, one = 1.0f;
-        f32x2 negzero2, one2;
-        uint32_t nzb, oneb;
-        memcpy(&nzb, &nz, 4); memcpy(&oneb, &one, 4);
-        negzero2 = ((f32x2)nzb << 32) | nzb; one2 = ((f32x2)oneb << 32) | oneb;
-#define NRT_RESIZE_X2(CT)                                                                                          \
-        do {                                                                                                       \
-          if (tz2 == 8) resize3d_x2_kernel<CT, 8><<<(int)grid2, 256, 0, st>>>(vol, out, rg, ntz2, nty2, ntx2, negzero2, one2);        \
-          else if (tz2 == 16) resize3d_x2_kernel<CT, 16><<<(int)grid2, 256, 0, st>>>(vol, out, rg, ntz2, nty2, ntx2, negzero2, one2); \
-          else resize3d_x2_kernel<CT, 32><<<(int)grid2, 256, 0, st>>>(vol, out, rg, ntz2, nty2, ntx2, negzero2, one2);               \
-        } while (0)
-        switch (C) {
-          case 1: NRT_RESIZE_X2(1); break;
-          case 2: NRT_RESIZE_X2(2); break;
-          case 3: NRT_RESIZE_X2(3); break;
-          default: NRT_RESIZE_X2(4); break;
-        }
-#undef NRT_RESIZE_X2
-        return check_launch("resize3d_x2_kernel");
       }
     }
     const int ntz = (out_n0 + TZ - 1) / TZ, nty = (rg.M[1] + 7) / 8, ntx = (rg.M[2] + 31) / 32;

@@ -621,7 +621,6 @@ class GaussianBlur(_Layer):
         self.seed = seed
         self._calls = 0
         self._kernel_cache = {}
-        self._fused_cache = {}
         super().__init__(**kwargs)
 
     def get_config(self):
@@ -662,18 +661,6 @@ class GaussianBlur(_Layer):
                 kernel = utils.gaussian_kernel(sigma=self.sigma, separate=True, device=x.device)
                 kernel = kernel if isinstance(kernel, list) else [kernel]
                 self._kernel_cache[key] = kernel
-            # NRT_BLUR_FUSED=1: single-channel 3-D volumes with kernels of at most 15 taps go through ONE
-            # kernel (nrt_blur3d_f32, 8 B/voxel of HBM traffic instead of 24).  Correct and tested, but on
-            # B200 it measured 0.63 ms against 0.37 ms for the three separable passes (8 x 160x192x224,
-            # sigma 1): its shared-memory tap loops and three block syncs per plane cost more than the
-            # saved traffic, so the passes stay the default.
-            if (x.dim() == 5 and x.shape[-1] == 1 and all(int(k.numel()) <= 15 for k in kernel)
-                    and os.environ.get('NRT_BLUR_FUSED', '0') == '1'):
-                fk = self._fused_cache.get(key)
-                if fk is None:
-                    fk = utils.pad_kernels_centered(kernel, x.device)
-                    self._fused_cache[key] = fk
-                return utils.blur3d_fused(x, fk)
             # an axis with sigma 0 gets the 1-tap kernel [1.0] (utils.py:628-633): x * 1 == x, skip the pass
             axes = [i for i, sg in enumerate(self.sigma) if sg > 0]
             return utils.separable_conv(x, [kernel[i] for i in axes], axis=axes, batched=True)

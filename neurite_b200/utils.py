@@ -626,53 +626,6 @@ def separable_conv(x, kernels, axis=None, batched=False, padding='SAME', strides
     return y if batched else y[0]
 
 
-def _blur3d_raw(x32, kz, ky, kx, K):
-    out = torch.empty_like(x32)
-    B, Z, Y, X = x32.shape[0], x32.shape[1], x32.shape[2], x32.shape[3]
-    with torch.cuda.device(x32.device):
-        check(lib.nrt_blur3d_f32(ptr(x32), ptr(out), B, Z, Y, X, ptr(kz), ptr(ky), ptr(kx), int(K), stream_ptr(x32.device)))
-    return out
-
-
-class _Blur3dFn(torch.autograd.Function):
-    """autograd shell of the fused blur: the adjoint of a 'SAME' odd-length cross-correlation is the
-    correlation with the flipped kernel."""
-
-    @staticmethod
-    def forward(ctx, x, kz, ky, kx, K):
-        ctx.save_for_backward(kz, ky, kx)
-        ctx.K = K
-        return _blur3d_raw(_as_f32(x.detach()).contiguous(), kz, ky, kx, K)
-
-    @staticmethod
-    def backward(ctx, g):
-        kz, ky, kx = ctx.saved_tensors
-        gx = _blur3d_raw(_as_f32(g).contiguous(), kz.flip(0).contiguous(), ky.flip(0).contiguous(),
-                         kx.flip(0).contiguous(), ctx.K)
-        return gx, None, None, None, None
-
-
-def pad_kernels_centered(kernels, device):
-    """[k_z, k_y, k_x] (odd lengths) -> three device tensors of K = max length taps, centred, zero padded."""
-    ks = [torch.as_tensor(k, dtype=torch.float32).reshape(-1) for k in kernels]
-    K = max(int(k.numel()) for k in ks)
-    K = max(K, 3)
-    out = []
-    for k in ks:
-        p = (K - k.numel()) // 2
-        out.append(torch.nn.functional.pad(k.cpu(), (p, p)).to(device).contiguous())
-    return out, K
-
-
-def blur3d_fused(x, kernels):
-    """[B, Z, Y, X, 1] blurred along all three axes by one kernel (nrt_blur3d_f32); `kernels` as
-    returned by pad_kernels_centered."""
-    require_cuda(x)
-    (kz, ky, kx), K = kernels
-    y = _Blur3dFn.apply(x.reshape(x.shape[:-1]), kz, ky, kx, K)
-    return y.reshape(x.shape)
-
-
 def subsample_indices(width, thick, upsample=True):
     """gather indices of subsample_axis for a drawn thickness (utils.py:812-823), fp32 like TF."""
     f32 = np.float32

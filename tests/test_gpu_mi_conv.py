@@ -157,12 +157,11 @@ def test_gaussian_kernel_golden_bit_exact(ne, name):
         np.testing.assert_array_equal(k.numpy(), g['k%d' % i])
 
 
-@pytest.mark.parametrize('generic', [False, True, 'fused'])
+@pytest.mark.parametrize('generic', [False, True])
 @pytest.mark.parametrize('name', golden_names('blur'))
 def test_gaussian_blur_golden(ne, monkeypatch, name, generic):
     if generic is True:
         monkeypatch.setenv('NRT_CONV_GENERIC', '1')
-    monkeypatch.setenv('NRT_BLUR_FUSED', '1' if generic == 'fused' else '0')
     g = load_golden(name)
     sigma = g['sigma'].tolist()
     lay = ne.layers.GaussianBlur(sigma=sigma)
@@ -184,11 +183,9 @@ def test_separable_conv_golden(ne, name):
     np.testing.assert_allclose(out, g['out'], rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize('fused', ['1', '0'])
-def test_blur_shapes_kernels_and_paths_vs_oracle(ne, monkeypatch, fused):
-    """fused 3-D kernel (C = 1, K <= 15) / column pass (inner >= 32) / row pass (inner < 32, C = 1 and 3),
-    wide kernels, ragged sizes, anisotropic and zero sigmas."""
-    monkeypatch.setenv('NRT_BLUR_FUSED', fused)
+def test_blur_shapes_kernels_and_paths_vs_oracle(ne):
+    """column pass (inner >= 32) / row pass (inner < 32, C = 1 and 3), wide kernels, ragged sizes, anisotropic and
+    zero sigmas."""
     rng = np.random.default_rng(21)
     for shape, sigma in (((1, 70, 33, 45, 1), 1.0), ((2, 13, 20, 37, 3), [2.0, 0.6, 1.4]), ((1, 5, 130, 1), 4.0),
                          ((1, 40, 41, 2), [0.0, 5.0]), ((3, 300, 1), 9.0), ((1, 20, 20, 20, 1), 6.5),
@@ -203,12 +200,9 @@ def test_blur_shapes_kernels_and_paths_vs_oracle(ne, monkeypatch, fused):
     assert ne.layers.GaussianBlur(sigma=0)(t) is t
 
 
-@pytest.mark.parametrize('fused', ['1', '0'])
-def test_blur_full_size_properties(ne, monkeypatch, fused):
+def test_blur_full_size_properties(ne):
     """160x192x224: constant stays constant away from the border (kernel sums to 1), the blur
-    is linear, an impulse reproduces the outer product of the 1-D kernels, and the fused kernel
-    agrees with the three passes."""
-    monkeypatch.setenv('NRT_BLUR_FUSED', fused)
+    is linear, an impulse reproduces the outer product of the 1-D kernels."""
     S = (160, 192, 224)
     lay = ne.layers.GaussianBlur(sigma=[1.0, 2.0, 1.5])
     ks = [k.numpy() for k in ne.utils.gaussian_kernel([1.0, 2.0, 1.5], separate=True)]
@@ -225,25 +219,6 @@ def test_blur_full_size_properties(ne, monkeypatch, fused):
     a = torch.randn((1,) + S + (1,), device='cuda')
     b = torch.randn_like(a)
     np.testing.assert_allclose(lay(a + 2 * b).cpu().numpy(), (lay(a) + 2 * lay(b)).cpu().numpy(), rtol=0, atol=2e-5)
-    ya = lay(a)
-    monkeypatch.setenv('NRT_BLUR_FUSED', '0' if fused == '1' else '1')
-    np.testing.assert_allclose(ya.cpu().numpy(), lay(a).cpu().numpy(), rtol=0, atol=3e-6)
-
-
-def test_fused_blur_gradient(ne, monkeypatch):
-    monkeypatch.setenv('NRT_BLUR_FUSED', '1')
-    rng = np.random.default_rng(33)
-    x = torch.from_numpy(rng.standard_normal((2, 10, 20, 70, 1)).astype(F32)).cuda().requires_grad_(True)
-    lay = ne.layers.GaussianBlur(sigma=[1.0, 0.5, 1.5])
-    y = lay(x)
-    w = torch.randn_like(y)
-    (g,) = torch.autograd.grad((y * w).sum(), x)
-    monkeypatch.setenv('NRT_BLUR_FUSED', '0')
-    x2 = x.detach().clone().requires_grad_(True)
-    y2 = lay(x2)
-    (g2,) = torch.autograd.grad((y2 * w).sum(), x2)
-    np.testing.assert_allclose(y.detach().cpu().numpy(), y2.detach().cpu().numpy(), rtol=0, atol=3e-6)
-    np.testing.assert_allclose(g.cpu().numpy(), g2.cpu().numpy(), rtol=0, atol=3e-6)
 
 
 def test_separable_conv_gradient(ne):

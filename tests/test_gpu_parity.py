@@ -446,8 +446,8 @@ def test_vxm_adjacent_transforms_vs_oracle(ne):
                                           ((40, 9, 21), 3, [2, 2, 3]), ((5, 33, 17), 2, 2), ((6, 7, 9), 1, [2, 2, 0.6]),
                                           ((33, 18, 20), 4, [0.5, 1.3, 2.1])])
 def test_resize_upsampling_vs_oracle(ne, monkeypatch, shape, C, zoom):
-    """up-sampling (and mixed) shapes through the TMA-staged tile kernels (packed two-voxel: default; one-voxel), the one-voxel z-marching kernel, the
-    packed two-voxels-per-thread kernel (even and odd output widths) and the generic kernel: -0.0 / rounding identical"""
+    """up-sampling (and mixed) shapes through the TMA-staged tile kernels (packed two-voxel: default, even and odd output widths; one-voxel), the
+    one-voxel z-marching kernel (global loads) and the generic kernel: -0.0 / rounding identical"""
     rng = np.random.default_rng(51)
     x = rng.standard_normal((2,) + shape + (C,)).astype(F32)
     x[0, 0, 0, :2] = 0.0                                     # exact zeros: the packed a*b = fma(a, b, -0) must keep their sign
@@ -459,8 +459,6 @@ def test_resize_upsampling_vs_oracle(ne, monkeypatch, shape, C, zoom):
     monkeypatch.setenv('NRT_RESIZE_TILE_X2', '0')             # -> staged source, one voxel per thread
     np.testing.assert_array_equal(ne.layers.Resize(zoom)(dev(x)).cpu().numpy(), ref)
     monkeypatch.setenv('NRT_RESIZE_TILE', '0')                # -> one-voxel z-marching kernel (global loads)
-    np.testing.assert_array_equal(ne.layers.Resize(zoom)(dev(x)).cpu().numpy(), ref)
-    monkeypatch.setenv('NRT_RESIZE_X2', '1')                  # -> packed two-voxel kernel
     np.testing.assert_array_equal(ne.layers.Resize(zoom)(dev(x)).cpu().numpy(), ref)
     monkeypatch.setenv('NRT_RESIZE_GENERIC', '1')
     np.testing.assert_array_equal(ne.layers.Resize(zoom)(dev(x)).cpu().numpy(), ref)
