@@ -430,6 +430,12 @@ def bench_warp(args):
     }
     del vol, flow
     torch.cuda.empty_cache()
+    # the NUMA binding was for the pinned staging buffers of the end-to-end path; the CPU legs below use every core
+    if orig_aff:
+        try:
+            os.sched_setaffinity(0, orig_aff)
+        except OSError:
+            pass
     if not args.no_extras:
         if world == 1:
             line['ops'] = run_ops(args, world, rank, local, dev)
@@ -444,7 +450,6 @@ def bench_warp(args):
                 torch.cuda.empty_cache()
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            cpu_setup(orig_aff)
             line['cpu_baseline'] = cpu_baseline_warp(args.method)
             if not args.no_numpy_baseline:
                 line['cpu_baseline_numpy'] = cpu_baseline_warp_numpy(args.method)
@@ -885,7 +890,6 @@ def bench_blur(args):
 def single_op(args, fn):
     import torch
     world, rank, local = dist_setup(args.gpus)
-    bind_host_to_gpu(local)
     dev = torch.device('cuda', local)
     rec = fn(args, world, rank, dev)
     if rank == 0:

@@ -23,4 +23,7 @@ for op in "warp_mc --channels 16 --flow smooth" "warp_mc --channels 3" "warp_mc 
   python -c "
 import json; d=json.loads(open('gpurun_out/r2p_op_$n.json').read().strip().splitlines()[-1]); print('$op', d['ms_per_step'], d['roofline']['frac'])"
 done
+( timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 500 \
+    -k "march_kernel_multichannel_bit_exact and 16-shape0 or resize_upsampling_vs_oracle and shape2 or lc3d_golden or warp_tile_configs_bit_exact and 2-shape0 or warp_slabs" 2>&1 | tail -8 ) > gpurun_out/r2p_sanitizer.txt 2>&1
+tail -3 gpurun_out/r2p_sanitizer.txt
 ls -la gpurun_out | grep r2p_ | wc -l
