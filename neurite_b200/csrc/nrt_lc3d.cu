@@ -230,14 +230,8 @@ template <int BB, int WPP>
 __global__ void __launch_bounds__((kLcMaxWarps * WPP + 1) * 32, 1)
 lc3d_patch_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ kernel,
                   const float* __restrict__ bias, float* __restrict__ out, LcGeo g, int b_base,
-                  int stages, int cq_log2, int pair) {
+                  int stages, int cq_log2) {
   constexpr int NB = BB * WPP;
-  // pair mode: CTAs 2i and 2i+1 walk the SAME positions and take NB batch items each (2 NB per launch).  They run
-  // on different SMs at the same pace, so the second request for a weight block is served by L2: the HBM stream stays
-  // one pass over the weights while every SM keeps the (better) occupancy of the NB-item configuration.
-  const int cta = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int ncta = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  b_base += pair ? (int)(blockIdx.x & 1) * NB : 0;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int CQ = 1 << cq_log2;
   const uint32_t blk_bytes = (uint32_t)g.F * g.Cout * sizeof(float);
@@ -256,7 +250,7 @@ lc3d_patch_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restr
   if (wid == groups * WPP) {
     if (lane == 0) {
       int k = 0;
-      for (int64_t n = cta; n < g.pn; n += ncta, ++k) {
+      for (int64_t n = blockIdx.x; n < g.pn; n += gridDim.x, ++k) {
         const int slot = k % stages, round = k / stages;
         if (round >= 1) mbar_wait(empty + slot, (uint32_t)((round - 1) & 1), 1000000 + k);
         unsigned char* dst = smem_raw + (size_t)slot * slot_stride;
@@ -276,7 +270,7 @@ lc3d_patch_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restr
   const int grp = wid / WPP, sub = wid - grp * WPP;
   const int b0 = b_base + sub * BB;
   int k = grp;
-  for (int64_t n = (int64_t)cta + (int64_t)grp * ncta; n < g.pn; n += (int64_t)groups * ncta, k += groups) {
+  for (int64_t n = (int64_t)blockIdx.x + (int64_t)grp * gridDim.x; n < g.pn; n += (int64_t)groups * gridDim.x, k += groups) {
     const int slot = k % stages;
     const uint32_t ph = (uint32_t)((k / stages) & 1);
     const unsigned char* base = smem_raw + (size_t)slot * slot_stride;
@@ -459,7 +453,7 @@ static int launch_stream(const float* x, const float* kernel, const float* bias,
 // Returns 1 when the geometry is not covered (caller takes lc3d_stream_kernel).
 template <int BB, int WPP>
 static int launch_patch(const float* x, const float* kernel, const float* bias, float* out, const LcGeo& g,
-                        int b_base, int cq_log2, cudaStream_t st, int pair = 0) {
+                        int b_base, int cq_log2, cudaStream_t st) {
   constexpr int NB = BB * WPP;
   if (g.feature_order != 0 || g.Cin % 4 != 0 || g.Cin > 256 || g.K[0] > 256 || g.K[1] > 256 || g.K[2] > 256 || !aligned16(x))
     return 1;
@@ -481,18 +475,13 @@ static int launch_patch(const float* x, const float* kernel, const float* bias, 
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("cudaFuncSetAttribute(lc3d_patch)");
   int grid = sm_count();
-  if (pair) {
-    grid &= ~1;                                    // CTA pairs
-    if (g.pn * 2 < grid) grid = (int)g.pn * 2;
-  } else if (g.pn < grid) {
-    grid = (int)g.pn;
-  }
+  if (g.pn < grid) grid = (int)g.pn;
   int nw = kLcMaxWarps;
   if (const char* e = getenv("NRT_LC3D_WARPS")) nw = atoi(e);
   if (nw < 1) nw = 1;
   if (nw > kLcMaxWarps) nw = kLcMaxWarps;
   if (nw > stages - 1) nw = stages - 1;
-  kern<<<grid, (nw * WPP + 1) * 32, smem, st>>>(tmx, kernel, bias, out, g, b_base, stages, cq_log2, pair);
+  kern<<<grid, (nw * WPP + 1) * 32, smem, st>>>(tmx, kernel, bias, out, g, b_base, stages, cq_log2);
   return check_launch("lc3d_patch_kernel");
 }
 
@@ -550,12 +539,8 @@ extern "C" int nrt_lc3d_fwd_f32(const float* x, const float* kernel, const float
         int prc;
         if (left >= 8) {
           // <4,2>: two warps per position, four batch items each; <2,4>: four warps, two items each (more warps in flight)
-          // <2,4>: four warps per position, two items each; <4,2>: two warps, four items each; 22 (pairs): CTA pairs share
-          // a position, four items per CTA (two warps x two items), the partner's weight block comes out of L2
-          const int b8 = env_int("NRT_LC3D_B8", 24);
-          prc = b8 == 22 ? launch_patch<2, 2>(x, kernel, bias, out, g, b, cq_log2, st, 1)
-              : b8 == 24 ? launch_patch<2, 4>(x, kernel, bias, out, g, b, cq_log2, st)
-                         : launch_patch<4, 2>(x, kernel, bias, out, g, b, cq_log2, st);
+          prc = env_int("NRT_LC3D_B8", 24) == 24 ? launch_patch<2, 4>(x, kernel, bias, out, g, b, cq_log2, st)
+                                                  : launch_patch<4, 2>(x, kernel, bias, out, g, b, cq_log2, st);
           if (prc <= 0) { rc = prc; b += 8; continue; }
         }
         else if (left >= 4) { prc = launch_patch<2, 2>(x, kernel, bias, out, g, b, cq_log2, st); if (prc <= 0) { rc = prc; b += 4; continue; } }

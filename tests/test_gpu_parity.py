@@ -355,13 +355,6 @@ def test_lc3d_vs_oracle_batches_activations_and_sharding(ne, monkeypatch, ffma2,
         ref = olc3d.locally_connected_3d(x, kernel, bias, (3, 3, 3), activation=act, literal=False)
         out = local_conv3d(dev(x), dev(kernel), dev(bias), (3, 3, 3), (1, 1, 1), O, activation=act).cpu().numpy()
         np.testing.assert_allclose(out, ref, rtol=1e-5, atol=2e-5)
-    if patch == '1':
-        # the batch-8 pass in its three shapes (4 warps x 2 items, 2 warps x 4 items, CTA pairs x 4 items): same bits
-        for b8 in ('42', '22'):
-            monkeypatch.setenv('NRT_LC3D_B8', b8)
-            alt = local_conv3d(dev(x), dev(kernel), dev(bias), (3, 3, 3), (1, 1, 1), O, activation='sigmoid').cpu().numpy()
-            np.testing.assert_array_equal(out, alt)
-        monkeypatch.delenv('NRT_LC3D_B8')
     if ffma2 == '1':
         monkeypatch.setenv('NRT_LC3D_FFMA2', '0')
         monkeypatch.setenv('NRT_LC3D_PATCH', '0')
