@@ -1,31 +1,25 @@
 #!/bin/bash
-# round 2, multi-GPU visit: N = $1 (2, 4 or 8).  NCCL equivalence tests, the slab / cfg5 ops and the default line.
+# round 2, multi-GPU visit: peer-memory transport of the slab plan (N = $1), plus the resize tile-x2 kernel on one GPU
 N=${1:-2}
 mkdir -p gpurun_out
-nvidia-smi -L | wc -l
+( timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 300 -k "resize" 2>&1 | tail -5 ) > gpurun_out/r2m_pytest_resize.log 2>&1; tail -2 gpurun_out/r2m_pytest_resize.log
+for v in "NRT_RESIZE_TILE_X2=1" "NRT_RESIZE_TILE_X2=0" "NRT_RESIZE_TILE_X2=1 NRT_RESIZE_TZ=16"; do ( env $v timeout 200 python bench.py --op resize --no-cpu-baseline ) > gpurun_out/r2m_tmp.json 2>> gpurun_out/r2m.err; python -c "
+import json; d=json.loads(open('gpurun_out/r2m_tmp.json').read().strip().splitlines()[-1]); print('resize $v', d['ms_per_step'], d['roofline']['frac'])"; done
 ( timeout 900 python -m pytest tests/test_multi_gpu.py -q --timeout 600 -m gpu 2>&1 | tail -15 ) > gpurun_out/r2m${N}_pytest_multi.log 2>&1; tail -4 gpurun_out/r2m${N}_pytest_multi.log
-run() {  # name, extra args
+run() {
   ( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 300)) bench.py --gpus $N $2 ) > gpurun_out/r2m${N}_$1.json 2>> gpurun_out/r2m${N}.err
   python - "$1" "$N" <<'PY'
 import json, sys
 name, n = sys.argv[1], sys.argv[2]
 try:
     d = json.loads(open('gpurun_out/r2m%s_%s.json' % (n, name)).read().strip().splitlines()[-1])
-    print(name, json.dumps({k: d[k] for k in d if k in ('value', 'ms_per_step', 'overlap', 'serial', 'exchange_only_us', 'kernels_only_us', 'limiter', 'batch', 'slab', 'error')})[:1500])
-    if name == 'default':
-        for k in ('slab', 'slab_c16', 'cfg5'):
-            print('  ', k, json.dumps(d.get(k))[:1200])
-        print('   e2e', d['e2e'], 'roofline', d['roofline']['frac'])
+    print(name, json.dumps({k: d[k] for k in d if k in ('overlap', 'overlap_nccl', 'serial', 'one_gpu_whole_volume', 'batch', 'slab', 'error')})[:2600])
 except Exception as e:
     print(name, 'unreadable', e)
 PY
 }
-if [ "$N" != "8" ]; then
-  run slab_c1 "--op warp_slab --slab-channels 1 --steps 200"
-  run slab_c16 "--op warp_slab --slab-channels 16 --steps 100"
-  run cfg5 "--op cfg5 --cfg5-steps 5"
-fi
+run slab_c1 "--op warp_slab --slab-channels 1 --steps 200"
+run slab_c16 "--op warp_slab --slab-channels 16 --steps 100"
 run slab_c16_b8 "--op warp_slab --slab-channels 16 --slab-batch 8 --steps 50"
-run dice "--op dice"
-run default "--steps 20 --warmup 5"
-tail -5 gpurun_out/r2m${N}.err
+run cfg5 "--op cfg5 --cfg5-steps 5"
+grep -v "^\*\|^$\|OMP_NUM" gpurun_out/r2m${N}.err | tail -12
