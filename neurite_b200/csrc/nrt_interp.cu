@@ -1375,13 +1375,16 @@ extern "C" {
 
 int nrt_interpn_f32(const float* vol, const int32_t* vol_shape, int D, int C, const float* loc,
                     int64_t n_out, int method, int has_fill, float fill, float* out, void* stream) {
-  int rc = check_common(D, C, method);
+  // the reference's interpn takes any number of dimensions (utils.py:106-120); the gather kernel is instantiated for
+  // D = 1..5 (2^D corners per point), the warp / resize entry points for the D <= 3 of the layers that call them
+  NRT_REQUIRE(D >= 1 && D <= 5, NRT_E_ARG, "D must be 1..5 (got %d)", D);
+  int rc = check_common(D <= 3 ? D : 3, C, method);
   if (rc != NRT_OK) return rc;
   NRT_REQUIRE(vol && vol_shape && out && (loc || n_out == 0), NRT_E_ARG, "null pointer");
   NRT_REQUIRE(n_out >= 0, NRT_E_ARG, "n_out < 0");
   Geo g;
   int64_t nvox = 1;
-  for (int d = 0; d < 3; ++d) {
+  for (int d = 0; d < 5; ++d) {
     g.S[d] = d < D ? vol_shape[d] : 1;
     NRT_REQUIRE(g.S[d] >= 1, NRT_E_ARG, "vol_shape[%d] = %d", d, g.S[d]);
     nvox *= g.S[d];
@@ -1389,6 +1392,10 @@ int nrt_interpn_f32(const float* vol, const int32_t* vol_shape, int D, int C, co
   NRT_REQUIRE(nvox <= 0x7fffffffLL, NRT_E_SIZE, "volume has %lld voxels (> int32)", (long long)nvox);
   g.src_z0 = 0; g.src_n0 = g.S[0]; g.C = C; g.has_fill = has_fill; g.fill = fill; g.err = nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (D == 4) return method == NRT_LINEAR ? launch_interpn<4, NRT_LINEAR>(vol, g, loc, n_out, out, st)
+                                          : launch_interpn<4, NRT_NEAREST>(vol, g, loc, n_out, out, st);
+  if (D == 5) return method == NRT_LINEAR ? launch_interpn<5, NRT_LINEAR>(vol, g, loc, n_out, out, st)
+                                          : launch_interpn<5, NRT_NEAREST>(vol, g, loc, n_out, out, st);
 #define CALL(DD, MM) launch_interpn<DD, MM>(vol, g, loc, n_out, out, st)
   NRT_DISPATCH_D_METHOD(D, method, CALL);
 #undef CALL

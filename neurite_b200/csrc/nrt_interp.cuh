@@ -9,7 +9,7 @@
 namespace nrt {
 
 struct Geo {
-  int S[3];        // full spatial extent of the source volume per axis (clip bounds)
+  int S[5];        // full spatial extent of the source volume per axis (clip bounds); axes 3, 4: interpn with D = 4, 5 only
   int src_z0;      // global index of the first resident source plane (axis 0)
   int src_n0;      // resident source planes
   int C;

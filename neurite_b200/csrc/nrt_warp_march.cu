@@ -156,9 +156,11 @@ warp3d_march_kernel(const __grid_constant__ CUtensorMap tm_vol, const __grid_con
       const float lz = __fadd_rn(fz, fl[0]);
       const float ly = __fadd_rn((float)gy, fl[1]);
       const float lx = __fadd_rn((float)gx, fl[2]);
-      // Quads of this thread: [q * QPT, (q + 1) * QPT), visited in a rotated order so that the lanes of a quarter
-      // warp -- consecutive voxels when the flow is smooth -- hit distinct 16-byte bank groups: a voxel is Q quads
-      // wide, 8 / Q voxels share a 128-byte bank cycle, so voxel v starts at rotation v * Q / 8.
+      // Quads of this thread: q, q + LPV, q + 2 LPV, ... (interleaved: in one pass the LPV lanes of a voxel read LPV
+      // ADJACENT quads, one contiguous 16 LPV-byte piece, so a quarter warp touches 8 / LPV pieces instead of 8
+      // scattered quads -- fewer bank-group collisions for incoherent flows), visited in a rotated order so that
+      // consecutive voxels -- a smooth flow -- hit distinct bank groups: a voxel is Q quads wide, 8 / Q voxels share a
+      // 128-byte bank cycle, so voxel v starts at rotation v * Q / 8.
       const int rot = (Cfg::VEC && QPT > 1) ? (((vy * TX + vx) * Q) >> 3) : 0;
       float res[Cfg::QPT][CPL];
       bool ok;
@@ -170,7 +172,7 @@ warp3d_march_kernel(const __grid_constant__ CUtensorMap tm_vol, const __grid_con
         ok = az.ok & ay.ok & ax.ok;
         int s0 = wbase + az.c0; s0 -= (s0 >= R) ? R : 0;
         int s1 = s0 + az.d;     s1 -= (s1 >= R) ? R : 0;
-        const int inplane = (ay.c0 * BX + ax.c0) * CCH + q * Cfg::QPT * CPL;
+        const int inplane = (ay.c0 * BX + ax.c0) * CCH + q * CPL;
         const float* p0 = reinterpret_cast<const float*>(smem_raw + (size_t)s0 * Cfg::SLOT_BYTES) + inplane;
         const float* p1 = reinterpret_cast<const float*>(smem_raw + (size_t)s1 * Cfg::SLOT_BYTES) + inplane;
         const int dy = ay.d * BX * CCH, dx = ax.d * CCH;
@@ -178,7 +180,7 @@ warp3d_march_kernel(const __grid_constant__ CUtensorMap tm_vol, const __grid_con
         corner_weights(az.wlo, az.whi, ay.wlo, ay.whi, ax.wlo, ax.whi, k);
 #pragma unroll
         for (int qi = 0; qi < Cfg::QPT; ++qi) {
-          const int qo = (Cfg::QPT > 1 ? ((qi + rot) % Cfg::QPT) : 0) * CPL;        // offset of this pass's quad
+          const int qo = (Cfg::QPT > 1 ? ((qi + rot) % Cfg::QPT) : 0) * LPV * CPL;  // offset of this pass's quad
           float v[8][CPL];
           lds_channels<CPL>(p0 + qo, v[0]);           lds_channels<CPL>(p0 + qo + dx, v[1]);
           lds_channels<CPL>(p0 + qo + dy, v[2]);      lds_channels<CPL>(p0 + qo + dy + dx, v[3]);
@@ -199,13 +201,13 @@ warp3d_march_kernel(const __grid_constant__ CUtensorMap tm_vol, const __grid_con
         const int cx = nearest_box<true, BX>(lx, ox, lo_x, hi_x, W - 1, ok);
         int s0 = wbase + cz; s0 -= (s0 >= R) ? R : 0;
         const float* p0 = reinterpret_cast<const float*>(smem_raw + (size_t)s0 * Cfg::SLOT_BYTES) +
-                          (cy * BX + cx) * CCH + q * Cfg::QPT * CPL;
+                          (cy * BX + cx) * CCH + q * CPL;
 #pragma unroll
         for (int qi = 0; qi < Cfg::QPT; ++qi)
-          lds_channels<CPL>(p0 + (Cfg::QPT > 1 ? ((qi + rot) % Cfg::QPT) : 0) * CPL, res[qi]);
+          lds_channels<CPL>(p0 + (Cfg::QPT > 1 ? ((qi + rot) % Cfg::QPT) : 0) * LPV * CPL, res[qi]);
       }
       if (gx >= W || gy >= H) continue;                         // lanes of a partial tile (after the loads: no divergence above)
-      float* op = outb + (((size_t)zl * H + gy) * W + gx) * Ctot + c_base + q * Cfg::QPT * CPL;
+      float* op = outb + (((size_t)zl * H + gy) * W + gx) * Ctot + c_base + q * CPL;
       if (!ok) {
         // rare: a corner outside the staged window -> the generic global gather (identical semantics, incl. the
         // fill rule and the resident-plane check that raises the device error flag)
@@ -217,8 +219,8 @@ warp3d_march_kernel(const __grid_constant__ CUtensorMap tm_vol, const __grid_con
 #pragma unroll
           for (int qi = 0; qi < Cfg::QPT; ++qi) {
             float r4[4];
-            gather_point<3, 4, METHOD>(volb, g, kc, oob, c_base + (q * Cfg::QPT + qi) * 4, r4);
-            *reinterpret_cast<float4*>(op + qi * 4) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+            gather_point<3, 4, METHOD>(volb, g, kc, oob, c_base + (q + LPV * qi) * 4, r4);
+            *reinterpret_cast<float4*>(op + LPV * qi * 4) = make_float4(r4[0], r4[1], r4[2], r4[3]);
           }
         } else {
 #pragma unroll
@@ -239,7 +241,7 @@ warp3d_march_kernel(const __grid_constant__ CUtensorMap tm_vol, const __grid_con
       if (CPL == 4) {
 #pragma unroll
         for (int qi = 0; qi < Cfg::QPT; ++qi) {
-          const int qo = (Cfg::QPT > 1 ? ((qi + rot) % Cfg::QPT) : 0) * 4;
+          const int qo = (Cfg::QPT > 1 ? ((qi + rot) % Cfg::QPT) : 0) * LPV * 4;
           *reinterpret_cast<float4*>(op + qo) = make_float4(res[qi][0], res[qi][1 % CPL], res[qi][2 % CPL], res[qi][3 % CPL]);
         }
       } else {

@@ -19,7 +19,8 @@ import torch
 from . import _lib
 from ._lib import lib, check, ptr, stream_ptr, i32_array, method_id, require_cuda
 
-MAX_DIMS = 3
+MAX_DIMS = 3             # warp / resize (the layers that call them are 1-3 D)
+MAX_INTERPN_DIMS = 5     # interpn itself takes any D in the reference (utils.py:106-120); built for 1..5
 
 
 def _as_f32(t):
@@ -44,9 +45,9 @@ def interpn(vol, loc, interp_method='linear', fill_value=None):
     if nb_dims > vol.dim():                                             # :115-117
         raise Exception("Loc dimension %d does not match volume dimension %d" % (nb_dims, vol.dim()))
     method = method_id(interp_method)                                   # AssertionError, :194-195
-    if nb_dims > MAX_DIMS:
+    if nb_dims > MAX_INTERPN_DIMS:
         raise NotImplementedError('neurite_b200.interpn supports up to %d spatial dims (got %d)'
-                                  % (MAX_DIMS, nb_dims))
+                                  % (MAX_INTERPN_DIMS, nb_dims))
     require_cuda(vol, loc)
     if vol.dim() == nb_dims:                                            # :119-120
         vol = vol.unsqueeze(-1)
@@ -56,6 +57,8 @@ def interpn(vol, loc, interp_method='linear', fill_value=None):
     vol32 = _as_f32(vol).contiguous()
     loc32 = _as_f32(loc).contiguous()                                   # :123-127
     if torch.is_grad_enabled() and (vol32.requires_grad or loc32.requires_grad):
+        if nb_dims > MAX_DIMS:
+            raise NotImplementedError('interpn gradients are built for up to %d spatial dims' % MAX_DIMS)
         out = _InterpnFn.apply(vol32, loc32, method, fill_value)
     else:
         out = _interpn_raw(vol32, loc32, method, fill_value)

@@ -25,7 +25,7 @@
 #include <omp.h>
 #endif
 
-#define MAXD 3
+#define MAXD 5
 
 void oracle_set_num_threads(int n) {
 #ifdef _OPENMP

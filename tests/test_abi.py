@@ -43,7 +43,7 @@ def test_argument_validation_returns_status_codes():
     assert lib.nrt_interpn_f32(null, shape, 3, 1, null, 0, 0, 0, 0.0, null, null) == -1      # null pointers
     assert b'null' in lib.nrt_last_error_string()
     one = ctypes.c_void_p(16)
-    assert lib.nrt_interpn_f32(one, shape, 4, 1, one, 0, 0, 0, 0.0, one, null) == -1         # D = 4
+    assert lib.nrt_interpn_f32(one, _lib.i32_array([2] * 6), 6, 1, one, 0, 0, 0, 0.0, one, null) == -1   # D = 6 (built for 1..5)
     assert lib.nrt_interpn_f32(one, shape, 3, 1, one, 0, 7, 0, 0.0, one, null) == -1         # bad method
     assert b'linear or nearest' in lib.nrt_last_error_string()
     assert lib.nrt_warp_f32(one, one, one, 1, shape, 3, 1, 0, 0, 0.0, 0, 9, 0, 4, 0, null, null) == -1   # src planes > volume

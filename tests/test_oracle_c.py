@@ -23,7 +23,8 @@ def test_c_warp_golden_bit_exact(name):
 
 
 @pytest.mark.parametrize('name', [n for n in golden_names('interpn_3d_c') if 'cnone' not in n] +
-                         ['interpn_1d_linear', 'interpn_1d_nearest'])
+                         ['interpn_1d_linear', 'interpn_1d_nearest', 'interpn_4d_linear_fillnone', 'interpn_4d_nearest_fill0p0',
+                          'interpn_5d_linear_fill2p5'])
 def test_c_interpn_golden_bit_exact(name):
     g = load_golden(name)
     vol = g['vol'] if g['vol'].ndim == g['loc'].shape[-1] + 1 else g['vol'][..., None]

@@ -96,6 +96,17 @@ def gen_interpn():
         out = npy(ne.utils.interpn(T(vol), T(loc), interp_method=method, fill_value=1.5))
         save('interpn_1d_%s' % method, ref, vol=vol, loc=loc, out=out, method=np.array(method),
              fill=np.array(1.5, dtype=F32))
+    # more than three dimensions: the reference's interpn is N-D (utils.py:106-120, 2^D corners in product order)
+    for D, vshape, C in ((4, (5, 6, 4, 7), 2), (5, (3, 4, 3, 5, 4), None)):
+        vol = rng.standard_normal(vshape if C is None else vshape + (C,)).astype(F32)
+        loc = np.stack([rng.uniform(-1.5, s + 0.5, (6, 7)) for s in vshape], -1).astype(F32)
+        loc[0, 0] = 0
+        loc[0, 1] = [s - 1 for s in vshape]
+        loc[0, 2] = [0.5 + (d % 2) for d in range(D)]
+        for method, fill in (('linear', None), ('linear', 2.5), ('nearest', 0.0)):
+            out = npy(ne.utils.interpn(T(vol), T(loc), interp_method=method, fill_value=fill))
+            save('interpn_%dd_%s_fill%s' % (D, method, 'none' if fill is None else str(fill).replace('.', 'p')), ref,
+                 vol=vol, loc=loc, out=out, method=np.array(method), fill=np.array(np.nan if fill is None else fill, dtype=F32))
     # integer-valued label volume + nearest + fill 0: the only in-repo usage (models.py:806-809)
     vol = rng.integers(0, 16, (8, 9, 10, 1)).astype(F32)
     loc = identity_plus((8, 9, 10), rng, 2.5)
