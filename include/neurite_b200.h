@@ -53,7 +53,7 @@ NRT_API const char* nrt_status_string(int status);
 
 /* ---------------------------------------------------------------------------------------
  * interpn -- replaces neurite/tf/utils/utils.py:73-220 (interpn).
- *   vol  [S_0..S_{D-1}, C]   loc [n_out, D]   out [n_out, C]      D in 1..3
+ *   vol  [S_0..S_{D-1}, C]   loc [n_out, D]   out [n_out, C]      D in 1..5
  *   method NRT_LINEAR: clip / floor / 2^D-corner gather in itertools.product order with
  *   weights ((w0*w1)*w2), separate mul and add roundings (utils.py:139-191);
  *   NRT_NEAREST: int32(round_half_even(loc)) THEN clip (utils.py:196-197).
