@@ -8,6 +8,7 @@ keras multi_gpu_model wrapper, neurite/tf/utils/model.py:298-321).
   * Dice / CCE            -- voxel-range sharding: every rank reduces its slab of every
                              batch item, the [B,L,3] partial sums are all-reduced
                              (metrics.Dice(group=...)); 768 B at cfg 3.
+  * gradients of that     -- `slab_warp(plan, vol, flow)`: autograd through the plan, halo part of d/dvol exchanged back
   * warp of ONE volume    -- output + flow split into contiguous z-slabs (axis 0, contiguous
                              in channels-last memory).  A rank needs source planes
                              [z0 - h, z1 + h) with h = ceil(max |flow_z|) + 1 (`SlabWarper`):
@@ -319,6 +320,72 @@ class SlabWarper:
             self._err.zero_()
             raise RuntimeError('SlabWarper: a sample fell outside the resident source planes '
                                '(halo %d too small for this flow)' % self.halo)
+
+
+class _SlabWarpFn(torch.autograd.Function):
+    """Gradient of the z-slab-sharded warp (TF-autodiff semantics of the whole-volume warp).
+
+    forward: the overlapped plan.  backward: the whole-volume gradient kernels run on the rank's EXTENDED slab (own
+    planes + the halo planes it received), with the flow and the upstream gradient zero over the halo planes -- by
+    construction of `halo` no sample of an own plane reaches the ends of the extended slab except at the true ends of
+    the volume, so clipping against the extended slab equals clipping against the volume.  d/dflow is local; the part
+    of d/dvol that landed in the halo planes belongs to the neighbours: it travels back (one exchange, the mirror image
+    of the forward one) and is added to their boundary planes."""
+
+    @staticmethod
+    def forward(ctx, plan, vol_slab, flow_slab):
+        out = plan(vol_slab.detach(), flow_slab.detach())
+        pad, lo, hi, nz = plan._pad, plan.lo_pad, plan.hi_pad, plan.nz
+        ctx.plan = plan
+        ctx.save_for_backward(plan._ext[:, pad - lo:pad + nz + hi].clone(), flow_slab.detach())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from ._lib import lib, check, ptr, stream_ptr, i32_array
+        plan = ctx.plan
+        ext, flow = ctx.saved_tensors
+        lo, hi, nz, halo = plan.lo_pad, plan.hi_pad, plan.nz, plan.halo
+        B, C = ext.shape[0], ext.shape[-1]
+        rest = tuple(ext.shape[2:-1])
+        n_ext = lo + nz + hi
+        flow_p = flow.new_zeros((B, n_ext) + rest + (flow.shape[-1],))
+        flow_p[:, lo:lo + nz] = flow
+        g_p = ext.new_zeros(ext.shape)
+        g_p[:, lo:lo + nz] = g.to(torch.float32)
+        gvol_ext = torch.zeros_like(ext)
+        gflow_p = torch.empty_like(flow_p)
+        with torch.cuda.device(ext.device):
+            check(lib.nrt_warp_bwd_f32(ptr(ext), ptr(flow_p), ptr(g_p), ptr(gvol_ext), ptr(gflow_p), B,
+                                       i32_array((n_ext,) + rest), flow.shape[-1], C, plan.method,
+                                       0 if plan.fill_value is None else 1, stream_ptr(ext.device)))
+        gvol = gvol_ext[:, lo:lo + nz].contiguous()
+        sends, recvs, adds = [], [], []
+        if plan.rank > 0:
+            sends.append((gvol_ext[:, :lo], plan.rank - 1))                   # what I scattered into the lower halo
+            r = ext.new_empty((B, halo) + tuple(ext.shape[2:]))
+            recvs.append((r, plan.rank - 1))                                  # what the lower rank scattered into MY first planes
+            adds.append((slice(0, halo), r))
+        if plan.rank < plan.world - 1:
+            sends.append((gvol_ext[:, lo + nz:], plan.rank + 1))
+            r = ext.new_empty((B, halo) + tuple(ext.shape[2:]))
+            recvs.append((r, plan.rank + 1))
+            adds.append((slice(nz - halo, nz), r))
+        _post_exchange(sends, recvs, plan.group)()
+        for sl, r in adds:
+            gvol[:, sl] += r
+        return None, gvol, gflow_p[:, lo:lo + nz].contiguous()
+
+
+def slab_warp(plan, vol_slab, flow_slab):
+    """Differentiable form of `plan(vol_slab, flow_slab)`: returns this rank's output planes; gradients flow to
+    `vol_slab` and `flow_slab` (halo contributions of d/dvol are exchanged with the neighbours in the backward pass).
+    Needs the halo transport (halo <= slab)."""
+    if torch.is_grad_enabled() and (vol_slab.requires_grad or flow_slab.requires_grad):
+        if not plan.fits:
+            raise NotImplementedError('slab_warp gradients need halo <= slab (the all-gather branch has none)')
+        return _SlabWarpFn.apply(plan, vol_slab, flow_slab)
+    return plan(vol_slab, flow_slab)
 
 
 def agreed_halo(flow_slab, group=None):

@@ -45,6 +45,8 @@ def _worker(rank, world, port, q):
                 ok = ok and torch.equal(part, whole[:, z0:z0 + nz])
         ok = ok and _slab_warper_reuse(nd, utils, dev, g, world, rank)
         ok = ok and _slab_warper_reuse(nd, utils, dev, g, world, rank, C=3, S=(40, 16, 64), transport='nccl')
+        ok = ok and _slab_warp_gradient(nd, utils, dev, g, world, rank)
+        ok = ok and _slab_warp_gradient(nd, utils, dev, g, world, rank, C=1, S=(64, 16, 32))
         # Dice / CCE: voxel-range sharding + all-reduce of the partial sums
         L = 16
         lab = torch.randint(0, L, (2,) + S, generator=g)
@@ -113,6 +115,28 @@ def _slab_warper_reuse(nd, utils, dev, g, world, rank, C=16, S=(48, 24, 32), tra
     return bool(ok)
 
 
+def _slab_warp_gradient(nd, utils, dev, g, world, rank, C=2, S=(32, 16, 64)):
+    """autograd through the slab plan == the whole-volume gradient, cut at the slab (d/dvol incl. what the neighbours
+    scattered into this rank's boundary planes; d/dflow local)"""
+    vol = torch.randn((2,) + S + (C,), generator=g).to(dev)
+    flow = ((torch.rand((2,) + S + (3,), generator=g) * 2 - 1) * 2.5).to(dev)
+    w = torch.randn((2,) + S + (C,), generator=g).to(dev)
+    vw, fw = vol.clone().requires_grad_(True), flow.clone().requires_grad_(True)
+    (utils._warp_batched(vw, fw) * w).sum().backward()
+    z0, nz = nd.slab_bounds(S[0], world, rank)
+    plan = nd.SlabWarper(S[0], halo=4)
+    if not plan.fits:
+        return True
+    vs = vol[:, z0:z0 + nz].contiguous().requires_grad_(True)
+    fs = flow[:, z0:z0 + nz].contiguous().requires_grad_(True)
+    out = nd.slab_warp(plan, vs, fs)
+    (out * w[:, z0:z0 + nz]).sum().backward()
+    plan.check()
+    ok = bool(torch.allclose(fs.grad, fw.grad[:, z0:z0 + nz], rtol=1e-5, atol=1e-5))
+    ok = ok and bool(torch.allclose(vs.grad, vw.grad[:, z0:z0 + nz], rtol=1e-5, atol=1e-5))
+    return ok
+
+
 def _mi_and_blur_sharded(ne, nd, dist, dev, S, g, world, rank, with_blur=True):
     """MutualInformation with the voxel range sharded (bins from the all-reduced min/max, one all-reduce of
     the sums, gradient incl. the min/max path) and the z-slab GaussianBlur must equal the unsharded results."""
@@ -171,6 +195,8 @@ def _one_gpu_worker(rank, world, port, q):
         from neurite_b200 import utils
         ok = ok and _slab_warper_reuse(nd, utils, dev, g, world, rank)
         ok = ok and _slab_warper_reuse(nd, utils, dev, g, world, rank, C=1, S=(24, 16, 64))
+        ok = ok and _slab_warp_gradient(nd, utils, dev, g, world, rank)
+        ok = ok and _slab_warp_gradient(nd, utils, dev, g, world, rank, C=1, S=(32, 16, 32))
         L = 16
         lab = torch.randint(0, L, (2,) + S, generator=g)
         t = torch.nn.functional.one_hot(lab, L).float().to(dev)
