@@ -132,8 +132,10 @@ def _slab_warp_gradient(nd, utils, dev, g, world, rank, C=2, S=(32, 16, 64)):
     out = nd.slab_warp(plan, vs, fs)
     (out * w[:, z0:z0 + nz]).sum().backward()
     plan.check()
-    ok = bool(torch.allclose(fs.grad, fw.grad[:, z0:z0 + nz], rtol=1e-5, atol=1e-5))
-    ok = ok and bool(torch.allclose(vs.grad, vw.grad[:, z0:z0 + nz], rtol=1e-5, atol=1e-5))
+    # (the plan works in slab coordinates: float(z - z0 + halo) + flow rounds differently from float(z) + flow in the last
+    #  bit, so the gradients agree to ~1e-6 of their scale, not bit for bit)
+    ok = bool((fs.grad - fw.grad[:, z0:z0 + nz]).abs().max() <= 5e-6 * float(fw.grad.abs().max()))
+    ok = ok and bool((vs.grad - vw.grad[:, z0:z0 + nz]).abs().max() <= 5e-6 * float(vw.grad.abs().max()))
     return ok
 
 
