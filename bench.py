@@ -698,13 +698,20 @@ def slab_record(args, world, rank, dev, channels=1, batch=1):
         graph = None
         if plan.active_transport == 'peer':
             # the same step as ONE CUDA-graph replay (no python / launch overhead between its pieces)
+            err = None
             try:
                 plan.capture(src, flow, out)
+            except Exception as ex:                          # noqa: BLE001
+                err = '%s: %s' % (type(ex).__name__, str(ex)[:200])
+            # the replay contains device-side barriers: every rank must have a graph, or nobody replays
+            okf = torch.tensor([0.0 if err else 1.0], device=dev)
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            if float(okf.item()) > 0:
                 ms_g = timed_region(plan.replay, steps, 3, world, min_preheat_s=0.0)
                 plan.check()
                 graph = {'ms_per_step': ms_g / steps, 'value': B * V * steps / (ms_g * 1e-3), 'unit': 'voxels/s'}
-            except Exception as ex:                          # noqa: BLE001
-                graph = {'error': '%s: %s' % (type(ex).__name__, str(ex)[:200])}
+            else:
+                graph = {'error': err or 'capture failed on another rank'}
         return {'transport': plan.active_transport, 'cuda_graph_replay': graph,
                 'ms_per_step': ms_ov / steps, 'value': B * V * steps / (ms_ov * 1e-3),
                 'unit': 'voxels/s', 'exchange_only_us': ms_ex / steps * 1e3, 'kernels_only_us': ms_k / steps * 1e3,
