@@ -344,7 +344,9 @@ int warp3d_march(const float* vol, const float* flow, float* out, int B, const i
 #define NRT_MARCH_G(cch, ty, tx, ahead, nw, qq, gg)                                                                 \
   rc = method == NRT_LINEAR ? launch_march<cch, ty, tx, 3, ahead, nw, NRT_LINEAR, qq, gg>(vol, flow, out, mg, st)  \
                             : launch_march<cch, ty, tx, 3, ahead, nw, NRT_NEAREST, qq, gg>(vol, flow, out, mg, st)
-  const int groups = env_int("NRT_MARCH_GROUPS", 2);
+  // measured on B200 (profiles/README.md): two plane groups = 16 consumer warps change nothing (C = 16 i.i.d. 0.584 vs
+  // 0.573, smooth 0.627 vs 0.633): the kernel is not short of warps; one group (ring 7 + 3) stays the default
+  const int groups = env_int("NRT_MARCH_GROUPS", 1);
   if (C % 16 == 0) {
     // QPT 2 / 4: a thread owns 8 / 16 channels of its voxel and shares the corner setup between them; with two quads
     // per thread a plane needs 8 warps, so two output planes are in flight (16 consumer warps, ring = 7 + 1 + 2)
