@@ -609,6 +609,215 @@ resize3d_tile_x2_kernel(const __grid_constant__ CUtensorMap tm_vol, const float*
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// resize3d_pair_kernel: the packed voxel-pair kernel again, with the three things its SASS and its capture
+// (profiles/r02_ncu_full_resize.txt: 83 instructions per voxel, issue-bound) showed to be overhead removed:
+//   * corner reads are LDS with 32-bit offsets and immediate channel offsets.  resize3d_tile_x2_kernel reads through
+//     a pointer that is shared OR global at run time, i.e. generic LD.E with 64-bit address arithmetic: 88
+//     instructions per 24 loads.  Here the marching loop is a template on the address space.
+//   * the two source planes of a z cell live in two register sets tagged with the source plane they hold; entering
+//     the next cell loads ONE plane into the set that is free and swaps the roles of the sets (two copies of the
+//     arithmetic, selected by a CTA-uniform branch) instead of moving 24 registers from `hi` to `lo`.
+//   * prologue: one thread derives the box origin from the tile's first / last output per axis (the linspace is
+//     monotonic: no loop over the table, no second block barrier) and issues the TMA load while the other threads
+//     build the tables; no dynamically indexed kernel parameters (they cost a 128-byte local-memory copy per thread).
+// Same arithmetic, same rounding order as resize3d_tile_x2_kernel (bit-exact with the oracle).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ Axis resize_axis(int S, int M, float delta, int i) {
+  // tf.linspace(0, S-1, M): endpoints exact, interior 0 + delta*i  (utils.py:259)
+  const float loc = (i == M - 1 && M > 1) ? (float)(S - 1) : __fmul_rn(delta, (float)i);
+  return axis_linear(loc, (float)(S - 1), S - 1);
+}
+
+template <int CT>
+__device__ __forceinline__ void resize_pair_emit(const f32x2 (&lo)[4][CT], const f32x2 (&hi)[4][CT], const f32x2 (&k)[8],
+                                                 f32x2 negzero2, f32x2 one2, f32x2 zero2, float* __restrict__ outb,
+                                                 bool has1) {
+  float ra[CT], rb[CT];
+#pragma unroll
+  for (int c = 0; c < CT; ++c) {
+    f32x2 r = fma2(fma2(k[0], lo[0][c], negzero2), one2, zero2);          // 0 + k0*v0
+#pragma unroll
+    for (int q = 1; q < 4; ++q) r = fma2(fma2(k[q], lo[q][c], negzero2), one2, r);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r = fma2(fma2(k[4 + q], hi[q][c], negzero2), one2, r);
+    unpack2(r, ra[c], rb[c]);
+  }
+  if (!has1) {
+#pragma unroll
+    for (int c = 0; c < CT; ++c) outb[c] = ra[c];
+  } else if (CT == 1) {
+    *reinterpret_cast<float2*>(outb) = make_float2(ra[0], rb[0]);
+  } else if (CT == 2) {
+    *reinterpret_cast<float4*>(outb) = make_float4(ra[0], ra[1 % CT], rb[0], rb[1 % CT]);
+  } else if (CT == 3) {
+    *reinterpret_cast<float2*>(outb) = make_float2(ra[0], ra[1 % CT]);
+    *reinterpret_cast<float2*>(outb + 2) = make_float2(ra[2 % CT], rb[0]);
+    *reinterpret_cast<float2*>(outb + 4) = make_float2(rb[1 % CT], rb[2 % CT]);
+  } else {
+    *reinterpret_cast<float4*>(outb) = make_float4(ra[0], ra[1 % CT], ra[2 % CT], ra[3 % CT]);
+    *reinterpret_cast<float4*>(outb + 4) = make_float4(rb[0], rb[1 % CT], rb[2 % CT], rb[3 % CT]);
+  }
+}
+
+// One corner (CT channels) of both voxels of a pair -> packed registers.  SHARED: 32-bit shared-window byte addresses and
+// ld.shared with the channel as an immediate offset (written as asm: left to itself the compiler keeps element indices
+// and re-derives every address from the window base inside the loop); else global element pointers.
+template <int OFF>
+__device__ __forceinline__ float lds_imm(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
+template <int CT, bool SHARED, typename AddrT>
+__device__ __forceinline__ void resize_pair_corner(f32x2 (&dst)[CT], AddrT a, AddrT b) {
+  if constexpr (SHARED) {
+    dst[0] = pack2(lds_imm<0>(a), lds_imm<0>(b));
+    if constexpr (CT > 1) dst[1] = pack2(lds_imm<4>(a), lds_imm<4>(b));
+    if constexpr (CT > 2) dst[2] = pack2(lds_imm<8>(a), lds_imm<8>(b));
+    if constexpr (CT > 3) dst[3] = pack2(lds_imm<12>(a), lds_imm<12>(b));
+  } else {
+#pragma unroll
+    for (int c = 0; c < CT; ++c) dst[c] = pack2(a[c], b[c]);
+  }
+}
+
+// SHARED: `sbox` = shared-window address of the staged box; else `src` = the batch item's volume in global memory.
+// oa / ob = (y, x) corner offsets (elements) of the pair's two voxels at the first staged plane lz (0 for global),
+// zs = z stride in elements.
+template <int CT, int TZ, bool SHARED>
+__device__ __forceinline__ void resize_pair_march(uint32_t sbox, const float* __restrict__ src, const int (&oa)[4],
+                                                  const int (&ob)[4], int zs, int lz, const float2* __restrict__ s_w,
+                                                  const int* __restrict__ s_i0, const int* __restrict__ s_i1, int nz,
+                                                  float2 wy, f32x2 exlo, f32x2 exhi, float* __restrict__ outb,
+                                                  size_t plane, bool has1, f32x2 negzero2, f32x2 one2) {
+  using AddrT = typename std::conditional<SHARED, uint32_t, const float*>::type;
+  const f32x2 zero2 = pack2(0.f, 0.f);
+  AddrT pa[4], pb[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if constexpr (SHARED) { pa[q] = sbox + 4u * (uint32_t)oa[q]; pb[q] = sbox + 4u * (uint32_t)ob[q]; }
+    else { pa[q] = src + oa[q]; pb[q] = src + ob[q]; }
+  }
+  const int zstep = SHARED ? zs * 4 : zs;                // bytes / elements per source plane
+  f32x2 P[4][CT], Q[4][CT];
+  int tagP = -1, tagQ = -1;                              // source plane held by either register set
+#pragma unroll 1
+  for (int z = 0; z < nz; ++z, outb += plane) {
+    const float2 wz = s_w[z];
+    const int i0 = s_i0[z], i1 = s_i1[z];
+    // (lo, hi) = (P, Q) unless Q already holds the lower plane: then (Q, P).  CTA-uniform.
+    const bool swapped = (tagQ == i0);
+    const int needP = swapped ? i1 : i0, needQ = swapped ? i0 : i1;
+    if (tagP != needP) {
+      const int zo = (needP - lz) * zstep;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) resize_pair_corner<CT, SHARED, AddrT>(P[q], pa[q] + zo, pb[q] + zo);
+      tagP = needP;
+    }
+    if (tagQ != needQ) {
+      const int zo = (needQ - lz) * zstep;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) resize_pair_corner<CT, SHARED, AddrT>(Q[q], pa[q] + zo, pb[q] + zo);
+      tagQ = needQ;
+    }
+    const float w00 = __fmul_rn(wz.x, wy.x), w01 = __fmul_rn(wz.x, wy.y);
+    const float w10 = __fmul_rn(wz.y, wy.x), w11 = __fmul_rn(wz.y, wy.y);
+    const f32x2 p00 = pack2(w00, w00), p01 = pack2(w01, w01), p10 = pack2(w10, w10), p11 = pack2(w11, w11);
+    f32x2 k[8];
+    k[0] = fma2(p00, exlo, negzero2); k[1] = fma2(p00, exhi, negzero2);
+    k[2] = fma2(p01, exlo, negzero2); k[3] = fma2(p01, exhi, negzero2);
+    k[4] = fma2(p10, exlo, negzero2); k[5] = fma2(p10, exhi, negzero2);
+    k[6] = fma2(p11, exlo, negzero2); k[7] = fma2(p11, exhi, negzero2);
+    if (swapped) resize_pair_emit<CT>(Q, P, k, negzero2, one2, zero2, outb, has1);
+    else resize_pair_emit<CT>(P, Q, k, negzero2, one2, zero2, outb, has1);
+  }
+}
+
+template <int CT, int TZ>
+__global__ void __launch_bounds__(256)
+resize3d_pair_kernel(const __grid_constant__ CUtensorMap tm_vol, const float* __restrict__ vol, float* __restrict__ out,
+                     ResizeGeo w, ResizeBox bxs, int ntz, int nty, int ntx, int xalign, f32x2 negzero2, f32x2 one2,
+                     int unstaged) {
+  constexpr int TY = 16, TX = 32, NT = TZ + TY + TX;   // a warp = two rows of 16 x-pairs
+  static_assert(NT < 255, "thread 255 issues the load, the threads below NT build the tables");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* s_box = reinterpret_cast<float*>(smem_raw);                                     // [bz][by][bx][CT]
+  const int box_elems = bxs.bz * bxs.by * bxs.bx * CT;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)box_elems * 4 + 15) & ~(size_t)15));
+  int* s_lo = reinterpret_cast<int*>(bar + 1);
+  __shared__ float2 s_w[NT];                                                             // (wlo, whi) per table entry
+  __shared__ int s_i[2][NT];                                                             // i0 / i1 per table entry
+  const Geo& g = w.g;
+  int tile = blockIdx.x;
+  const int tx = tile % ntx; tile /= ntx;
+  const int ty = tile % nty; tile /= nty;
+  const int tz = tile % ntz;
+  const int b = tile / ntz;
+  const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;
+  const int nz = min(TZ, w.out_n0 - z0);                 // every tile of the grid has at least one output
+  if (threadIdx.x == 255) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    // box = [first corner of the tile's first output, last corner of its last output] per axis; x start aligned
+    const int lz = resize_axis(g.S[0], w.M[0], w.delta[0], w.out_z0 + z0).i0;
+    const int hz = resize_axis(g.S[0], w.M[0], w.delta[0], w.out_z0 + z0 + nz - 1).i1;
+    const int ly = resize_axis(g.S[1], w.M[1], w.delta[1], y0).i0;
+    const int hy = resize_axis(g.S[1], w.M[1], w.delta[1], min(y0 + TY, w.M[1]) - 1).i1;
+    int lx = resize_axis(g.S[2], w.M[2], w.delta[2], x0).i0;
+    const int hx = resize_axis(g.S[2], w.M[2], w.delta[2], min(x0 + TX, w.M[2]) - 1).i1;
+    lx -= lx % xalign;
+    const int ok = (hz - lz + 1 <= bxs.bz) && (hy - ly + 1 <= bxs.by) && (hx - lx + 1 <= bxs.bx) && !unstaged;
+    s_lo[0] = lz; s_lo[1] = ly; s_lo[2] = lx; s_lo[3] = ok;
+    if (ok) {
+      mbar_expect_tx(bar, (uint32_t)(box_elems * sizeof(float)));
+      tma_load_4d(s_box, &tm_vol, bar, lx * CT, ly, lz, b);
+    }
+  } else if (threadIdx.x < NT) {
+    const int t = threadIdx.x;
+    const int d = t < TZ ? 0 : (t < TZ + TY ? 1 : 2);
+    const int i = d == 0 ? w.out_z0 + z0 + t : (d == 1 ? y0 + (t - TZ) : x0 + (t - TZ - TY));
+    const int Sd = d == 0 ? g.S[0] : (d == 1 ? g.S[1] : g.S[2]);
+    const int Md = d == 0 ? w.M[0] : (d == 1 ? w.M[1] : w.M[2]);
+    const float dd = d == 0 ? w.delta[0] : (d == 1 ? w.delta[1] : w.delta[2]);
+    float2 ww = make_float2(0.f, 0.f);
+    int i0 = -1, i1 = -1;
+    if (i < Md && (d != 0 || t < nz)) {
+      const Axis a = resize_axis(Sd, Md, dd, i);
+      i0 = a.i0; i1 = a.i1; ww = make_float2(a.wlo, a.whi);
+    }
+    s_w[t] = ww; s_i[0][t] = i0; s_i[1][t] = i1;
+  }
+  __syncthreads();
+  const bool staged = s_lo[3] != 0;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int row = wid * 2 + (lane >> 4), xp = lane & 15;
+  const int ox = x0 + 2 * xp, oy = y0 + row;
+  if (staged) mbar_wait(bar, 0);
+  if (oy >= w.M[1] || ox >= w.M[2]) return;
+  const int zs = staged ? bxs.by * bxs.bx * CT : g.S[1] * g.S[2] * CT;
+  const int ys = staged ? bxs.bx * CT : g.S[2] * CT;
+  const int lz = staged ? s_lo[0] : 0, ly = staged ? s_lo[1] : 0, lx = staged ? s_lo[2] : 0;
+  const bool has1 = ox + 1 < w.M[2];                    // odd output width: the pair's second voxel may not exist
+  const int ta = TZ + TY + 2 * xp, tb = has1 ? ta + 1 : ta;     // (a missing second voxel repeats the first: legal reads)
+  const float2 wy = s_w[TZ + row], wa = s_w[ta], wb = s_w[tb];
+  const int y_o0 = (s_i[0][TZ + row] - ly) * ys, y_o1 = (s_i[1][TZ + row] - ly) * ys;
+  const int a_o0 = (s_i[0][ta] - lx) * CT, a_o1 = (s_i[1][ta] - lx) * CT;
+  const int b_o0 = (s_i[0][tb] - lx) * CT, b_o1 = (s_i[1][tb] - lx) * CT;
+  const int oa[4] = {y_o0 + a_o0, y_o0 + a_o1, y_o1 + a_o0, y_o1 + a_o1};
+  const int ob[4] = {y_o0 + b_o0, y_o0 + b_o1, y_o1 + b_o0, y_o1 + b_o1};
+  float* outb = out + ((size_t)b * w.out_vox + ((size_t)z0 * w.M[1] + oy) * w.M[2] + ox) * CT;
+  size_t plane = (size_t)w.M[1] * w.M[2] * CT;
+  asm volatile("" : "+l"(plane));                       // opaque: keeps it in registers (it was re-derived from the parameters every plane)
+  const f32x2 exlo = pack2(wa.x, wb.x), exhi = pack2(wa.y, wb.y);
+  if (staged)
+    resize_pair_march<CT, TZ, true>(smem_u32(s_box), nullptr, oa, ob, zs, lz, s_w, s_i[0], s_i[1], nz, wy, exlo, exhi,
+                                    outb, plane, has1, negzero2, one2);
+  else                                                  // box larger than the staged extents: straight from global memory
+    resize_pair_march<CT, TZ, false>(0u, vol + (size_t)b * w.src_batch_stride, oa, ob, zs, lz, s_w, s_i[0], s_i[1], nz,
+                                     wy, exlo, exhi, outb, plane, has1, negzero2, one2);
+}
+
 // largest source extent any tile of T outputs needs along one axis, with the device's fp32 linspace arithmetic
 static int resize_axis_extent(int S, int M, float delta, int first, int count, int T, int align) {
   int ext = 1;
@@ -1525,21 +1734,31 @@ int nrt_resize_f32(const float* vol, float* out, int B, const int32_t* in_shape,
     // up-sampling: source box of every output tile staged by TMA (resize3d_tile_kernel)
     if (method == NRT_LINEAR && C >= 1 && C <= 4 && env_int("NRT_RESIZE_TILE", 1) && aligned16(vol) &&
         (rg.g.S[2] * C) % 4 == 0 && ((C != 2 && C != 4) || (reinterpret_cast<uintptr_t>(out) & (C == 4 ? 15u : 7u)) == 0)) {
-      const int tzt = (TZ == 64) ? 32 : TZ;
+      // NRT_RESIZE_TILE_X2: 2 = resize3d_pair_kernel (default), 1 = resize3d_tile_x2_kernel, 0 = one voxel per thread
+      const int x2mode = env_int("NRT_RESIZE_TILE_X2", 2);
+      // 64 planes per CTA (half the prologues and box waits) only in the pair kernel, which runs 2 CTAs per SM anyway
+      // and can afford a 100 KB box
+      const size_t box_budget = (x2mode >= 2 ? 100 : 72) * 1024;
       const int xalign = (C == 4) ? 1 : (C == 2 ? 2 : 4);
-      ResizeBox bxs;
-      bxs.bz = resize_axis_extent(rg.g.S[0], rg.M[0], rg.delta[0], out_z0, out_n0, tzt, 1);
-      // packed two-voxel variant (16-row tiles): needs an even row pitch / aligned output for its 64 / 128-bit stores
-      const bool x2 = env_int("NRT_RESIZE_TILE_X2", 1) && (rg.M[2] * C) % (C == 2 ? 4 : 2) == 0 &&
+      // packed two-voxel variants (16-row tiles): need an even row pitch / aligned output for their 64 / 128-bit stores
+      const bool x2 = x2mode != 0 && (rg.M[2] * C) % (C == 2 ? 4 : 2) == 0 &&
                       (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && (rg.out_vox * C) % 4 == 0;
+      const int unstaged = env_int("NRT_RESIZE_UNSTAGED", 0);      // test hook: every CTA takes its global-memory path
       const int tyt = x2 ? 16 : 8;
+      ResizeBox bxs;
       bxs.by = resize_axis_extent(rg.g.S[1], rg.M[1], rg.delta[1], 0, rg.M[1], tyt, 1);
       bxs.bx = resize_axis_extent(rg.g.S[2], rg.M[2], rg.delta[2], 0, rg.M[2], 32, xalign);
       bxs.bx = (bxs.bx + xalign - 1) / xalign * xalign;
+      int tzt = (TZ == 64 && !(x2 && x2mode >= 2)) ? 32 : TZ;
+      bxs.bz = resize_axis_extent(rg.g.S[0], rg.M[0], rg.delta[0], out_z0, out_n0, tzt, 1);
+      if (tzt == 64 && (size_t)bxs.bz * bxs.by * bxs.bx * C * 4 > box_budget) {       // 64 planes do not fit: 32
+        tzt = 32;
+        bxs.bz = resize_axis_extent(rg.g.S[0], rg.M[0], rg.delta[0], out_z0, out_n0, tzt, 1);
+      }
       const size_t box_bytes = (size_t)bxs.bz * bxs.by * bxs.bx * C * 4;
       const int ntz3 = (out_n0 + tzt - 1) / tzt, nty3 = (rg.M[1] + tyt - 1) / tyt, ntx3 = (rg.M[2] + 31) / 32;
       const int64_t grid3 = (int64_t)B * ntz3 * nty3 * ntx3;
-      if (box_bytes <= 72 * 1024 && bxs.bx * C <= 256 && bxs.by <= 256 && bxs.bz <= 256 && grid3 <= 0x7fffffffLL) {
+      if (box_bytes <= box_budget && bxs.bx * C <= 256 && bxs.by <= 256 && bxs.bz <= 256 && grid3 <= 0x7fffffffLL) {
         CUtensorMap tmv;
         const uint64_t vd[4] = {(uint64_t)rg.g.S[2] * C, (uint64_t)rg.g.S[1], (uint64_t)rg.g.S[0], (uint64_t)B};
         const uint32_t vb[4] = {(uint32_t)(bxs.bx * C), (uint32_t)bxs.by, (uint32_t)bxs.bz, 1};
@@ -1553,7 +1772,13 @@ int nrt_resize_f32(const float* vol, float* out, int B, const int32_t* in_shape,
         const bool minb3 = env_int("NRT_RESIZE_MINB", 1) == 3;        // registers capped for 3 CTAs per SM (experiment)
 #define NRT_RESIZE_TILE(CT, TZZ)                                                                                          \
         do {                                                                                                              \
-          if (x2 && minb3) {                                                                                              \
+          if (x2 && x2mode >= 2) {                                                                                        \
+            auto kern = resize3d_pair_kernel<CT, TZZ>;                                                                    \
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)        \
+              return check_launch("cudaFuncSetAttribute(resize3d_pair)");                                                 \
+            kern<<<(int)grid3, 256, smem, st>>>(tmv, vol, out, rg, bxs, ntz3, nty3, ntx3, xalign, negzero2, one2,         \
+                                                unstaged);                                                                \
+          } else if (x2 && minb3) {                                                                                       \
             auto kern = resize3d_tile_x2_kernel<CT, TZZ, 3>;                                                              \
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)        \
               return check_launch("cudaFuncSetAttribute(resize3d_tile_x2)");                                              \
@@ -1571,7 +1796,15 @@ int nrt_resize_f32(const float* vol, float* out, int B, const int32_t* in_shape,
           }                                                                                                               \
         } while (0)
 #define NRT_RESIZE_TILE_C(CT)                                                                                             \
-        do { if (tzt == 8) NRT_RESIZE_TILE(CT, 8); else if (tzt == 16) NRT_RESIZE_TILE(CT, 16); else NRT_RESIZE_TILE(CT, 32); } while (0)
+        do {                                                                                                              \
+          if (tzt == 64) {                                                                                                \
+            auto kern = resize3d_pair_kernel<CT, 64>;                                                                     \
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)        \
+              return check_launch("cudaFuncSetAttribute(resize3d_pair)");                                                 \
+            kern<<<(int)grid3, 256, smem, st>>>(tmv, vol, out, rg, bxs, ntz3, nty3, ntx3, xalign, negzero2, one2,         \
+                                                unstaged);                                                                \
+          } else if (tzt == 8) NRT_RESIZE_TILE(CT, 8); else if (tzt == 16) NRT_RESIZE_TILE(CT, 16); else NRT_RESIZE_TILE(CT, 32);       \
+        } while (0)
         switch (C) {
           case 1: NRT_RESIZE_TILE_C(1); break;
           case 2: NRT_RESIZE_TILE_C(2); break;

@@ -69,6 +69,8 @@ __device__ __forceinline__ int64_t patch_origin(const LcGeo& g, int64_t p) {
 // ---------------------------------------------------------------------------------------
 constexpr int kLcMaxWarps = 7;              // consumer groups (<= ring slots - 1) + 1 producer warp
 constexpr int kLcMaxStages = 8;
+constexpr int kLcB8Default = 142;           // NRT_LC3D_B8 / NRT_LC3D_B4 defaults (see nrt_lc3d_fwd_f32)
+constexpr int kLcB4Default = 22;
 
 // P2: the 4 x BB accumulators are updated with packed fma.rn.f32x2 (two fused multiply-adds per issue slot on
 // sm_100): the weight pairs are the halves of the LDS.128 result, the input value is broadcast to both halves.
@@ -348,6 +350,157 @@ lc3d_patch_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restr
 
 
 // ---------------------------------------------------------------------------------------
+// row kernel (batch >= 4, Cout = 16).  In lc3d_patch_kernel a lane owns ONE output quad and a slice of the patch
+// features: per float4 of weights it gets from shared memory (16 B) and per input value (4 B) it issues 2 * BB packed
+// FMAs, i.e. 4-6 bytes of shared-memory traffic per FFMA2 and lane.  The shared-memory crossbar delivers 128 B per clock
+// and SM, the FMA pipes take 128 lane-FFMA2 per clock: at batch 8 that kernel needs ~1300 crossbar cycles per position
+// against the 1180 cycles the position's 27.6 KB weight block takes to arrive from HBM (profiles/r02_ncu_full_lc3d_b8.txt:
+// shared-memory wavefronts 67 %, short-scoreboard stalls 3.6 per issue).
+// Here a lane owns patch ROWS j = lane, lane + 32, ... and ALL 16 output channels of BB batch items: a weight row
+// (64 B) and BB input values feed 8 * BB FFMA2 -- 1.25-1.5 B per FFMA2 and lane -- and the 16 * BB partial sums of the
+// 32 lanes are folded once per position with a reduce-scatter of shuffles (each step halves what a lane still holds).
+// Bank conflicts: rows are 64 B apart, so the lanes of a quarter-warp would hit two bank groups with the same chunk of
+// their rows; lane l therefore reads its row's four 16-byte chunks in the order q ^ m, m = (l >> 1) & 3, and accumulates
+// chunk q ^ m in register set q.
+// The fold needs no selects.  Final owner of (item, chunk): item from lane bits 4, 3 (and 0 at eight items), chunk
+// from lane bits 2, 1 -- i.e. chunk m.  (a) A lane keeps batch SLOT b for item b ^ pb, pb = its own item: its lower
+// slots then hold the items it must keep at every batch step (mask 16, 8, 1: partners that share m) and it hands over
+// the upper half.  (b) Register set 0 holds chunk 0 ^ m = the lane's own chunk, and set d holds chunk m ^ d = the own
+// chunk of lane l ^ 2d: one shuffle per set and value sends every chunk to its owner.
+// Same ring, barriers and TMA patch load as lc3d_patch_kernel.  Summation order differs from the other kernels
+// (rows are summed lane-wise first): results agree to fp32 rounding, not bit for bit.
+// ---------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void fold_upper(float* v, int mask) {      // v[0 .. N/2) += partner's v[N/2 .. N)
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i + N / 2], mask);
+}
+
+template <int BB, int WPP>
+__global__ void __launch_bounds__((kLcMaxWarps * WPP + 1) * 32, 1)
+lc3d_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ kernel,
+                 const float* __restrict__ bias, float* __restrict__ out, LcGeo g, int b_base, int stages) {
+  static_assert(BB == 4 || BB == 8, "the fold is written for 4 or 8 batch items per warp");
+  constexpr int NB = BB * WPP;
+  constexpr int CO = 16;                                 // output channels (host checks g.Cout == 16)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t blk_bytes = (uint32_t)g.F * CO * sizeof(float);
+  const uint32_t patch_bytes = (uint32_t)g.F * NB * sizeof(float);
+  const uint32_t patch_off = (blk_bytes + 127u) & ~127u;
+  const uint32_t slot_stride = (patch_off + patch_bytes + 127u) & ~127u;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * slot_stride);
+  uint64_t* empty = full + stages;
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int groups = ((int)(blockDim.x >> 5) - 1) / WPP;
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, WPP); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (wid == groups * WPP) {                             // producer: identical to lc3d_patch_kernel's
+    if (lane == 0) {
+      int k = 0;
+      for (int64_t n = blockIdx.x; n < g.pn; n += gridDim.x, ++k) {
+        const int slot = k % stages, round = k / stages;
+        if (round >= 1) mbar_wait(empty + slot, (uint32_t)((round - 1) & 1), 1000000 + k);
+        unsigned char* dst = smem_raw + (size_t)slot * slot_stride;
+        mbar_expect_tx(full + slot, blk_bytes + patch_bytes);
+        bulk_load_1d(dst, kernel + n * (int64_t)g.F * CO, blk_bytes, full + slot);
+        int64_t p = g.p0 + n;
+        const int o2 = (int)(p % g.O[2]); p /= g.O[2];
+        const int o1 = (int)(p % g.O[1]);
+        const int o0 = (int)(p / g.O[1]);
+        tma_load_5d(dst + patch_off, &tm_x, full + slot, 0, o2 * g.St[2], o1 * g.St[1], o0 * g.St[0], b_base);
+      }
+    }
+    return;
+  }
+  const int grp = wid / WPP, sub = wid - grp * WPP;
+  const int b0 = b_base + sub * BB;
+  const int m = (lane >> 1) & 3;                         // chunk permutation of this lane = the chunk it ends up with
+  // the item this lane ends up with; batch slot b of the lane accumulates item b ^ pb
+  const int pb = BB == 8 ? ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + (lane & 1) : ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+  int xoff[BB];
+#pragma unroll
+  for (int b = 0; b < BB; ++b) xoff[b] = (b ^ pb) * g.F;
+  const int iters = (g.F + 31) >> 5;
+  int k = grp;
+  for (int64_t n = (int64_t)blockIdx.x + (int64_t)grp * gridDim.x; n < g.pn; n += (int64_t)groups * gridDim.x, k += groups) {
+    const int slot = k % stages;
+    const uint32_t ph = (uint32_t)((k / stages) & 1);
+    const unsigned char* base = smem_raw + (size_t)slot * slot_stride;
+    // this lane's first row, its four chunks in the lane's order; a row step of 32 is 512 float4
+    const float4* wq0 = reinterpret_cast<const float4*>(base) + lane * 4 + (0 ^ m);
+    const float4* wq1 = reinterpret_cast<const float4*>(base) + lane * 4 + (1 ^ m);
+    const float4* wq2 = reinterpret_cast<const float4*>(base) + lane * 4 + (2 ^ m);
+    const float4* wq3 = reinterpret_cast<const float4*>(base) + lane * 4 + (3 ^ m);
+    const float* xp = reinterpret_cast<const float*>(base + patch_off) + (size_t)sub * BB * g.F + lane;
+    unsigned long long acc2[BB][8];                      // [slot][register set q, pair] = channels 4 * (q ^ m) + 2 * pair ..
+#pragma unroll
+    for (int b = 0; b < BB; ++b)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc2[b][i] = 0ull;
+    if (k >= stages) mbar_wait(empty + slot, ph ^ 1u, 2000000 + k);      // parity aliasing guard (lc3d_patch_kernel)
+    mbar_wait(full + slot, ph, k);
+#pragma unroll 2
+    for (int c = 0; c < iters; ++c) {
+      if (lane + (c << 5) < g.F) {                       // ragged last step: rows past F do not exist
+        const float4 w0 = wq0[c * 128], w1 = wq1[c * 128], w2 = wq2[c * 128], w3 = wq3[c * 128];
+        unsigned long long wp[8];
+        asm("mov.b64 %0, {%1, %2};" : "=l"(wp[0]) : "f"(w0.x), "f"(w0.y));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(wp[1]) : "f"(w0.z), "f"(w0.w));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(wp[2]) : "f"(w1.x), "f"(w1.y));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(wp[3]) : "f"(w1.z), "f"(w1.w));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(wp[4]) : "f"(w2.x), "f"(w2.y));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(wp[5]) : "f"(w2.z), "f"(w2.w));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(wp[6]) : "f"(w3.x), "f"(w3.y));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(wp[7]) : "f"(w3.z), "f"(w3.w));
+#pragma unroll
+        for (int b = 0; b < BB; ++b) {
+          const float xv = xp[xoff[b] + (c << 5)];
+          unsigned long long xx;
+          asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(xv));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[b][i]) : "l"(xx), "l"(wp[i]));
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + slot);            // slot free: every lane has read its rows
+    // ---- fold the 32 lanes' partial sums: v[slot][register set][channel in chunk]
+    float v[BB * 16];
+#pragma unroll
+    for (int b = 0; b < BB; ++b)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(v[b * 16 + 2 * i]), "=f"(v[b * 16 + 2 * i + 1]) : "l"(acc2[b][i]));
+    fold_upper<BB * 16>(v, 16);
+    fold_upper<BB * 8>(v, 8);
+    if (BB == 8) fold_upper<BB * 4>(v, 1);
+    // slot 0 = item pb, 16 values [set][e]; every other set goes to the lane that owns its chunk
+    float u[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      u[e] = v[e] + __shfl_xor_sync(0xffffffffu, v[4 + e], 2);
+      u[e] += __shfl_xor_sync(0xffffffffu, v[8 + e], 4);
+      u[e] += __shfl_xor_sync(0xffffffffu, v[12 + e], 6);
+    }
+    if (BB == 4) {                                       // lanes l and l ^ 1 hold two halves of the same sum
+#pragma unroll
+      for (int e = 0; e < 4; ++e) u[e] += __shfl_xor_sync(0xffffffffu, u[e], 1);
+    }
+    if (BB == 8 || (lane & 1) == 0) {
+      const int ch = m * 4;
+      const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + n * CO + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 r;
+      r.x = activate(u[0] + bv.x, g.activation); r.y = activate(u[1] + bv.y, g.activation);
+      r.z = activate(u[2] + bv.z, g.activation); r.w = activate(u[3] + bv.w, g.activation);
+      *reinterpret_cast<float4*>(out + ((int64_t)(b0 + pb) * g.pn + n) * CO + ch) = r;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // generic kernel: one thread per (b, position, filter)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -485,6 +638,43 @@ static int launch_patch(const float* x, const float* kernel, const float* bias, 
   return check_launch("lc3d_patch_kernel");
 }
 
+// batch >= 4 with 16 output channels: rows owned by lanes, all channels per lane (lc3d_rows_kernel).
+// Returns 1 when the geometry is not covered (caller takes lc3d_patch_kernel).
+template <int BB, int WPP>
+static int launch_rows(const float* x, const float* kernel, const float* bias, float* out, const LcGeo& g,
+                       int b_base, cudaStream_t st) {
+  constexpr int NB = BB * WPP;
+  if (g.Cout != 16 || g.feature_order != 0 || g.Cin % 4 != 0 || g.Cin > 256 || g.K[0] > 256 || g.K[1] > 256 ||
+      g.K[2] > 256 || !aligned16(x) || (bias && (reinterpret_cast<uintptr_t>(bias) & 15u) != 0))
+    return 1;
+  const uint32_t blk_bytes = (uint32_t)g.F * 16 * sizeof(float);
+  const uint32_t patch_bytes = (uint32_t)g.F * NB * sizeof(float);
+  const uint32_t patch_off = (blk_bytes + 127u) & ~127u;
+  const uint32_t slot_stride = (patch_off + patch_bytes + 127u) & ~127u;
+  int stages = (int)((220 * 1024 - 2 * kLcMaxStages * sizeof(uint64_t) - 128) / (size_t)slot_stride);
+  if (stages < 3) return 1;
+  if (stages > kLcMaxStages) stages = kLcMaxStages;
+  if (const char* e = getenv("NRT_LC3D_STAGES")) { const int s = atoi(e); if (s >= 3 && s < stages) stages = s; }
+  const size_t smem = (size_t)stages * slot_stride + (size_t)stages * 16 + 16;
+  CUtensorMap tmx;
+  const uint64_t xd[5] = {(uint64_t)g.Cin, (uint64_t)g.I[2], (uint64_t)g.I[1], (uint64_t)g.I[0], (uint64_t)g.B};
+  const uint32_t xb[5] = {(uint32_t)g.Cin, (uint32_t)g.K[2], (uint32_t)g.K[1], (uint32_t)g.K[0], (uint32_t)NB};
+  int rc = encode_f32_tiled(&tmx, x, 5, xd, xb);
+  if (rc != NRT_OK) return rc;
+  auto kern = lc3d_rows_kernel<BB, WPP>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return check_launch("cudaFuncSetAttribute(lc3d_rows)");
+  int grid = sm_count();
+  if (g.pn < grid) grid = (int)g.pn;
+  int nw = kLcMaxWarps;                          // consumer groups: as many as the ring allows, one slot left in flight
+  if (const char* e = getenv("NRT_LC3D_WARPS")) nw = atoi(e);
+  if (nw < 1) nw = 1;
+  if (nw > kLcMaxWarps) nw = kLcMaxWarps;
+  if (nw > stages - 1) nw = stages - 1;
+  kern<<<grid, (nw * WPP + 1) * 32, smem, st>>>(tmx, kernel, bias, out, g, b_base, stages);
+  return check_launch("lc3d_rows_kernel");
+}
+
 }  // namespace nrt
 
 using namespace nrt;
@@ -538,12 +728,22 @@ extern "C" int nrt_lc3d_fwd_f32(const float* x, const float* kernel, const float
         // batch > 1: the position's input patch arrives by TMA next to its weight block (lc3d_patch_kernel)
         int prc;
         if (left >= 8) {
-          // <4,2>: two warps per position, four batch items each; <2,4>: four warps, two items each (more warps in flight)
-          prc = env_int("NRT_LC3D_B8", 24) == 24 ? launch_patch<2, 4>(x, kernel, bias, out, g, b, cq_log2, st)
-                                                  : launch_patch<4, 2>(x, kernel, bias, out, g, b, cq_log2, st);
+          // NRT_LC3D_B8: 142 / 181 = row kernel (lanes own patch rows and all 16 channels), two warps x four items /
+          // one warp x eight items per position; 24 / 42 = patch kernel (lanes own an output quad), <2,4> / <4,2>
+          const int mode = env_int("NRT_LC3D_B8", kLcB8Default);
+          prc = 1;
+          if (mode == 142) prc = launch_rows<4, 2>(x, kernel, bias, out, g, b, st);
+          else if (mode == 181) prc = launch_rows<8, 1>(x, kernel, bias, out, g, b, st);
+          if (prc == 1)
+            prc = mode == 42 ? launch_patch<4, 2>(x, kernel, bias, out, g, b, cq_log2, st)
+                             : launch_patch<2, 4>(x, kernel, bias, out, g, b, cq_log2, st);
           if (prc <= 0) { rc = prc; b += 8; continue; }
         }
-        else if (left >= 4) { prc = launch_patch<2, 2>(x, kernel, bias, out, g, b, cq_log2, st); if (prc <= 0) { rc = prc; b += 4; continue; } }
+        else if (left >= 4) {
+          prc = env_int("NRT_LC3D_B4", kLcB4Default) == 141 ? launch_rows<4, 1>(x, kernel, bias, out, g, b, st) : 1;
+          if (prc == 1) prc = launch_patch<2, 2>(x, kernel, bias, out, g, b, cq_log2, st);
+          if (prc <= 0) { rc = prc; b += 4; continue; }
+        }
         else {
           // two batch items: <2,1> = one warp per position doing both, <1,2> = two warps per position, one item each
           prc = env_int("NRT_LC3D_B2", 12) == 21 ? launch_patch<2, 1>(x, kernel, bias, out, g, b, cq_log2, st)

@@ -358,6 +358,10 @@ def test_lc3d_vs_oracle_batches_activations_and_sharding(ne, monkeypatch, ffma2,
         out = local_conv3d(dev(x), dev(kernel), dev(bias), (3, 3, 3), (1, 1, 1), O, activation=act).cpu().numpy()
         np.testing.assert_allclose(out, ref, rtol=1e-5, atol=2e-5)
     if ffma2 == '1':
+        # (the quad-per-lane kernels share one summation order; the row kernels are compared in their own test)
+        monkeypatch.setenv('NRT_LC3D_B8', '24')
+        monkeypatch.setenv('NRT_LC3D_B4', '22')
+        out = local_conv3d(dev(x), dev(kernel), dev(bias), (3, 3, 3), (1, 1, 1), O, activation='sigmoid').cpu().numpy()
         monkeypatch.setenv('NRT_LC3D_FFMA2', '0')
         monkeypatch.setenv('NRT_LC3D_PATCH', '0')
         scalar = local_conv3d(dev(x), dev(kernel), dev(bias), (3, 3, 3), (1, 1, 1), O, activation='sigmoid').cpu().numpy()
@@ -378,6 +382,59 @@ def test_lc3d_vs_oracle_batches_activations_and_sharding(ne, monkeypatch, ffma2,
     a = local_conv3d(dev(x), dev(kernel[:h]), dev(bias.reshape(-1, 16)[:h]), (3, 3, 3), (1, 1, 1), O, p0=0, p_count=h)
     b = local_conv3d(dev(x), dev(kernel[h:]), dev(bias.reshape(-1, 16)[h:]), (3, 3, 3), (1, 1, 1), O, p0=h, p_count=P - h)
     np.testing.assert_allclose(torch.cat([a, b], 1).cpu().numpy(), ref, rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('b8,b4', [('142', '141'), ('181', '22'), ('24', '22')])
+def test_lc3d_row_kernels_vs_oracle(ne, monkeypatch, b8, b4):
+    """batch 13 = passes of 8 + 4 + 1 items through the row kernels (lanes own patch rows and all 16 channels: two
+    warps x four items, one warp x eight items, one warp x four items) against the oracle and against the
+    quad-per-lane kernels; bias, activations, a ragged patch (F = 20 < 32 rows), F = 48, strides 2, position shards"""
+    from neurite_b200.layers import local_conv3d
+    monkeypatch.setenv('NRT_LC3D_B8', b8)
+    monkeypatch.setenv('NRT_LC3D_B4', b4)
+    rng = np.random.default_rng(113)
+    x = rng.standard_normal((13, 8, 9, 10, 16)).astype(F32)
+    O = (6, 7, 8)
+    kernel = (rng.standard_normal((int(np.prod(O)), 27 * 16, 16)) * 0.05).astype(F32)
+    bias = rng.standard_normal(O + (16,)).astype(F32)
+    for act in (None, 'relu', 'sigmoid'):
+        ref = olc3d.locally_connected_3d(x, kernel, bias, (3, 3, 3), activation=act, literal=False)
+        out = local_conv3d(dev(x), dev(kernel), dev(bias), (3, 3, 3), (1, 1, 1), O, activation=act).cpu().numpy()
+        np.testing.assert_allclose(out, ref, rtol=1e-5, atol=2e-5)
+    out = local_conv3d(dev(x), dev(kernel), None, (3, 3, 3), (1, 1, 1), O).cpu().numpy()
+    np.testing.assert_allclose(out, olc3d.locally_connected_3d(x, kernel, None, (3, 3, 3), literal=False), rtol=1e-5, atol=2e-5)
+    for ks, st, Cin, shp in (((1, 1, 5), (1, 1, 1), 4, (3, 4, 9)), ((2, 3, 2), (2, 2, 2), 4, (9, 8, 11)), ((2, 2, 2), (1, 2, 1), 8, (5, 6, 4))):
+        xs = rng.standard_normal((12,) + shp + (Cin,)).astype(F32)
+        Os = tuple((shp[d] - ks[d]) // st[d] + 1 for d in range(3))
+        kk = (rng.standard_normal((int(np.prod(Os)), int(np.prod(ks)) * Cin, 16)) * 0.1).astype(F32)
+        bb = rng.standard_normal(Os + (16,)).astype(F32)
+        refs = olc3d.locally_connected_3d(xs, kk, bb, ks, strides=st, activation='tanh', literal=False)
+        outs = local_conv3d(dev(xs), dev(kk), dev(bb), ks, st, Os, activation='tanh').cpu().numpy()
+        np.testing.assert_allclose(outs, refs, rtol=1e-5, atol=2e-5)
+    # position sharding with the same kernels
+    ref = olc3d.locally_connected_3d(x, kernel, bias, (3, 3, 3), literal=False).reshape(13, -1, 16)
+    P = kernel.shape[0]
+    h = P // 2 + 3
+    a = local_conv3d(dev(x), dev(kernel[:h]), dev(bias.reshape(-1, 16)[:h]), (3, 3, 3), (1, 1, 1), O, p0=0, p_count=h)
+    b = local_conv3d(dev(x), dev(kernel[h:]), dev(bias.reshape(-1, 16)[h:]), (3, 3, 3), (1, 1, 1), O, p0=h, p_count=P - h)
+    np.testing.assert_allclose(torch.cat([a, b], 1).cpu().numpy(), ref, rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('b8', ['24', '142', '181'])
+def test_lc3d_batch8_shared_weights_equal_conv3d(ne, monkeypatch, b8):
+    """cfg 4 geometry, batch 8, many positions per CTA (22^3 positions over 148 CTAs: every ring slot is reused many
+    times): with position-shared weights the layer must equal a plain conv3d"""
+    monkeypatch.setenv('NRT_LC3D_B8', b8)
+    rng = np.random.default_rng(19)
+    x = torch.from_numpy(rng.standard_normal((8, 24, 24, 24, 16)).astype(F32)).cuda()
+    w = torch.from_numpy((rng.standard_normal((3, 3, 3, 16, 16)) * 0.1).astype(F32)).cuda()
+    P = 22 ** 3
+    kernel = w.reshape(1, 432, 16).expand(P, 432, 16).contiguous()
+    from neurite_b200.layers import local_conv3d
+    out = local_conv3d(x, kernel, None, (3, 3, 3), (1, 1, 1), (22, 22, 22))
+    torch.backends.cudnn.allow_tf32 = False
+    ref = torch.nn.functional.conv3d(x.permute(0, 4, 1, 2, 3), w.permute(4, 3, 0, 1, 2)).permute(0, 2, 3, 4, 1)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=1e-4)
 
 
 def test_lc3d_shared_weights_equal_conv3d_cfg4_shape(ne):
@@ -448,8 +505,9 @@ def test_vxm_adjacent_transforms_vs_oracle(ne):
                                           ((40, 9, 21), 3, [2, 2, 3]), ((5, 33, 17), 2, 2), ((6, 7, 9), 1, [2, 2, 0.6]),
                                           ((33, 18, 20), 4, [0.5, 1.3, 2.1])])
 def test_resize_upsampling_vs_oracle(ne, monkeypatch, shape, C, zoom):
-    """up-sampling (and mixed) shapes through the TMA-staged tile kernels (packed two-voxel: default, even and odd output widths; one-voxel), the
-    one-voxel z-marching kernel (global loads) and the generic kernel: -0.0 / rounding identical"""
+    """up-sampling (and mixed) shapes through the TMA-staged tile kernels (voxel-pair kernel: default, even and odd
+    output widths, and its global-memory path; the first packed kernel; one voxel per thread), the one-voxel
+    z-marching kernel (global loads) and the generic kernel: -0.0 / rounding identical"""
     rng = np.random.default_rng(51)
     x = rng.standard_normal((2,) + shape + (C,)).astype(F32)
     x[0, 0, 0, :2] = 0.0                                     # exact zeros: the packed a*b = fma(a, b, -0) must keep their sign
@@ -458,6 +516,15 @@ def test_resize_upsampling_vs_oracle(ne, monkeypatch, shape, C, zoom):
     out = ne.layers.Resize(zoom)(dev(x))
     np.testing.assert_array_equal(out.cpu().numpy(), ref)
     np.testing.assert_array_equal(np.signbit(out.cpu().numpy()), np.signbit(ref))
+    monkeypatch.setenv('NRT_RESIZE_UNSTAGED', '1')            # -> pair kernel, every CTA on its global-memory path
+    out = ne.layers.Resize(zoom)(dev(x)).cpu().numpy()
+    np.testing.assert_array_equal(out, ref)
+    np.testing.assert_array_equal(np.signbit(out), np.signbit(ref))
+    monkeypatch.delenv('NRT_RESIZE_UNSTAGED')
+    monkeypatch.setenv('NRT_RESIZE_TILE_X2', '1')             # -> the first packed kernel (generic loads, lo/hi copies)
+    out = ne.layers.Resize(zoom)(dev(x)).cpu().numpy()
+    np.testing.assert_array_equal(out, ref)
+    np.testing.assert_array_equal(np.signbit(out), np.signbit(ref))
     monkeypatch.setenv('NRT_RESIZE_TILE_X2', '0')             # -> staged source, one voxel per thread
     np.testing.assert_array_equal(ne.layers.Resize(zoom)(dev(x)).cpu().numpy(), ref)
     monkeypatch.setenv('NRT_RESIZE_TILE', '0')                # -> one-voxel z-marching kernel (global loads)
