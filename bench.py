@@ -462,7 +462,8 @@ def run_ops(args, world, rank, local, dev):
     ops = {}
     for name, fn in (('dice', lambda: dice_record(args, world, rank, dev, cce=False)),
                      ('cce', lambda: dice_record(args, world, rank, dev, cce=True)),
-                     ('lc3d', lambda: lc3d_record(args, world, rank, dev)),
+                     ('lc3d', lambda: lc3d_record(args, world, rank, dev, batch=1)),
+                     ('lc3d_b8', lambda: lc3d_record(args, world, rank, dev, batch=8, cpu=False)),
                      ('resize', lambda: resize_record(args, world, rank, dev)),
                      ('warp_c16', lambda: warp_mc_record(args, world, rank, dev, 16))):
         try:
@@ -470,7 +471,7 @@ def run_ops(args, world, rank, local, dev):
             ops[name] = {'workload': r['config']['workload'], 'metric': r['metric'], 'value': r['value'], 'unit': r['unit'],
                          'steps': r['steps'], 'ms_per_step': r['ms_per_step'],
                          'roofline': {k: r['roofline'][k] for k in ('achieved', 'peak', 'frac', 'bytes_model', 'traffic', 'traffic_source')},
-                         'gpu_launches': r['gpu_launches'], 'cpu_baseline': r.get('cpu_baseline')}
+                         'gpu_launches': r['gpu_launches'], 'clocks': r.get('clocks'), 'cpu_baseline': r.get('cpu_baseline')}
         except Exception as ex:                              # noqa: BLE001 -- one op must not take the headline down
             ops[name] = {'error': '%s: %s' % (type(ex).__name__, str(ex)[:300])}
         import torch
@@ -532,12 +533,12 @@ def dice_record(args, world, rank, dev, cce=False):
     return line
 
 
-def lc3d_record(args, world, rank, dev):
+def lc3d_record(args, world, rank, dev, batch=None, cpu=True):
     import numpy as np
     import torch
     from neurite_b200.layers import local_conv3d
-    B = args.lc_batch
-    steps = max(args.steps, OPS_STEPS) if B == 1 else max(args.steps, 20)
+    B = batch or args.lc_batch
+    steps = max(args.steps, OPS_STEPS)
     I, Cin, Cout = 64, 16, 16
     O = I - 2
     P, F = O ** 3, 27 * Cin
@@ -554,11 +555,12 @@ def lc3d_record(args, world, rank, dev):
                      'BASELINE.json configs[3]: LocallyConnected3D 3x3x3, 16->16, input [%d,64,64,64,16], kernel '
                      '[238328,432,16] = 6.59 GB streamed once per step (> L2)' % B)
     line['roofline'] = roofline(4.0 * (P * F * Cout + B * I ** 3 * Cin + B * P * Cout + P * Cout), ms / steps,
-                                'lc3d' if B == 1 else 'lc3d_b8', '4*(P*F*Cout + B*in + B*P*Cout + P*Cout)', 'lc3d_stream_kernel')
+                                'lc3d' if B == 1 else ('lc3d_b8' if B == 8 else None), '4*(P*F*Cout + B*in + B*P*Cout + P*Cout)',
+                                'lc3d_rows_kernel<4,2>' if B >= 8 else 'lc3d_patch_kernel')
     line['gpu_launches'] = steps
     line['clocks'] = clocks
     del x, kernel, bias
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and cpu and not args.no_cpu_baseline:
         cport = cpu_setup()
         Is = 26                                              # 24^3 positions: 0.38 GB of weights, streamed once per run
         Os = Is - 2

@@ -302,25 +302,10 @@ resize3d_kernel(const float* __restrict__ vol, float* __restrict__ out, ResizeGe
 // A tile whose box would not fit the staged extents (cannot happen when host and device agree) or a zoom whose
 // boxes are larger than the budget (down-sampling) takes resize3d_kernel.
 // ---------------------------------------------------------------------------------------
-// packed fp32x2 arithmetic (FFMA2 issues at the scalar FFMA rate on sm_100: two results per issue slot).
-// Bit-exactness: ptxas fuses mul.f32x2 + add.f32x2 into one FFMA2 (single rounding) even with fmad=false, so the
-// reference's separately rounded ops are written as  a*b = fma(a, b, -0)  and  a+b = fma(a, 1, b)  with the identity
-// operands (-0,-0) and (1,1) passed as kernel PARAMETERS (visible constants are folded and re-fused).
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float a, float b) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-
+// packed fp32x2 arithmetic (pack2 / fma2 in nrt_interp.cuh; FFMA2 issues at the scalar FFMA rate on sm_100: two results
+// per issue slot).  Bit-exactness: ptxas fuses mul.f32x2 + add.f32x2 into one FFMA2 (single rounding) even with
+// fmad=false, so the reference's separately rounded ops are written as  a*b = fma(a, b, -0)  and  a+b = fma(a, 1, b)
+// with the identity operands (-0,-0) and (1,1) passed as kernel PARAMETERS (visible constants are folded and re-fused).
 struct ResizeBox { int bz, by, bx; };            // staged source extents (bx already padded for the TMA alignment)
 
 template <int CT, int TZ>
@@ -1125,7 +1110,9 @@ warp3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol,
   // speculative box is useless; the box is then re-staged around the displaced position, so that the halo only has
   // to cover the variation of the flow inside the tile.  An incoherent flow averages out and keeps the box.
   // (Measured, profiles/: every warp doing this redundantly costs 12 % on the BASELINE workload -- 8 x 60
-  // instructions per tile are ~9 % of the tile's instruction count -- one warp + one block barrier costs ~1 %.)
+  // instructions per tile are ~9 % of the tile's instruction count -- one warp + one block barrier costs 2-2.6 %.
+  // Handing the decision over through a third mbarrier instead of the block barrier, so that warps 1-7 never wait for
+  // the flow tile, measured the same: 0.2220 vs 0.2177 ms with following off, same box.)
   int sz = 0, sy = 0, sx = 0;
   if (follow) {                                      // launch-uniform
     if (threadIdx.x < 32) {

@@ -216,6 +216,25 @@ struct BoxBounds { int lo_z, hi_z, lo_y, hi_y, lo_x, hi_x; };
 // last_stride_elems != 0: element stride of the LAST dimension (batch items not densely packed; multiple of 4)
 int encode_f32_tiled(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint32_t* box,
                      uint64_t last_stride_elems = 0);
+// packed fp32x2 arithmetic: two results per issue slot (fma.rn.f32x2).  The reference's separately rounded products and
+// sums are written as a*b = fma(a, b, -0) and a+b = fma(a, 1, b), identity operands passed as kernel parameters
+// (see nrt_interp.cu, resize3d kernels, for why).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+
 int env_int(const char* name, int dflt);
 
 // multi-channel D = 3 warp through the z-marching ring kernel (nrt_warp_march.cu); *used = false when not covered

@@ -109,17 +109,21 @@ def test_warp_march_kernel_multichannel_bit_exact(ne, monkeypatch, C, shape, amp
     flow = rng.uniform(-amp, amp, (2,) + shape + (3,)).astype(F32)
     flow[1] += np.array([1.2, -0.7, 2.1], dtype=F32)
     flow[0, 0, 0, :3] = [[0, 0, 0], [-40, 50, 3], [0.5, 1.5, -0.5]]
+    vol[1, 2:5, 3:7] = 0.0                                   # exact zeros of either sign: the packed a*b = fma(a, b, -0)
+    vol[1, 3, 4:6] = -0.0                                    # must give the scalar chain's sign of zero
     dv, df = dev(vol), dev(flow)
     for method, fill in (('linear', None), ('linear', -1.5), ('nearest', 0.0)):
         ref = ointerp.spatial_transformer(vol, flow, method, 'ij', fill)
         lay = ne.layers.SpatialTransformer(interp_method=method, fill_value=fill)
-        for env in ({}, {'NRT_MARCH_NW': '8', 'NRT_MARCH_QPT': '1'}, {'NRT_MARCH_NSEG': '3'}, {'NRT_MARCH_GROUPS': '1'},
+        for env in ({}, {'NRT_MARCH_NW': '8', 'NRT_MARCH_QPT': '1'}, {'NRT_MARCH_NSEG': '3'}, {'NRT_MARCH_GROUPS': '2'},
                     {'NRT_MARCH_QPT': '4'}, {'NRT_MARCH_NSEG': '40'}):
             for k in ('NRT_MARCH_NW', 'NRT_MARCH_NSEG', 'NRT_MARCH_QPT', 'NRT_MARCH_GROUPS'):
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
-            np.testing.assert_array_equal(lay([dv, df]).cpu().numpy(), ref)
+            out = lay([dv, df]).cpu().numpy()
+            np.testing.assert_array_equal(out, ref)
+            np.testing.assert_array_equal(np.signbit(out), np.signbit(ref))
 
 
 def test_warp_box_follows_smooth_flow(ne, monkeypatch):
