@@ -236,8 +236,11 @@ _CPU_READY = False
 
 def cpu_setup(orig_affinity=None):
     """One recipe for BOTH CPU legs (cpu_baseline of our arm and --impl reference): threads bound to cores
-    (OMP_PROC_BIND=close, OMP_PLACES=cores -- must be in the environment before libgomp starts), every core of
-    the box, inputs first-touched by the OpenMP threads, the MEDIAN of >= 20 runs reported."""
+    (OMP_PROC_BIND=close, OMP_PLACES=cores -- must be in the environment before libgomp starts), as many threads as
+    the box gives this container -- min(cores in the affinity mask, cgroup CPU quota): the GPU boxes show 128 cores
+    but cap the container at 16 CPUs per 100 ms period, and 128 runnable threads get the whole group throttled for
+    the rest of a period (tools/cpu_leg_probe.py: 4.5 ms best, 94 ms median with 128 threads; 20.4-20.8 ms min-max
+    with 16) -- inputs first-touched by the OpenMP threads, the MEDIAN of >= 20 runs reported."""
     global _CPU_READY
     if orig_affinity:
         try:
@@ -247,7 +250,8 @@ def cpu_setup(orig_affinity=None):
     if not _CPU_READY:
         os.environ.setdefault('OMP_PROC_BIND', 'close')
         os.environ.setdefault('OMP_PLACES', 'cores')
-        os.environ.setdefault('OMP_WAIT_POLICY', 'active')
+        # passive: idle OpenMP threads must not keep spinning into the container's CPU quota while the GPU legs run
+        os.environ.setdefault('OMP_WAIT_POLICY', 'passive')
         from oracle import cport
         cport.build()
         cport.use_all_cores()
@@ -272,6 +276,7 @@ def cpu_record(fn, units, unit, what, budget_s=6.0, min_runs=20):
     cport = cpu_setup()
     med, n, best = median_time(fn, budget_s, min_runs)
     return {'value': units / med, 'unit': unit, 'cores': cport.num_threads(), 'kind': 'port',
+            'cgroup_cpu_limit': cport.cgroup_cpu_limit(),
             'sample': '%s; median of %d runs (best %.3g %s), threads bound (OMP_PROC_BIND=close, OMP_PLACES=cores), '
                       'inputs first-touched by the OpenMP threads' % (what, n, units / best, unit)}
 
@@ -362,7 +367,7 @@ def bench_reference(args):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': warp_config(args, world),
         'cpu_baseline': {'value': value, 'unit': 'voxels/s', 'cores': cport.num_threads(), 'kind': 'port',
-                         'sample': sample},
+                         'cgroup_cpu_limit': cport.cgroup_cpu_limit(), 'sample': sample},
         'e2e': {'value': value, 'unit': 'voxels/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }), flush=True)
@@ -515,7 +520,7 @@ def dice_record(args, world, rank, dev, cce=False):
                      'BASELINE.json configs[2]: %s, y_true one-hot / y_pred softmax [4,160,192,224,16], voxel range sharded '
                      'over %d GPU(s) + all-reduce of [4,16,3] partial sums' % (name, world), {'l2': '3.5 GB read per step > L2'})
     line['roofline'] = roofline(8.0 * (B * nz * SHAPE[1] * SHAPE[2] * L), ms / steps, 'cce' if cce else 'dice',
-                                '8 B per (voxel,label)', 'cce_vec4_kernel' if cce else 'dice_sums_vec4_kernel')
+                                '8 B per (voxel,label)', 'cce_vec4u_kernel<4,4>' if cce else 'dice_sums_vec4_kernel')
     line['gpu_launches'] = steps * (2 if cce else 3)
     line['clocks'] = clocks
     del t, p, lab

@@ -607,6 +607,9 @@ resize3d_tile_x2_kernel(const __grid_constant__ CUtensorMap tm_vol, const float*
 //     monotonic: no loop over the table, no second block barrier) and issues the TMA load while the other threads
 //     build the tables; no dynamically indexed kernel parameters (they cost a 128-byte local-memory copy per thread).
 // Same arithmetic, same rounding order as resize3d_tile_x2_kernel (bit-exact with the oracle).
+// Tried on top and dropped (profiles/README.md): a persistent CTA with two box buffers that prefetches the next tile's
+// box (the wait for the box is 16.5 % of the warp samples here).  Correct, but the extra loop state does not fit the
+// 128 registers that 2 CTAs per SM allow: spill reloads inside the plane loop, 0.247 ms against 0.166.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ Axis resize_axis(int S, int M, float delta, int i) {
   // tf.linspace(0, S-1, M): endpoints exact, interior 0 + delta*i  (utils.py:259)
@@ -1759,7 +1762,7 @@ int nrt_resize_f32(const float* vol, float* out, int B, const int32_t* in_shape,
         const bool minb3 = env_int("NRT_RESIZE_MINB", 1) == 3;        // registers capped for 3 CTAs per SM (experiment)
 #define NRT_RESIZE_TILE(CT, TZZ)                                                                                          \
         do {                                                                                                              \
-          if (x2 && x2mode >= 2) {                                                                                        \
+          if (x2 && x2mode >= 2) {                                                                                 \
             auto kern = resize3d_pair_kernel<CT, TZZ>;                                                                    \
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)        \
               return check_launch("cudaFuncSetAttribute(resize3d_pair)");                                                 \

@@ -170,8 +170,8 @@ dice_label_counts_kernel(const int32_t* __restrict__ t, const int32_t* __restric
 }
 
 // combine block partials [b][blk][kind][l] -> sums [b][l][kind], fp64, fixed order
-__global__ void dice_combine_kernel(const float* __restrict__ partial, int nblk, int L,
-                                    float* __restrict__ sums) {
+__global__ void dice_combine_serial_kernel(const float* __restrict__ partial, int nblk, int L,
+                                           float* __restrict__ sums) {
   const int b = blockIdx.x;
   for (int o = threadIdx.x; o < 3 * L; o += blockDim.x) {
     double s = 0.0;
@@ -179,6 +179,40 @@ __global__ void dice_combine_kernel(const float* __restrict__ partial, int nblk,
     const int kind = o / L, l = o - kind * L;
     sums[((int64_t)b * L + l) * 3 + kind] = (float)s;
   }
+}
+
+// The same in two levels (3L <= blockDim): the serial kernel's 48 threads each walk all ~300 block partials, a 37 us
+// tail behind a 507 us streaming kernel (profiles/r02_launches_bench.csv).  Here slice s of blockDim / 3L slices sums
+// blocks s, s + nslice, ... (consecutive threads read consecutive outputs: coalesced), then one thread per output adds
+// the slices in order.  fp64, fixed order.
+__global__ void dice_combine_kernel(const float* __restrict__ partial, int nblk, int L,
+                                    float* __restrict__ sums) {
+  extern __shared__ double s_part[];                   // [nslice][3L]
+  const int b = blockIdx.x, n3 = 3 * L;
+  const int nslice = blockDim.x / n3;
+  const int slice = threadIdx.x / n3, o = threadIdx.x - slice * n3;
+  if (slice < nslice) {
+    double s = 0.0;
+    for (int k = slice; k < nblk; k += nslice) s += (double)partial[((int64_t)b * nblk + k) * n3 + o];
+    s_part[slice * n3 + o] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < n3) {
+    double s = 0.0;
+    for (int sl = 0; sl < nslice; ++sl) s += s_part[sl * n3 + threadIdx.x];
+    const int kind = threadIdx.x / L, l = threadIdx.x - kind * L;
+    sums[((int64_t)b * L + l) * 3 + kind] = (float)s;
+  }
+}
+
+static int launch_dice_combine(const float* partial, int nblk, int B, int L, float* sums, cudaStream_t st) {
+  if (3 * L <= 1024) {
+    const int nslice = 1024 / (3 * L);
+    dice_combine_kernel<<<B, 1024, (size_t)nslice * 3 * L * sizeof(double), st>>>(partial, nblk, L, sums);
+  } else {
+    dice_combine_serial_kernel<<<B, 128, 0, st>>>(partial, nblk, L, sums);
+  }
+  return check_launch("dice_combine_kernel");
 }
 
 __global__ void dice_finalize_kernel(const float* __restrict__ sums, int n, float eps,
@@ -207,6 +241,7 @@ argmax_kernel(const float* __restrict__ x, int64_t n, int L, int32_t* __restrict
 // ---------------------------------------------------------------------------------------
 // categorical cross-entropy
 // ---------------------------------------------------------------------------------------
+constexpr int kCceUnrollDefault = 4;       // NRT_CCE_UNROLL default (see nrt_cce_f32)
 struct CceArgs {
   const float* label_w;
   const float* sample_w;
@@ -269,6 +304,83 @@ cce_vec4_kernel(const float4* __restrict__ t4, const float4* __restrict__ p4, Cc
       if (a.sample_w) l *= __ldg(a.sample_w + r);
       if (a.per_elem) a.per_elem[r] = l;
       acc += l;
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) s_red[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int i = 0; i < kThreads / 32; ++i) s += s_red[i];
+    partial[blockIdx.x] = s;
+  }
+}
+
+// The same with Q = C/4 lanes per row at compile time (the group shuffles unroll: no loop counters, no branches) and
+// U rows per thread and pass, i.e. U independent pairs of streaming loads in flight per thread.  cce_vec4_kernel
+// (profiles/r02_ncu_full_cce.txt) runs one load pair per thread and waits 8.6 long-scoreboard cycles per issue at 74 %
+// issue-active with half of its instructions on the ALU pipe (the run-time shuffle loops).
+template <int Q>
+__device__ __forceinline__ float group_sum_c(float v) {
+#pragma unroll
+  for (int o = Q >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int Q>
+__device__ __forceinline__ float group_max_c(float v) {
+#pragma unroll
+  for (int o = Q >> 1; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <int Q, int U>
+__global__ void __launch_bounds__(kThreads)
+cce_vec4u_kernel(const float4* __restrict__ t4, const float4* __restrict__ p4, CceArgs a, float* __restrict__ partial) {
+  __shared__ float s_red[kThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int sub = lane & (Q - 1);
+  constexpr int RPP = kThreads / Q;                      // rows per pass and sub-step
+  float4 lw = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (a.label_w) lw = __ldg(reinterpret_cast<const float4*>(a.label_w) + sub);
+  const float eps = 1e-7f, one_m_eps = __fsub_rn(1.0f, 1e-7f);
+  const float sm_keep = __fsub_rn(1.0f, a.smoothing), sm_add = __fdiv_rn(a.smoothing, (float)a.C);
+  float acc = 0.f;
+  // block-uniform trip count: the group shuffles need every lane of the warp present
+  for (int64_t r0 = (int64_t)blockIdx.x * (RPP * U); r0 < a.n; r0 += (int64_t)gridDim.x * (RPP * U)) {
+    float4 t[U], p[U];
+    int64_t r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      r[u] = r0 + u * RPP + tid / Q;
+      t[u] = make_float4(0.f, 0.f, 0.f, 0.f); p[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (r[u] < a.n) { t[u] = ld_stream_f4(t4 + r[u] * Q + sub); p[u] = ld_stream_f4(p4 + r[u] * Q + sub); }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float4 tt = t[u];
+      const float4 pp = p[u];
+      tt.x *= lw.x; tt.y *= lw.y; tt.z *= lw.z; tt.w *= lw.w;                   // metrics.py:648
+      if (a.smoothing != 0.f) {
+        tt.x = tt.x * sm_keep + sm_add; tt.y = tt.y * sm_keep + sm_add; tt.z = tt.z * sm_keep + sm_add; tt.w = tt.w * sm_keep + sm_add;
+      }
+      float l;
+      if (!a.from_logits) {
+        const float rs = __frcp_rn(group_sum_c<Q>((pp.x + pp.y) + (pp.z + pp.w)));
+        const float a0 = fminf(fmaxf(pp.x * rs, eps), one_m_eps), a1 = fminf(fmaxf(pp.y * rs, eps), one_m_eps);
+        const float a2 = fminf(fmaxf(pp.z * rs, eps), one_m_eps), a3 = fminf(fmaxf(pp.w * rs, eps), one_m_eps);
+        l = (tt.x * __logf(a0) + tt.y * __logf(a1)) + (tt.z * __logf(a2) + tt.w * __logf(a3));
+      } else {
+        const float m = group_max_c<Q>(fmaxf(fmaxf(pp.x, pp.y), fmaxf(pp.z, pp.w)));
+        const float z0 = pp.x - m, z1 = pp.y - m, z2 = pp.z - m, z3 = pp.w - m;
+        const float lse = logf(group_sum_c<Q>((expf(z0) + expf(z1)) + (expf(z2) + expf(z3))));
+        l = (tt.x * (z0 - lse) + tt.y * (z1 - lse)) + (tt.z * (z2 - lse) + tt.w * (z3 - lse));
+      }
+      l = -group_sum_c<Q>(l);
+      if (sub == 0 && r[u] < a.n) {
+        if (a.sample_w) l *= __ldg(a.sample_w + r[u]);
+        if (a.per_elem) a.per_elem[r[u]] = l;
+        acc += l;
+      }
     }
   }
   acc = warp_sum(acc);
@@ -405,8 +517,7 @@ int nrt_dice_sums_f32(const float* y_true, const float* y_pred, int B, int64_t V
   }
   int rc = check_launch("dice_sums kernel");
   if (rc != NRT_OK) return rc;
-  dice_combine_kernel<<<B, 128, 0, st>>>(partial, nblk, L, sums);
-  return check_launch("dice_combine_kernel");
+  return launch_dice_combine(partial, nblk, B, L, sums, st);
 }
 
 int nrt_dice_label_sums_i32(const int32_t* t_lab, const int32_t* p_lab, int B, int64_t V, int L, int64_t v0,
@@ -423,8 +534,7 @@ int nrt_dice_label_sums_i32(const int32_t* t_lab, const int32_t* p_lab, int B, i
   dice_label_counts_kernel<<<grid, kThreads, 3 * L * sizeof(int), st>>>(t_lab, p_lab, V, v0, nv, L, partial);
   int rc = check_launch("dice_label_counts_kernel");
   if (rc != NRT_OK) return rc;
-  dice_combine_kernel<<<B, 128, 0, st>>>(partial, nblk, L, sums);
-  return check_launch("dice_combine_kernel");
+  return launch_dice_combine(partial, nblk, B, L, sums, st);
 }
 
 int nrt_argmax_f32(const float* x, int64_t n, int L, int32_t* idx, void* stream) {
@@ -463,7 +573,29 @@ int nrt_cce_f32(const float* y_true, const float* y_pred, const float* label_w, 
     cudaMemsetAsync(sum_out, 0, sizeof(float), st);
     return check_launch("cce memset");
   }
-  if (vec_ok) {
+  // NRT_CCE_UNROLL: rows per thread and pass in the compile-time-Q kernel (default 2; 0 = the run-time-q kernel)
+  const char* ue = getenv("NRT_CCE_UNROLL");
+  const int unroll = ue && *ue ? atoi(ue) : kCceUnrollDefault;
+  if (vec_ok && (unroll == 2 || unroll == 4)) {
+    const int rows_per_pass = kThreads / q * unroll;
+    grid = (int)imin64((n + rows_per_pass - 1) / rows_per_pass, (int64_t)min(kMaxBlocks * 4, sm_count() * 8));
+    const float4* t4 = reinterpret_cast<const float4*>(y_true);
+    const float4* p4 = reinterpret_cast<const float4*>(y_pred);
+#define NRT_CCE_Q(QQ)                                                                                   \
+    do {                                                                                                \
+      if (unroll == 2) cce_vec4u_kernel<QQ, 2><<<grid, kThreads, 0, st>>>(t4, p4, a, partial);          \
+      else cce_vec4u_kernel<QQ, 4><<<grid, kThreads, 0, st>>>(t4, p4, a, partial);                      \
+    } while (0)
+    switch (q) {
+      case 1: NRT_CCE_Q(1); break;
+      case 2: NRT_CCE_Q(2); break;
+      case 4: NRT_CCE_Q(4); break;
+      case 8: NRT_CCE_Q(8); break;
+      case 16: NRT_CCE_Q(16); break;
+      default: NRT_CCE_Q(32); break;
+    }
+#undef NRT_CCE_Q
+  } else if (vec_ok) {
     const int rows_per_pass = kThreads / q;
     grid = (int)imin64((n + rows_per_pass - 1) / rows_per_pass, (int64_t)min(kMaxBlocks * 4, sm_count() * 8));
     cce_vec4_kernel<<<grid, kThreads, 0, st>>>(reinterpret_cast<const float4*>(y_true),

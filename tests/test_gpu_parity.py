@@ -219,6 +219,10 @@ def test_resize_full_size_and_slabs(ne):
     assert tuple(out.shape) == (1, 160, 192, 224, 3)
     ref = ointerp.resize_layer(x, 2)
     np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    x3 = dev(np.concatenate([x, x[:, ::-1].copy(), x * 0.5], 0))
+    out3 = ne.layers.Resize(2)(x3)
+    assert torch.equal(out3[0], out[0]) and torch.equal(out3[2], ne.layers.Resize(2)(x3[2:3])[0])
+    np.testing.assert_array_equal(out3[1].cpu().numpy(), ointerp.resize_layer(x[:, ::-1], 2)[0])
     a = utils._resize_batched(dev(x), [2, 2, 2], 'linear', out_z0=0, out_n0=70)
     b = utils._resize_batched(dev(x), [2, 2, 2], 'linear', out_z0=70, out_n0=90)
     assert torch.equal(torch.cat([a, b], 1), out)
@@ -299,10 +303,14 @@ def test_cce_golden(ne, name):
     np.testing.assert_allclose(float(c.loss(dev(g['y_true']), dev(g['y_pred']))), g['loss'], rtol=1e-5)
 
 
-def test_cce_variants_vs_oracle(ne):
+@pytest.mark.parametrize('unroll', ['0', '2', '4'])
+def test_cce_variants_vs_oracle(ne, monkeypatch, unroll):
+    """run-time-q kernel (0) and the compile-time-Q kernels with 2 / 4 rows per thread; 2 x 37 x 41 rows: ragged
+    last pass of every variant"""
+    monkeypatch.setenv('NRT_CCE_UNROLL', unroll)
     rng = np.random.default_rng(11)
-    for C in (2, 3, 4, 5, 16, 32, 128):
-        t = np.eye(C, dtype=F32)[rng.integers(0, C, (2, 6, 7))]
+    for C in (2, 3, 4, 5, 8, 16, 32, 64, 128):
+        t = np.eye(C, dtype=F32)[rng.integers(0, C, (2, 37, 41) if C in (4, 16) else (2, 6, 7))]
         p = rng.uniform(0.01, 1, t.shape).astype(F32)
         lw = rng.uniform(0.5, 2, C).astype(F32)
         sw = rng.uniform(0.5, 2, t.shape[:-1]).astype(F32)
