@@ -29,6 +29,43 @@ def test_reference_arm_prints_one_json_line():
     assert '160x192x224' in d['metric'] and d['config']['volume'] == [160, 192, 224]
 
 
+def test_cpu_legs_respect_the_container_cpu_quota(monkeypatch, tmp_path):
+    """the GPU boxes show 128 cores but give the container 16 CPUs per period (cgroup v2 cpu.max): the CPU legs must not
+    start more runnable threads than that (they get throttled into a bimodal timing); v1 files and 'max' are understood"""
+    import builtins
+    from oracle import cport
+    real_open = builtins.open
+    files = {}
+
+    def fake_open(path, *a, **k):
+        if isinstance(path, str) and path.startswith('/sys/fs/cgroup/'):
+            if path not in files:
+                raise FileNotFoundError(path)
+            f = tmp_path / path.strip('/').replace('/', '_')
+            f.write_text(files[path])
+            return real_open(f, *a, **k)
+        return real_open(path, *a, **k)
+
+    monkeypatch.setattr(builtins, 'open', fake_open)
+    files['/sys/fs/cgroup/cpu.max'] = '1600000 100000\n'
+    assert cport.cgroup_cpu_limit() == 16.0
+    monkeypatch.setattr(os, 'sched_getaffinity', lambda pid: set(range(128)))
+    before = cport.num_threads()
+    try:
+        assert cport.use_all_cores() == 16
+        files['/sys/fs/cgroup/cpu.max'] = 'max 100000\n'
+        assert cport.cgroup_cpu_limit() is None
+        del files['/sys/fs/cgroup/cpu.max']
+        files['/sys/fs/cgroup/cpu/cpu.cfs_quota_us'] = '-1\n'
+        files['/sys/fs/cgroup/cpu/cpu.cfs_period_us'] = '100000\n'
+        assert cport.cgroup_cpu_limit() is None
+        files['/sys/fs/cgroup/cpu/cpu.cfs_quota_us'] = '250000\n'
+        assert cport.cgroup_cpu_limit() == 2.5
+        assert cport.use_all_cores() == 2
+    finally:
+        cport.set_num_threads(before)
+
+
 def test_bounded_cpu_baseline_timers():
     import bench
     from oracle import cport
