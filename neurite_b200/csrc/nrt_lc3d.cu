@@ -369,6 +369,10 @@ lc3d_patch_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restr
 // chunk of lane l ^ 2d: one shuffle per set and value sends every chunk to its owner.
 // Same ring, barriers and TMA patch load as lc3d_patch_kernel.  Summation order differs from the other kernels
 // (rows are summed lane-wise first): results agree to fp32 rounding, not bit for bit.
+// Measured on B200 at cfg 4, batch 8 (profiles/README.md): <4,2> (two warps x four items per position) 1.354-1.417 ms =
+// 0.74-0.77 of the HBM roofline, power-capped at 1695-1785 MHz (1.224 ms in a single launch under ncu); <8,1> 1.653 ms
+// (255 registers, 4-5 consumer warps); lc3d_patch_kernel<2,4> on the same box 1.814 ms.  Batch 4: <4,1> 1.323 ms vs
+// 1.232 ms for lc3d_patch_kernel<2,2>, which therefore keeps the passes of four.
 // ---------------------------------------------------------------------------------------
 template <int N>
 __device__ __forceinline__ void fold_upper(float* v, int mask) {      // v[0 .. N/2) += partner's v[N/2 .. N)
