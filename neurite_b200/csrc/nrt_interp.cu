@@ -446,167 +446,20 @@ resize3d_tile_kernel(const __grid_constant__ CUtensorMap tm_vol, const float* __
   }
 }
 
-// resize3d_tile_x2_kernel: staged source box (as above) + TWO x positions per thread: the two voxels of a thread form
-// the halves of packed fp32x2 registers.  With the load latency gone the staged kernel is issue-bound (87 % issue-active, 134
-// instructions per voxel at C = 3, profiles/r02_ncu_full_resize_tile.txt); here the 60 separately rounded multiplies
-// / adds of a voxel are shared by a voxel pair and so are the table reads, addresses and the loop.
-template <int CT, int TZ, int MINB = 1>
-__global__ void __launch_bounds__(256, MINB)
-resize3d_tile_x2_kernel(const __grid_constant__ CUtensorMap tm_vol, const float* __restrict__ vol, float* __restrict__ out,
-                        ResizeGeo w, ResizeBox bxs, int ntz, int nty, int ntx, int xalign, f32x2 negzero2, f32x2 one2) {
-  constexpr int TY = 16, TX = 32;                      // a warp = two rows of 16 x-pairs
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* s_box = reinterpret_cast<float*>(smem_raw);                                     // [bz][by][bx][CT]
-  const int box_elems = bxs.bz * bxs.by * bxs.bx * CT;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)box_elems * 4 + 15) & ~(size_t)15));
-  int* s_lo = reinterpret_cast<int*>(bar + 1);
-  __shared__ float2 s_w[TZ + TY + TX];                                                   // (wlo, whi) per table entry
-  __shared__ int s_i[2][TZ + TY + TX];                                                   // i0 / i1 per table entry
-  const Geo& g = w.g;
-  int tile = blockIdx.x;
-  const int tx = tile % ntx; tile /= ntx;
-  const int ty = tile % nty; tile /= nty;
-  const int tz = tile % ntz;
-  const int b = tile / ntz;
-  const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;
-  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
-  if (threadIdx.x < TZ + TY + TX) {
-    const int t = threadIdx.x;
-    const int d = t < TZ ? 0 : (t < TZ + TY ? 1 : 2);
-    const int i = d == 0 ? w.out_z0 + z0 + t : (d == 1 ? y0 + (t - TZ) : x0 + (t - TZ - TY));
-    float2 ww = make_float2(0.f, 0.f);
-    int i0 = -1, i1 = -1;
-    if (i < w.M[d] && (d != 0 || z0 + t < w.out_n0)) {
-      const float loc = (i == w.M[d] - 1 && w.M[d] > 1) ? (float)(g.S[d] - 1) : __fmul_rn(w.delta[d], (float)i);
-      const Axis a = axis_linear(loc, (float)(g.S[d] - 1), g.S[d] - 1);
-      i0 = a.i0; i1 = a.i1; ww = make_float2(a.wlo, a.whi);
-    }
-    s_w[t] = ww; s_i[0][t] = i0; s_i[1][t] = i1;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int lo[3], ok = 1;
-    const int first[3] = {0, TZ, TZ + TY}, count[3] = {TZ, TY, TX}, ext[3] = {bxs.bz, bxs.by, bxs.bx};
-    for (int d = 0; d < 3; ++d) {
-      lo[d] = s_i[0][first[d]];
-      if (d == 2) lo[d] -= lo[d] % xalign;
-      int hi = lo[d];
-      for (int k = 0; k < count[d]; ++k) hi = max(hi, s_i[1][first[d] + k]);
-      ok &= (hi - lo[d] + 1 <= ext[d]);
-    }
-    s_lo[0] = lo[0]; s_lo[1] = lo[1]; s_lo[2] = lo[2]; s_lo[3] = ok;
-    if (ok) {
-      mbar_expect_tx(bar, (uint32_t)(box_elems * sizeof(float)));
-      tma_load_4d(s_box, &tm_vol, bar, lo[2] * CT, lo[1], lo[0], b);
-    }
-  }
-  __syncthreads();
-  const bool staged = s_lo[3] != 0;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int row = wid * 2 + (lane >> 4), xp = lane & 15;
-  const int ox = x0 + 2 * xp, oy = y0 + row;
-  const int sz_ = staged ? bxs.by * bxs.bx * CT : g.S[1] * g.S[2] * CT;
-  const int sy_ = staged ? bxs.bx * CT : g.S[2] * CT;
-  const int lz = staged ? s_lo[0] : 0, ly = staged ? s_lo[1] : 0, lx = staged ? s_lo[2] : 0;
-  if (staged) mbar_wait(bar, 0);
-  if (oy >= w.M[1] || ox >= w.M[2]) return;
-  const bool has1 = ox + 1 < w.M[2];                    // odd output width: the pair's second voxel may not exist
-  const int ta = TZ + TY + 2 * xp, tb = has1 ? ta + 1 : ta;     // (a missing second voxel repeats the first: legal reads)
-  const float2 wy = s_w[TZ + row], wa = s_w[ta], wb = s_w[tb];
-  const int y_o0 = (s_i[0][TZ + row] - ly) * sy_, y_o1 = (s_i[1][TZ + row] - ly) * sy_;
-  const int a_o0 = (s_i[0][ta] - lx) * CT, a_o1 = (s_i[1][ta] - lx) * CT;
-  const int b_o0 = (s_i[0][tb] - lx) * CT, b_o1 = (s_i[1][tb] - lx) * CT;
-  const float* src = staged ? s_box : vol + (size_t)b * w.src_batch_stride;
-  float* outb = out + ((size_t)b * w.out_vox + ((size_t)z0 * w.M[1] + oy) * w.M[2] + ox) * CT;
-  const size_t plane = (size_t)w.M[1] * w.M[2] * CT;
-  const float* qa[4] = {src + y_o0 + a_o0, src + y_o0 + a_o1, src + y_o1 + a_o0, src + y_o1 + a_o1};
-  const float* qb[4] = {src + y_o0 + b_o0, src + y_o0 + b_o1, src + y_o1 + b_o0, src + y_o1 + b_o1};
-  const f32x2 exlo = pack2(wa.x, wb.x), exhi = pack2(wa.y, wb.y);
-  const f32x2 zero2 = pack2(0.f, 0.f);
-  f32x2 lo[4][CT], hi[4][CT];
-  int cur0 = -1, cur1 = -1;
-#pragma unroll 1
-  for (int z = 0; z < TZ; ++z, outb += plane) {
-    if (z0 + z >= w.out_n0) break;
-    const float2 wz = s_w[z];
-    const int z_o0 = (s_i[0][z] - lz) * sz_, z_o1 = (s_i[1][z] - lz) * sz_;
-    if (z_o0 != cur0) {
-      if (z_o0 == cur1) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int c = 0; c < CT; ++c) lo[q][c] = hi[q][c];
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int c = 0; c < CT; ++c) lo[q][c] = pack2(qa[q][z_o0 + c], qb[q][z_o0 + c]);
-      }
-      cur0 = z_o0;
-    }
-    if (z_o1 != cur1) {
-      if (z_o1 == cur0) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int c = 0; c < CT; ++c) hi[q][c] = lo[q][c];
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int c = 0; c < CT; ++c) hi[q][c] = pack2(qa[q][z_o1 + c], qb[q][z_o1 + c]);
-      }
-      cur1 = z_o1;
-    }
-    const float w00 = __fmul_rn(wz.x, wy.x), w01 = __fmul_rn(wz.x, wy.y);
-    const float w10 = __fmul_rn(wz.y, wy.x), w11 = __fmul_rn(wz.y, wy.y);
-    const f32x2 p00 = pack2(w00, w00), p01 = pack2(w01, w01), p10 = pack2(w10, w10), p11 = pack2(w11, w11);
-    f32x2 k[8];
-    k[0] = fma2(p00, exlo, negzero2); k[1] = fma2(p00, exhi, negzero2);
-    k[2] = fma2(p01, exlo, negzero2); k[3] = fma2(p01, exhi, negzero2);
-    k[4] = fma2(p10, exlo, negzero2); k[5] = fma2(p10, exhi, negzero2);
-    k[6] = fma2(p11, exlo, negzero2); k[7] = fma2(p11, exhi, negzero2);
-    float ra[CT], rb[CT];
-#pragma unroll
-    for (int c = 0; c < CT; ++c) {
-      f32x2 r = fma2(fma2(k[0], lo[0][c], negzero2), one2, zero2);          // 0 + k0*v0
-#pragma unroll
-      for (int q = 1; q < 4; ++q) r = fma2(fma2(k[q], lo[q][c], negzero2), one2, r);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) r = fma2(fma2(k[4 + q], hi[q][c], negzero2), one2, r);
-      unpack2(r, ra[c], rb[c]);
-    }
-    if (!has1) {
-#pragma unroll
-      for (int c = 0; c < CT; ++c) outb[c] = ra[c];
-    } else if (CT == 1) {
-      *reinterpret_cast<float2*>(outb) = make_float2(ra[0], rb[0]);
-    } else if (CT == 2) {
-      *reinterpret_cast<float4*>(outb) = make_float4(ra[0], ra[1 % CT], rb[0], rb[1 % CT]);
-    } else if (CT == 3) {
-      *reinterpret_cast<float2*>(outb) = make_float2(ra[0], ra[1 % CT]);
-      *reinterpret_cast<float2*>(outb + 2) = make_float2(ra[2 % CT], rb[0]);
-      *reinterpret_cast<float2*>(outb + 4) = make_float2(rb[1 % CT], rb[2 % CT]);
-    } else {
-      *reinterpret_cast<float4*>(outb) = make_float4(ra[0], ra[1 % CT], ra[2 % CT], ra[3 % CT]);
-      *reinterpret_cast<float4*>(outb + 4) = make_float4(rb[0], rb[1 % CT], rb[2 % CT], rb[3 % CT]);
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------
-// resize3d_pair_kernel: the packed voxel-pair kernel again, with the three things its SASS and its capture
+// resize3d_pair_kernel: the packed voxel-pair kernel, second version: the three things the first version's SASS and capture
 // (profiles/r02_ncu_full_resize.txt: 83 instructions per voxel, issue-bound) showed to be overhead removed:
-//   * corner reads are LDS with 32-bit offsets and immediate channel offsets.  resize3d_tile_x2_kernel reads through
-//     a pointer that is shared OR global at run time, i.e. generic LD.E with 64-bit address arithmetic: 88
-//     instructions per 24 loads.  Here the marching loop is a template on the address space.
+//   * corner reads are LDS with 32-bit offsets and immediate channel offsets.  The first packed kernel (round 2,
+//     removed) read through a pointer that is shared OR global at run time, i.e. generic LD.E with 64-bit address
+//     arithmetic: 88 instructions per 24 loads.  Here the marching loop is a template on the address space.
 //   * the two source planes of a z cell live in two register sets tagged with the source plane they hold; entering
 //     the next cell loads ONE plane into the set that is free and swaps the roles of the sets (two copies of the
 //     arithmetic, selected by a CTA-uniform branch) instead of moving 24 registers from `hi` to `lo`.
 //   * prologue: one thread derives the box origin from the tile's first / last output per axis (the linspace is
 //     monotonic: no loop over the table, no second block barrier) and issues the TMA load while the other threads
 //     build the tables; no dynamically indexed kernel parameters (they cost a 128-byte local-memory copy per thread).
-// Same arithmetic, same rounding order as resize3d_tile_x2_kernel (bit-exact with the oracle).
+// Same arithmetic and rounding order as resize3d_tile_kernel (bit-exact with the oracle); two x positions per thread
+// are the halves of packed fp32x2 registers.
 // Tried on top and dropped (profiles/README.md): a persistent CTA with two box buffers that prefetches the next tile's
 // box (the wait for the box is 16.5 % of the warp samples here).  Correct, but the extra loop state does not fit the
 // 128 registers that 2 CTAs per SM allow: spill reloads inside the plane loop, 0.247 ms against 0.166.
@@ -1724,27 +1577,21 @@ int nrt_resize_f32(const float* vol, float* out, int B, const int32_t* in_shape,
     // up-sampling: source box of every output tile staged by TMA (resize3d_tile_kernel)
     if (method == NRT_LINEAR && C >= 1 && C <= 4 && env_int("NRT_RESIZE_TILE", 1) && aligned16(vol) &&
         (rg.g.S[2] * C) % 4 == 0 && ((C != 2 && C != 4) || (reinterpret_cast<uintptr_t>(out) & (C == 4 ? 15u : 7u)) == 0)) {
-      // NRT_RESIZE_TILE_X2: 2 = resize3d_pair_kernel (default), 1 = resize3d_tile_x2_kernel, 0 = one voxel per thread
-      const int x2mode = env_int("NRT_RESIZE_TILE_X2", 2);
-      // 64 planes per CTA (half the prologues and box waits) only in the pair kernel, which runs 2 CTAs per SM anyway
-      // and can afford a 100 KB box
-      const size_t box_budget = (x2mode >= 2 ? 100 : 72) * 1024;
       const int xalign = (C == 4) ? 1 : (C == 2 ? 2 : 4);
-      // packed two-voxel variants (16-row tiles): need an even row pitch / aligned output for their 64 / 128-bit stores
-      const bool x2 = x2mode != 0 && (rg.M[2] * C) % (C == 2 ? 4 : 2) == 0 &&
+      // voxel-pair kernel (16-row tiles; NRT_RESIZE_TILE_X2=0: one voxel per thread): needs an even row pitch / aligned
+      // output for its 64 / 128-bit stores.  It runs 2 CTAs per SM (registers) and can afford a 100 KB box.
+      const bool x2 = env_int("NRT_RESIZE_TILE_X2", 1) != 0 && (rg.M[2] * C) % (C == 2 ? 4 : 2) == 0 &&
                       (reinterpret_cast<uintptr_t>(out) & 15u) == 0 && (rg.out_vox * C) % 4 == 0;
+      const size_t box_budget = (x2 ? 100 : 72) * 1024;
       const int unstaged = env_int("NRT_RESIZE_UNSTAGED", 0);      // test hook: every CTA takes its global-memory path
       const int tyt = x2 ? 16 : 8;
       ResizeBox bxs;
       bxs.by = resize_axis_extent(rg.g.S[1], rg.M[1], rg.delta[1], 0, rg.M[1], tyt, 1);
       bxs.bx = resize_axis_extent(rg.g.S[2], rg.M[2], rg.delta[2], 0, rg.M[2], 32, xalign);
       bxs.bx = (bxs.bx + xalign - 1) / xalign * xalign;
-      int tzt = (TZ == 64 && !(x2 && x2mode >= 2)) ? 32 : TZ;
+      // (64 planes per CTA -- half the prologues and box waits, an 82 KB box -- measured slower than 32: 0.172 vs 0.166 ms)
+      const int tzt = (TZ == 64) ? 32 : TZ;
       bxs.bz = resize_axis_extent(rg.g.S[0], rg.M[0], rg.delta[0], out_z0, out_n0, tzt, 1);
-      if (tzt == 64 && (size_t)bxs.bz * bxs.by * bxs.bx * C * 4 > box_budget) {       // 64 planes do not fit: 32
-        tzt = 32;
-        bxs.bz = resize_axis_extent(rg.g.S[0], rg.M[0], rg.delta[0], out_z0, out_n0, tzt, 1);
-      }
       const size_t box_bytes = (size_t)bxs.bz * bxs.by * bxs.bx * C * 4;
       const int ntz3 = (out_n0 + tzt - 1) / tzt, nty3 = (rg.M[1] + tyt - 1) / tyt, ntx3 = (rg.M[2] + 31) / 32;
       const int64_t grid3 = (int64_t)B * ntz3 * nty3 * ntx3;
@@ -1759,25 +1606,14 @@ int nrt_resize_f32(const float* vol, float* out, int B, const int32_t* in_shape,
         uint32_t nzb, oneb;
         memcpy(&nzb, &nzf, 4); memcpy(&oneb, &onef, 4);
         const f32x2 negzero2 = ((f32x2)nzb << 32) | nzb, one2 = ((f32x2)oneb << 32) | oneb;
-        const bool minb3 = env_int("NRT_RESIZE_MINB", 1) == 3;        // registers capped for 3 CTAs per SM (experiment)
 #define NRT_RESIZE_TILE(CT, TZZ)                                                                                          \
         do {                                                                                                              \
-          if (x2 && x2mode >= 2) {                                                                                 \
+          if (x2) {                                                                                                       \
             auto kern = resize3d_pair_kernel<CT, TZZ>;                                                                    \
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)        \
               return check_launch("cudaFuncSetAttribute(resize3d_pair)");                                                 \
             kern<<<(int)grid3, 256, smem, st>>>(tmv, vol, out, rg, bxs, ntz3, nty3, ntx3, xalign, negzero2, one2,         \
                                                 unstaged);                                                                \
-          } else if (x2 && minb3) {                                                                                       \
-            auto kern = resize3d_tile_x2_kernel<CT, TZZ, 3>;                                                              \
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)        \
-              return check_launch("cudaFuncSetAttribute(resize3d_tile_x2)");                                              \
-            kern<<<(int)grid3, 256, smem, st>>>(tmv, vol, out, rg, bxs, ntz3, nty3, ntx3, xalign, negzero2, one2);        \
-          } else if (x2) {                                                                                                \
-            auto kern = resize3d_tile_x2_kernel<CT, TZZ>;                                                                 \
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)        \
-              return check_launch("cudaFuncSetAttribute(resize3d_tile_x2)");                                              \
-            kern<<<(int)grid3, 256, smem, st>>>(tmv, vol, out, rg, bxs, ntz3, nty3, ntx3, xalign, negzero2, one2);        \
           } else {                                                                                                        \
             auto kern = resize3d_tile_kernel<CT, TZZ>;                                                                    \
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)        \
@@ -1786,15 +1622,7 @@ int nrt_resize_f32(const float* vol, float* out, int B, const int32_t* in_shape,
           }                                                                                                               \
         } while (0)
 #define NRT_RESIZE_TILE_C(CT)                                                                                             \
-        do {                                                                                                              \
-          if (tzt == 64) {                                                                                                \
-            auto kern = resize3d_pair_kernel<CT, 64>;                                                                     \
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)        \
-              return check_launch("cudaFuncSetAttribute(resize3d_pair)");                                                 \
-            kern<<<(int)grid3, 256, smem, st>>>(tmv, vol, out, rg, bxs, ntz3, nty3, ntx3, xalign, negzero2, one2,         \
-                                                unstaged);                                                                \
-          } else if (tzt == 8) NRT_RESIZE_TILE(CT, 8); else if (tzt == 16) NRT_RESIZE_TILE(CT, 16); else NRT_RESIZE_TILE(CT, 32);       \
-        } while (0)
+        do { if (tzt == 8) NRT_RESIZE_TILE(CT, 8); else if (tzt == 16) NRT_RESIZE_TILE(CT, 16); else NRT_RESIZE_TILE(CT, 32); } while (0)
         switch (C) {
           case 1: NRT_RESIZE_TILE_C(1); break;
           case 2: NRT_RESIZE_TILE_C(2); break;

@@ -69,8 +69,6 @@ __device__ __forceinline__ int64_t patch_origin(const LcGeo& g, int64_t p) {
 // ---------------------------------------------------------------------------------------
 constexpr int kLcMaxWarps = 7;              // consumer groups (<= ring slots - 1) + 1 producer warp
 constexpr int kLcMaxStages = 8;
-constexpr int kLcB8Default = 142;           // NRT_LC3D_B8 / NRT_LC3D_B4 defaults (see nrt_lc3d_fwd_f32)
-constexpr int kLcB4Default = 22;
 
 // P2: the 4 x BB accumulators are updated with packed fma.rn.f32x2 (two fused multiply-adds per issue slot on
 // sm_100): the weight pairs are the halves of the LDS.128 result, the input value is broadcast to both halves.
@@ -384,7 +382,7 @@ template <int BB, int WPP>
 __global__ void __launch_bounds__((kLcMaxWarps * WPP + 1) * 32, 1)
 lc3d_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ kernel,
                  const float* __restrict__ bias, float* __restrict__ out, LcGeo g, int b_base, int stages) {
-  static_assert(BB == 4 || BB == 8, "the fold is written for 4 or 8 batch items per warp");
+  static_assert(BB == 4 || BB == 8, "the fold is written for 4 or 8 batch items per warp (8: measured slower, not built)");
   constexpr int NB = BB * WPP;
   constexpr int CO = 16;                                 // output channels (host checks g.Cout == 16)
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -732,26 +730,16 @@ extern "C" int nrt_lc3d_fwd_f32(const float* x, const float* kernel, const float
         // batch > 1: the position's input patch arrives by TMA next to its weight block (lc3d_patch_kernel)
         int prc;
         if (left >= 8) {
-          // NRT_LC3D_B8: 142 / 181 = row kernel (lanes own patch rows and all 16 channels), two warps x four items /
-          // one warp x eight items per position; 24 / 42 = patch kernel (lanes own an output quad), <2,4> / <4,2>
-          const int mode = env_int("NRT_LC3D_B8", kLcB8Default);
-          prc = 1;
-          if (mode == 142) prc = launch_rows<4, 2>(x, kernel, bias, out, g, b, st);
-          else if (mode == 181) prc = launch_rows<8, 1>(x, kernel, bias, out, g, b, st);
-          if (prc == 1)
-            prc = mode == 42 ? launch_patch<4, 2>(x, kernel, bias, out, g, b, cq_log2, st)
-                             : launch_patch<2, 4>(x, kernel, bias, out, g, b, cq_log2, st);
+          // row kernel (lanes own patch rows and all 16 channels; two warps x four items per position), else -- other
+          // channel counts, NRT_LC3D_ROWS=0 -- the patch kernel (lanes own an output quad; four warps x two items)
+          prc = env_int("NRT_LC3D_ROWS", 1) ? launch_rows<4, 2>(x, kernel, bias, out, g, b, st) : 1;
+          if (prc == 1) prc = launch_patch<2, 4>(x, kernel, bias, out, g, b, cq_log2, st);
           if (prc <= 0) { rc = prc; b += 8; continue; }
         }
-        else if (left >= 4) {
-          prc = env_int("NRT_LC3D_B4", kLcB4Default) == 141 ? launch_rows<4, 1>(x, kernel, bias, out, g, b, st) : 1;
-          if (prc == 1) prc = launch_patch<2, 2>(x, kernel, bias, out, g, b, cq_log2, st);
-          if (prc <= 0) { rc = prc; b += 4; continue; }
-        }
+        else if (left >= 4) { prc = launch_patch<2, 2>(x, kernel, bias, out, g, b, cq_log2, st); if (prc <= 0) { rc = prc; b += 4; continue; } }
         else {
-          // two batch items: <2,1> = one warp per position doing both, <1,2> = two warps per position, one item each
-          prc = env_int("NRT_LC3D_B2", 12) == 21 ? launch_patch<2, 1>(x, kernel, bias, out, g, b, cq_log2, st)
-                                                  : launch_patch<1, 2>(x, kernel, bias, out, g, b, cq_log2, st);
+          // two batch items: two warps per position, one item each (one warp doing both measured slower)
+          prc = launch_patch<1, 2>(x, kernel, bias, out, g, b, cq_log2, st);
           if (prc <= 0) { rc = prc; b += 2; continue; }
         }
       }

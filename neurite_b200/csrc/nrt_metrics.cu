@@ -241,7 +241,6 @@ argmax_kernel(const float* __restrict__ x, int64_t n, int L, int32_t* __restrict
 // ---------------------------------------------------------------------------------------
 // categorical cross-entropy
 // ---------------------------------------------------------------------------------------
-constexpr int kCceUnrollDefault = 4;       // NRT_CCE_UNROLL default (see nrt_cce_f32)
 struct CceArgs {
   const float* label_w;
   const float* sample_w;
@@ -252,74 +251,11 @@ struct CceArgs {
   float smoothing;
 };
 
-__device__ __forceinline__ float group_sum(float v, int q) {
-  for (int o = q >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ float group_max(float v, int q) {
-  for (int o = q >> 1; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-
-// q = C/4 lanes per row (q a power of two <= 32): perfectly coalesced float4 streams
-__global__ void __launch_bounds__(kThreads)
-cce_vec4_kernel(const float4* __restrict__ t4, const float4* __restrict__ p4, CceArgs a, int q,
-                float* __restrict__ partial) {
-  __shared__ float s_red[kThreads / 32];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int sub = lane & (q - 1);
-  const int rows_per_pass = kThreads / q;
-  float4 lw = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (a.label_w) lw = __ldg(reinterpret_cast<const float4*>(a.label_w) + sub);
-  const float eps = 1e-7f, one_m_eps = __fsub_rn(1.0f, 1e-7f);
-  const float sm_keep = __fsub_rn(1.0f, a.smoothing), sm_add = __fdiv_rn(a.smoothing, (float)a.C);
-  float acc = 0.f;
-  // block-uniform trip count: the group shuffles below need every lane of the warp present
-  for (int64_t r0 = (int64_t)blockIdx.x * rows_per_pass; r0 < a.n; r0 += (int64_t)gridDim.x * rows_per_pass) {
-    const int64_t r = r0 + tid / q;
-    const bool valid = r < a.n;
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f), p = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (valid) { t = ld_stream_f4(t4 + r * q + sub); p = ld_stream_f4(p4 + r * q + sub); }
-    t.x *= lw.x; t.y *= lw.y; t.z *= lw.z; t.w *= lw.w;                       // metrics.py:648
-    if (a.smoothing != 0.f) {
-      t.x = t.x * sm_keep + sm_add; t.y = t.y * sm_keep + sm_add; t.z = t.z * sm_keep + sm_add; t.w = t.w * sm_keep + sm_add;
-    }
-    float l;
-    if (!a.from_logits) {
-      // HBM-bound only if the per-element math stays short: one reciprocal per voxel instead
-      // of C divisions, and the SFU logarithm (__logf: abs err <= 2^-21.4 on [0.5,2], <= 3 ulp
-      // elsewhere) -- both far inside the 1e-5 relative tolerance of the reduced loss.
-      const float rs = __frcp_rn(group_sum((p.x + p.y) + (p.z + p.w), q));
-      const float a0 = fminf(fmaxf(p.x * rs, eps), one_m_eps), a1 = fminf(fmaxf(p.y * rs, eps), one_m_eps);
-      const float a2 = fminf(fmaxf(p.z * rs, eps), one_m_eps), a3 = fminf(fmaxf(p.w * rs, eps), one_m_eps);
-      l = (t.x * __logf(a0) + t.y * __logf(a1)) + (t.z * __logf(a2) + t.w * __logf(a3));
-    } else {
-      const float m = group_max(fmaxf(fmaxf(p.x, p.y), fmaxf(p.z, p.w)), q);
-      const float z0 = p.x - m, z1 = p.y - m, z2 = p.z - m, z3 = p.w - m;
-      const float lse = logf(group_sum((expf(z0) + expf(z1)) + (expf(z2) + expf(z3)), q));
-      l = (t.x * (z0 - lse) + t.y * (z1 - lse)) + (t.z * (z2 - lse) + t.w * (z3 - lse));
-    }
-    l = -group_sum(l, q);
-    if (sub == 0 && valid) {
-      if (a.sample_w) l *= __ldg(a.sample_w + r);
-      if (a.per_elem) a.per_elem[r] = l;
-      acc += l;
-    }
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) s_red[tid >> 5] = acc;
-  __syncthreads();
-  if (tid == 0) {
-    float s = 0.f;
-    for (int i = 0; i < kThreads / 32; ++i) s += s_red[i];
-    partial[blockIdx.x] = s;
-  }
-}
-
-// The same with Q = C/4 lanes per row at compile time (the group shuffles unroll: no loop counters, no branches) and
-// U rows per thread and pass, i.e. U independent pairs of streaming loads in flight per thread.  cce_vec4_kernel
-// (profiles/r02_ncu_full_cce.txt) runs one load pair per thread and waits 8.6 long-scoreboard cycles per issue at 74 %
-// issue-active with half of its instructions on the ALU pipe (the run-time shuffle loops).
+// Q = C/4 lanes per row (a power of two <= 32, compile time: the group shuffles unroll, no loop counters, no branches):
+// perfectly coalesced float4 streams; U rows per thread and pass, i.e. U independent pairs of streaming loads in flight
+// per thread.  The first version (profiles/r02_ncu_full_cce.txt) took q at run time and ran one load pair per thread:
+// 8.6 long-scoreboard stall cycles per issue at 74 % issue-active with half of its instructions on the ALU pipe, 0.84 of
+// the HBM roofline; two rows per thread 0.90, four 1.00 (profiles/r02_ncu_full_cce_u4.txt).
 template <int Q>
 __device__ __forceinline__ float group_sum_c(float v) {
 #pragma unroll
@@ -573,33 +509,20 @@ int nrt_cce_f32(const float* y_true, const float* y_pred, const float* label_w, 
     cudaMemsetAsync(sum_out, 0, sizeof(float), st);
     return check_launch("cce memset");
   }
-  // NRT_CCE_UNROLL: rows per thread and pass in the compile-time-Q kernel (default 2; 0 = the run-time-q kernel)
-  const char* ue = getenv("NRT_CCE_UNROLL");
-  const int unroll = ue && *ue ? atoi(ue) : kCceUnrollDefault;
-  if (vec_ok && (unroll == 2 || unroll == 4)) {
-    const int rows_per_pass = kThreads / q * unroll;
+  if (vec_ok) {
+    constexpr int kU = 4;                                // rows per thread and pass
+    const int rows_per_pass = kThreads / q * kU;
     grid = (int)imin64((n + rows_per_pass - 1) / rows_per_pass, (int64_t)min(kMaxBlocks * 4, sm_count() * 8));
     const float4* t4 = reinterpret_cast<const float4*>(y_true);
     const float4* p4 = reinterpret_cast<const float4*>(y_pred);
-#define NRT_CCE_Q(QQ)                                                                                   \
-    do {                                                                                                \
-      if (unroll == 2) cce_vec4u_kernel<QQ, 2><<<grid, kThreads, 0, st>>>(t4, p4, a, partial);          \
-      else cce_vec4u_kernel<QQ, 4><<<grid, kThreads, 0, st>>>(t4, p4, a, partial);                      \
-    } while (0)
     switch (q) {
-      case 1: NRT_CCE_Q(1); break;
-      case 2: NRT_CCE_Q(2); break;
-      case 4: NRT_CCE_Q(4); break;
-      case 8: NRT_CCE_Q(8); break;
-      case 16: NRT_CCE_Q(16); break;
-      default: NRT_CCE_Q(32); break;
+      case 1: cce_vec4u_kernel<1, kU><<<grid, kThreads, 0, st>>>(t4, p4, a, partial); break;
+      case 2: cce_vec4u_kernel<2, kU><<<grid, kThreads, 0, st>>>(t4, p4, a, partial); break;
+      case 4: cce_vec4u_kernel<4, kU><<<grid, kThreads, 0, st>>>(t4, p4, a, partial); break;
+      case 8: cce_vec4u_kernel<8, kU><<<grid, kThreads, 0, st>>>(t4, p4, a, partial); break;
+      case 16: cce_vec4u_kernel<16, kU><<<grid, kThreads, 0, st>>>(t4, p4, a, partial); break;
+      default: cce_vec4u_kernel<32, kU><<<grid, kThreads, 0, st>>>(t4, p4, a, partial); break;
     }
-#undef NRT_CCE_Q
-  } else if (vec_ok) {
-    const int rows_per_pass = kThreads / q;
-    grid = (int)imin64((n + rows_per_pass - 1) / rows_per_pass, (int64_t)min(kMaxBlocks * 4, sm_count() * 8));
-    cce_vec4_kernel<<<grid, kThreads, 0, st>>>(reinterpret_cast<const float4*>(y_true),
-                                               reinterpret_cast<const float4*>(y_pred), a, q, partial);
   } else {
     grid = (int)imin64((n + kThreads - 1) / kThreads, (int64_t)min(kMaxBlocks * 4, sm_count() * 8));
     cce_row_kernel<<<grid, kThreads, 0, st>>>(y_true, y_pred, a, partial);

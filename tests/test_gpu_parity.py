@@ -303,11 +303,9 @@ def test_cce_golden(ne, name):
     np.testing.assert_allclose(float(c.loss(dev(g['y_true']), dev(g['y_pred']))), g['loss'], rtol=1e-5)
 
 
-@pytest.mark.parametrize('unroll', ['0', '2', '4'])
-def test_cce_variants_vs_oracle(ne, monkeypatch, unroll):
-    """run-time-q kernel (0) and the compile-time-Q kernels with 2 / 4 rows per thread; 2 x 37 x 41 rows: ragged
-    last pass of every variant"""
-    monkeypatch.setenv('NRT_CCE_UNROLL', unroll)
+def test_cce_variants_vs_oracle(ne):
+    """every lanes-per-row instantiation (C = 4 .. 128), the row kernel (C = 2, 3, 5); 2 x 37 x 41 rows: a ragged
+    last pass of the four-rows-per-thread loop"""
     rng = np.random.default_rng(11)
     for C in (2, 3, 4, 5, 8, 16, 32, 64, 128):
         t = np.eye(C, dtype=F32)[rng.integers(0, C, (2, 37, 41) if C in (4, 16) else (2, 6, 7))]
@@ -371,8 +369,7 @@ def test_lc3d_vs_oracle_batches_activations_and_sharding(ne, monkeypatch, ffma2,
         np.testing.assert_allclose(out, ref, rtol=1e-5, atol=2e-5)
     if ffma2 == '1':
         # (the quad-per-lane kernels share one summation order; the row kernels are compared in their own test)
-        monkeypatch.setenv('NRT_LC3D_B8', '24')
-        monkeypatch.setenv('NRT_LC3D_B4', '22')
+        monkeypatch.setenv('NRT_LC3D_ROWS', '0')
         out = local_conv3d(dev(x), dev(kernel), dev(bias), (3, 3, 3), (1, 1, 1), O, activation='sigmoid').cpu().numpy()
         monkeypatch.setenv('NRT_LC3D_FFMA2', '0')
         monkeypatch.setenv('NRT_LC3D_PATCH', '0')
@@ -396,14 +393,13 @@ def test_lc3d_vs_oracle_batches_activations_and_sharding(ne, monkeypatch, ffma2,
     np.testing.assert_allclose(torch.cat([a, b], 1).cpu().numpy(), ref, rtol=1e-5, atol=2e-5)
 
 
-@pytest.mark.parametrize('b8,b4', [('142', '141'), ('181', '22'), ('24', '22')])
-def test_lc3d_row_kernels_vs_oracle(ne, monkeypatch, b8, b4):
-    """batch 13 = passes of 8 + 4 + 1 items through the row kernels (lanes own patch rows and all 16 channels: two
-    warps x four items, one warp x eight items, one warp x four items) against the oracle and against the
-    quad-per-lane kernels; bias, activations, a ragged patch (F = 20 < 32 rows), F = 48, strides 2, position shards"""
+@pytest.mark.parametrize('rows', ['1', '0'])
+def test_lc3d_row_kernel_vs_oracle(ne, monkeypatch, rows):
+    """batch 13 = passes of 8 + 4 + 1 items: the pass of 8 through the row kernel (lanes own patch rows and all 16
+    channels, two warps x four items per position) or the quad-per-lane patch kernel, against the oracle; bias,
+    activations, a ragged patch (F = 20 < 32 rows), F = 48, strides 2, position shards"""
     from neurite_b200.layers import local_conv3d
-    monkeypatch.setenv('NRT_LC3D_B8', b8)
-    monkeypatch.setenv('NRT_LC3D_B4', b4)
+    monkeypatch.setenv('NRT_LC3D_ROWS', rows)
     rng = np.random.default_rng(113)
     x = rng.standard_normal((13, 8, 9, 10, 16)).astype(F32)
     O = (6, 7, 8)
@@ -432,11 +428,11 @@ def test_lc3d_row_kernels_vs_oracle(ne, monkeypatch, b8, b4):
     np.testing.assert_allclose(torch.cat([a, b], 1).cpu().numpy(), ref, rtol=1e-5, atol=2e-5)
 
 
-@pytest.mark.parametrize('b8', ['24', '142', '181'])
-def test_lc3d_batch8_shared_weights_equal_conv3d(ne, monkeypatch, b8):
+@pytest.mark.parametrize('rows', ['1', '0'])
+def test_lc3d_batch8_shared_weights_equal_conv3d(ne, monkeypatch, rows):
     """cfg 4 geometry, batch 8, many positions per CTA (22^3 positions over 148 CTAs: every ring slot is reused many
     times): with position-shared weights the layer must equal a plain conv3d"""
-    monkeypatch.setenv('NRT_LC3D_B8', b8)
+    monkeypatch.setenv('NRT_LC3D_ROWS', rows)
     rng = np.random.default_rng(19)
     x = torch.from_numpy(rng.standard_normal((8, 24, 24, 24, 16)).astype(F32)).cuda()
     w = torch.from_numpy((rng.standard_normal((3, 3, 3, 16, 16)) * 0.1).astype(F32)).cuda()
@@ -518,8 +514,8 @@ def test_vxm_adjacent_transforms_vs_oracle(ne):
                                           ((33, 18, 20), 4, [0.5, 1.3, 2.1])])
 def test_resize_upsampling_vs_oracle(ne, monkeypatch, shape, C, zoom):
     """up-sampling (and mixed) shapes through the TMA-staged tile kernels (voxel-pair kernel: default, even and odd
-    output widths, and its global-memory path; the first packed kernel; one voxel per thread), the one-voxel
-    z-marching kernel (global loads) and the generic kernel: -0.0 / rounding identical"""
+    output widths, and its global-memory path; one voxel per thread), the one-voxel z-marching kernel (global loads)
+    and the generic kernel: -0.0 / rounding identical"""
     rng = np.random.default_rng(51)
     x = rng.standard_normal((2,) + shape + (C,)).astype(F32)
     x[0, 0, 0, :2] = 0.0                                     # exact zeros: the packed a*b = fma(a, b, -0) must keep their sign
@@ -533,10 +529,6 @@ def test_resize_upsampling_vs_oracle(ne, monkeypatch, shape, C, zoom):
     np.testing.assert_array_equal(out, ref)
     np.testing.assert_array_equal(np.signbit(out), np.signbit(ref))
     monkeypatch.delenv('NRT_RESIZE_UNSTAGED')
-    monkeypatch.setenv('NRT_RESIZE_TILE_X2', '1')             # -> the first packed kernel (generic loads, lo/hi copies)
-    out = ne.layers.Resize(zoom)(dev(x)).cpu().numpy()
-    np.testing.assert_array_equal(out, ref)
-    np.testing.assert_array_equal(np.signbit(out), np.signbit(ref))
     monkeypatch.setenv('NRT_RESIZE_TILE_X2', '0')             # -> staged source, one voxel per thread
     np.testing.assert_array_equal(ne.layers.Resize(zoom)(dev(x)).cpu().numpy(), ref)
     monkeypatch.setenv('NRT_RESIZE_TILE', '0')                # -> one-voxel z-marching kernel (global loads)

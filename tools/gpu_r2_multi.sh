@@ -1,10 +1,7 @@
 #!/bin/bash
-# round 2, multi-GPU visit: peer-memory transport of the slab plan (N = $1), plus the resize tile-x2 kernel on one GPU
+# round 2, multi-GPU visit: peer-memory transport of the slab plan (N = $1)
 N=${1:-2}
 mkdir -p gpurun_out
-( timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 300 -k "resize" 2>&1 | tail -5 ) > gpurun_out/r2m_pytest_resize.log 2>&1; tail -2 gpurun_out/r2m_pytest_resize.log
-for v in "NRT_RESIZE_TILE_X2=1" "NRT_RESIZE_TILE_X2=0" "NRT_RESIZE_TILE_X2=1 NRT_RESIZE_TZ=16"; do ( env $v timeout 200 python bench.py --op resize --no-cpu-baseline ) > gpurun_out/r2m_tmp.json 2>> gpurun_out/r2m.err; python -c "
-import json; d=json.loads(open('gpurun_out/r2m_tmp.json').read().strip().splitlines()[-1]); print('resize $v', d['ms_per_step'], d['roofline']['frac'])"; done
 ( timeout 900 python -m pytest tests/test_multi_gpu.py -q --timeout 600 -m gpu 2>&1 | tail -15 ) > gpurun_out/r2m${N}_pytest_multi.log 2>&1; tail -4 gpurun_out/r2m${N}_pytest_multi.log
 run() {
   ( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 300)) bench.py --gpus $N $2 ) > gpurun_out/r2m${N}_$1.json 2>> gpurun_out/r2m${N}.err

@@ -14,8 +14,8 @@ prof() {  # name, kernel regex, bench args
 prof warp warp3d_tile "--e2e-steps 1"
 prof warp_c16 warp3d_march "--op warp_mc --channels 16"
 prof resize resize3d "--op resize"
-prof lc3d lc3d_stream "--op lc3d"
-prof lc3d_b8 lc3d_patch "--op lc3d --lc-batch 8"
+prof lc3d lc3d_patch "--op lc3d"
+prof lc3d_b8 lc3d_rows "--op lc3d --lc-batch 8"
 prof dice dice_sums "--op dice"
 prof cce cce_vec4 "--op cce"
 for op in "warp_mc --channels 16 --flow smooth" "warp_mc --channels 3" "warp_mc --channels 4" "lc3d --lc-batch 8" "lc3d --lc-batch 2" "mi" "blur" "resize"; do
