@@ -371,22 +371,16 @@ int warp3d_march(const float* vol, const float* flow, float* out, int B, const i
 #define NRT_MARCH_Q(cch, ty, tx, ahead, nw, qq)                                                                \
   rc = method == NRT_LINEAR ? launch_march<cch, ty, tx, 3, ahead, nw, NRT_LINEAR, qq>(vol, flow, out, mg, st)  \
                             : launch_march<cch, ty, tx, 3, ahead, nw, NRT_NEAREST, qq>(vol, flow, out, mg, st)
-#define NRT_MARCH_G(cch, ty, tx, ahead, nw, qq, gg)                                                                 \
-  rc = method == NRT_LINEAR ? launch_march<cch, ty, tx, 3, ahead, nw, NRT_LINEAR, qq, gg>(vol, flow, out, mg, st)  \
-                            : launch_march<cch, ty, tx, 3, ahead, nw, NRT_NEAREST, qq, gg>(vol, flow, out, mg, st)
-  // measured on B200 (profiles/README.md): two plane groups = 16 consumer warps change nothing (C = 16 i.i.d. 0.584 vs
-  // 0.573, smooth 0.627 vs 0.633): the kernel is not short of warps; one group (ring 7 + 3) stays the default
-  const int groups = env_int("NRT_MARCH_GROUPS", 1);
+  // (two output planes in flight per CTA -- template parameter G = 2: 16 consumer warps with two quads per thread, ring
+  // 7 + 1 + 2 -- measured the same as one, C = 16 i.i.d. 0.584 vs 0.573, smooth 0.627 vs 0.633: the kernel is not short
+  // of warps.  Not instantiated.)
   if (C % 16 == 0) {
-    // QPT 2 / 4: a thread owns 8 / 16 channels of its voxel and shares the corner setup between them; with two quads
-    // per thread a plane needs 8 warps, so two output planes are in flight (16 consumer warps, ring = 7 + 1 + 2)
+    // QPT 2 / 4: a thread owns 8 / 16 channels of its voxel and shares the corner setup between them
     if (qpt == 4) NRT_MARCH_Q(16, 8, 16, 3, 4, 4);
-    else if (qpt == 2 && groups == 2) NRT_MARCH_G(16, 8, 16, 2, 16, 2, 2);
     else if (qpt == 2) NRT_MARCH_Q(16, 8, 16, 3, 8, 2);
     else if (nw16 == 8) NRT_MARCH(16, 8, 16, 3, 8); else NRT_MARCH(16, 8, 16, 3, 16);
   } else if (C % 8 == 0) {
-    if (qpt >= 2 && groups == 2) NRT_MARCH_G(8, 8, 32, 2, 16, 2, 2);
-    else if (qpt >= 2) NRT_MARCH_Q(8, 8, 32, 3, 8, 2);
+    if (qpt >= 2) NRT_MARCH_Q(8, 8, 32, 3, 8, 2);
     else if (nw16 == 8) NRT_MARCH(8, 8, 32, 3, 8); else NRT_MARCH(8, 8, 32, 3, 16);
   } else if (C % 4 == 0) {
     if (nw16 == 8) NRT_MARCH(4, 16, 32, 3, 8); else NRT_MARCH(4, 16, 32, 3, 16);
@@ -396,7 +390,6 @@ int warp3d_march(const float* vol, const float* flow, float* out, int B, const i
     NRT_MARCH(2, 16, 32, 3, 16);
   }
 #undef NRT_MARCH_Q
-#undef NRT_MARCH_G
 #undef NRT_MARCH
   if (rc == 1) return NRT_OK;
   *used = true;

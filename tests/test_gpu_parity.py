@@ -101,8 +101,8 @@ def test_warp_tile_configs_bit_exact(ne, monkeypatch, cfg, shape, amp, halo, met
 @pytest.mark.parametrize('shape,amp', [((20, 24, 32), 3.0), ((11, 13, 52), 6.0), ((40, 18, 100), 2.5)])
 def test_warp_march_kernel_multichannel_bit_exact(ne, monkeypatch, C, shape, amp):
     """z-marching ring kernel (nrt_warp_march.cu): every channel count it is built for, ragged tiles, flows
-    inside and far outside the staged window, one / two / four quads per thread, one and two plane groups, forced z
-    segmentations (down to one output plane per segment: a plane group without work)."""
+    inside and far outside the staged window, one / two / four quads per thread, forced z segmentations (down to one
+    output plane per segment)."""
     monkeypatch.setenv('NRT_MARCH_SMALLC', '1')
     rng = np.random.default_rng(C * 100 + shape[0])
     vol = rng.standard_normal((2,) + shape + (C,)).astype(F32)
@@ -115,9 +115,9 @@ def test_warp_march_kernel_multichannel_bit_exact(ne, monkeypatch, C, shape, amp
     for method, fill in (('linear', None), ('linear', -1.5), ('nearest', 0.0)):
         ref = ointerp.spatial_transformer(vol, flow, method, 'ij', fill)
         lay = ne.layers.SpatialTransformer(interp_method=method, fill_value=fill)
-        for env in ({}, {'NRT_MARCH_NW': '8', 'NRT_MARCH_QPT': '1'}, {'NRT_MARCH_NSEG': '3'}, {'NRT_MARCH_GROUPS': '2'},
+        for env in ({}, {'NRT_MARCH_NW': '8', 'NRT_MARCH_QPT': '1'}, {'NRT_MARCH_NSEG': '3'},
                     {'NRT_MARCH_QPT': '4'}, {'NRT_MARCH_NSEG': '40'}):
-            for k in ('NRT_MARCH_NW', 'NRT_MARCH_NSEG', 'NRT_MARCH_QPT', 'NRT_MARCH_GROUPS'):
+            for k in ('NRT_MARCH_NW', 'NRT_MARCH_NSEG', 'NRT_MARCH_QPT'):
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
